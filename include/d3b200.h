@@ -1,0 +1,148 @@
+/*
+ * d3b200 -- C ABI of the B200-native DFT-D3 hot path (libd3b200.so).
+ *
+ * This is the drop-in boundary for tad-dftd3's pairwise / three-body path.
+ * The reference has no FFI of its own (it is pure PyTorch); the boundary it
+ * offers is the Python call surface
+ *
+ *     tad_dftd3.dftd3(numbers, positions, param, *, ref, rcov, rvdw, r4r2,
+ *                     cutoff, ...)                      src/tad_dftd3/disp.py:79-165
+ *
+ * whose body (disp.py:150-165: cn_d3 -> weight_references -> atomic_c6 ->
+ * dispersion) is what the entry points below replace.  The host side that
+ * calls them is `tad_dftd3_b200/ops.py` (ctypes + torch.autograd.Function,
+ * mirroring the reference's only custom op, model/c6.py:401-480).
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless said otherwise; the library never
+ *    allocates, never synchronises, keeps no mutable global state and launches
+ *    on the stream it is given (a `cudaStream_t` passed as `void*`);
+ *  - a padded batch is `numbers[nbatch][natoms]` (int64, 0 = padding or ghost
+ *    atom) and `positions[nbatch][natoms][3]`, row-major, as produced by
+ *    tad-mctc's `pack` and consumed by the reference; lengths in Bohr,
+ *    energies in Hartree;
+ *  - return value 0 = success, otherwise an error code; the message is
+ *    available (per host thread) from `d3b200_last_error()`;
+ *  - the `_f32` entry points take `float` arrays; scalar parameters are
+ *    always passed as host doubles.
+ */
+#ifndef D3B200_H
+#define D3B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3B200_ABI_VERSION 1
+#define D3B200_MAX_ELEMENT 104 /* reference defaults.py:72 */
+#define D3B200_NREF 7          /* reference systems per element, reference.py:32-161 */
+
+enum d3b200_status {
+  D3B200_OK = 0,
+  D3B200_EINVAL = 1,  /* bad argument (null pointer, size) */
+  D3B200_ESIZE = 2,   /* structure too large for this entry point */
+  D3B200_ECUDA = 3    /* CUDA runtime error, see d3b200_last_error() */
+};
+
+/* Damping parameters and cutoffs (host memory).
+ * s6,s8,a1,a2: rational damping, reference damping/rational.py:38-68 and
+ * disp.py:300-301; s9, rs9, alp: ATM term, disp.py:343-347, damping/atm.py;
+ * cutoff: dispersion cutoff (disp.py:137, default 50); cn_cutoff, kcn: the
+ * coordination number's own cutoff and steepness (tad-mctc defaults 25, 16). */
+typedef struct d3b200_params {
+  double s6, s8, a1, a2;
+  double s9, rs9, alp;
+  double cutoff, cn_cutoff, kcn;
+} d3b200_params;
+
+/* Model data and per-atom inputs shared by all batch entry points.
+ *  rcov, r4r2 : per atom `[nbatch][natoms]` (the reference's `rcov=`, `r4r2=`
+ *               keyword arrays, disp.py:141-148) or, with *_per_element != 0,
+ *               per element tables indexed by Z (length >= 104);
+ *  refcn      : `[104][7]`, -1 = reference absent      (reference.py:32-161)
+ *  refc6      : `[104][104][7][7]`                     (reference.py:164-187)
+ *               must be symmetric, K[z1][z2][a][b] == K[z2][z1][b][a];
+ *  rvdw       : ATM only. rvdw_mode 0: absent, 1: `[104][104]` element-pair
+ *               table, 2: dense `[nbatch][natoms][natoms]` (the reference's
+ *               `rvdw=` keyword, disp.py:143-146). */
+typedef struct d3b200_model_f64 {
+  const double* rcov;
+  const double* r4r2;
+  int rcov_per_element;
+  int r4r2_per_element;
+  const double* refcn;
+  const double* refc6;
+  const double* rvdw;
+  int rvdw_mode;
+} d3b200_model_f64;
+
+typedef struct d3b200_model_f32 {
+  const float* rcov;
+  const float* r4r2;
+  int rcov_per_element;
+  int r4r2_per_element;
+  const float* refcn;
+  const float* refc6;
+  const float* rvdw;
+  int rvdw_mode;
+} d3b200_model_f32;
+
+int d3b200_abi_version(void);
+const char* d3b200_last_error(void);
+
+/* Largest `natoms` the fused one-CTA-per-structure kernels accept
+ * (order: 0 = energy / vjp, 1 = second order). */
+int d3b200_batch_max_atoms_f64(int order);
+int d3b200_batch_max_atoms_f32(int order);
+
+/* Atom-resolved D3(BJ)[+ATM] energies of a padded batch.
+ * Replaces the body of `dftd3()`, reference disp.py:150-165 (+ disp.py:168-242).
+ *   energy : `[nbatch][natoms]`, exact zeros on padding.
+ * The ATM term is evaluated iff par->s9 != 0 (disp.py:234). */
+int d3b200_batch_energy_f64(int nbatch, int natoms, const int64_t* numbers,
+                            const double* positions, const d3b200_model_f64* model,
+                            const d3b200_params* par, double* energy, void* stream);
+int d3b200_batch_energy_f32(int nbatch, int natoms, const int64_t* numbers,
+                            const float* positions, const d3b200_model_f32* model,
+                            const d3b200_params* par, float* energy, void* stream);
+
+/* Vector-Jacobian product of the above: with L = sum_i g[i] * E[i],
+ *   grad  : dL/dpositions `[nbatch][natoms][3]`
+ *   pgrad : dL/d(s6, s8, a1, a2, s9) per structure `[nbatch][5]`, or NULL.
+ *   energy: optional `[nbatch][natoms]` (NULL to skip).
+ * Replaces torch autograd through disp.py:150-165 (the analytic backward that
+ * the reference only has for atomic_c6, model/c6.py:294-374). */
+int d3b200_batch_vjp_f64(int nbatch, int natoms, const int64_t* numbers,
+                         const double* positions, const d3b200_model_f64* model,
+                         const d3b200_params* par, const double* g, double* energy,
+                         double* grad, double* pgrad, void* stream);
+int d3b200_batch_vjp_f32(int nbatch, int natoms, const int64_t* numbers,
+                         const float* positions, const d3b200_model_f32* model,
+                         const d3b200_params* par, const float* g, float* energy,
+                         float* grad, float* pgrad, void* stream);
+
+/* Second order: directional derivative of (E, grad, pgrad) along the tangent
+ * (dpositions, dpar->{s6,s8,a1,a2,s9}).  Because grad = dL/dx, the tangent of
+ * grad is the Hessian-vector product of L; the tangent of E is the JVP of the
+ * energies.  This is the double-backward that `examples/hessian.py:84-94`
+ * (jacrev o jacrev) and `gradgradcheck` need.  dpar may be NULL (zero tangent);
+ * any output may be NULL. */
+int d3b200_batch_hvp_f64(int nbatch, int natoms, const int64_t* numbers,
+                         const double* positions, const double* dpositions,
+                         const d3b200_model_f64* model, const d3b200_params* par,
+                         const d3b200_params* dpar, const double* g, double* grad,
+                         double* pgrad, double* denergy, double* dgrad,
+                         double* dpgrad, void* stream);
+int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
+                         const float* positions, const float* dpositions,
+                         const d3b200_model_f32* model, const d3b200_params* par,
+                         const d3b200_params* dpar, const float* g, float* grad,
+                         float* pgrad, float* denergy, float* dgrad, float* dpgrad,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3B200_H */

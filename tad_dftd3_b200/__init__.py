@@ -1,0 +1,23 @@
+"""
+tad_dftd3_b200 -- B200-native DFT-D3 dispersion hot path.
+
+Drop-in for `tad_dftd3` (dftd3/tad-dftd3 v0.5.0) on CUDA devices:
+
+    import tad_dftd3_b200 as d3
+    energy = d3.dftd3(numbers, positions, param)      # atom-resolved, Hartree
+
+Same signature, padded-batch convention, `Reference` data holder and damping
+parameter dicts as the reference; the body runs as hand-written sm_100a CUDA
+kernels behind the C ABI in `include/d3b200.h`, with analytic first and second
+derivatives wired into torch autograd / torch.func.
+"""
+from . import damping, data, defaults, disp, model, ncoord, reference
+from .disp import dftd3
+from .reference import Reference
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "dftd3", "damping", "data", "defaults", "disp", "model", "ncoord", "reference",
+    "Reference", "__version__",
+]

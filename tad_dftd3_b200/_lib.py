@@ -1,0 +1,94 @@
+"""
+ctypes binding of `libd3b200.so` (the C ABI declared in `include/d3b200.h`).
+
+There is no CPU fallback: if the shared library is missing this module raises
+at first use and tells the caller how to build it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libd3b200.so")
+
+ABI_VERSION = 1
+
+
+class Params(C.Structure):
+    """`d3b200_params` (host memory)."""
+
+    _fields_ = [(k, C.c_double) for k in
+                ("s6", "s8", "a1", "a2", "s9", "rs9", "alp", "cutoff", "cn_cutoff", "kcn")]
+
+
+class Model(C.Structure):
+    """`d3b200_model_f64` / `_f32` (same layout: pointers + ints)."""
+
+    _fields_ = [
+        ("rcov", C.c_void_p),
+        ("r4r2", C.c_void_p),
+        ("rcov_per_element", C.c_int),
+        ("r4r2_per_element", C.c_int),
+        ("refcn", C.c_void_p),
+        ("refc6", C.c_void_p),
+        ("rvdw", C.c_void_p),
+        ("rvdw_mode", C.c_int),
+    ]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_SIGNATURES = {
+    "d3b200_abi_version": ([], C.c_int),
+    "d3b200_last_error": ([], C.c_char_p),
+    "d3b200_batch_max_atoms_f64": ([_I], C.c_int),
+    "d3b200_batch_max_atoms_f32": ([_I], C.c_int),
+}
+for _sfx in ("f64", "f32"):
+    _SIGNATURES[f"d3b200_batch_energy_{_sfx}"] = (
+        [_I, _I, _P, _P, C.POINTER(Model), C.POINTER(Params), _P, _P], C.c_int)
+    _SIGNATURES[f"d3b200_batch_vjp_{_sfx}"] = (
+        [_I, _I, _P, _P, C.POINTER(Model), C.POINTER(Params), _P, _P, _P, _P, _P], C.c_int)
+    _SIGNATURES[f"d3b200_batch_hvp_{_sfx}"] = (
+        [_I, _I, _P, _P, _P, C.POINTER(Model), C.POINTER(Params), C.POINTER(Params),
+         _P, _P, _P, _P, _P, _P, _P], C.c_int)
+
+_lib = None
+
+
+class D3LibraryError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    """Names that `include/d3b200.h` declares (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise D3LibraryError(
+                f"{LIB_PATH} is missing. tad_dftd3_b200 has no CPU or eager "
+                "fallback; build the CUDA library with "
+                "`python -m tad_dftd3_b200.build` (needs nvcc, sm_100a)."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so is stale
+            fn.argtypes = argtypes
+            fn.restype = restype
+        if handle.d3b200_abi_version() != ABI_VERSION:
+            raise D3LibraryError("libd3b200.so ABI version mismatch; rebuild it")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().d3b200_last_error().decode()
+        if rc == 2:
+            raise ValueError(msg)
+        raise D3LibraryError(f"libd3b200 error {rc}: {msg}")

@@ -1,0 +1,73 @@
+"""
+Build `libd3b200.so` in-tree with nvcc for sm_100a.
+
+    python -m tad_dftd3_b200.build [--force]
+
+The shared library is a plain C-ABI library (no torch, no Python headers):
+`include/d3b200.h` declares its entry points.  It is git-ignored but travels
+to the GPU box with the working tree.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libd3b200.so")
+STAMP = os.path.join(HERE, ".libd3b200.stamp")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--use_fast_math=false" if False else "-Xptxas=-v",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def sources():
+    return sorted(
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))
+    ) + [os.path.join(os.path.dirname(HERE), "include", "d3b200.h")]
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in sources():
+        h.update(f.encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(exe):
+        raise RuntimeError("nvcc not found; libd3b200.so cannot be built")
+    return exe
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    digest = _digest()
+    if not force and os.path.isfile(LIB) and os.path.isfile(STAMP):
+        if open(STAMP).read().strip() == digest:
+            return LIB
+    cus = [f for f in sources() if f.endswith(".cu")]
+    cmd = [nvcc(), *NVCC_FLAGS, "-o", LIB, *cus]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libd3b200.so")
+    with open(os.path.join(HERE, "ptxas_info.log"), "w") as fh:
+        fh.write(res.stderr)
+    with open(STAMP, "w") as fh:
+        fh.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,219 @@
+// C ABI of libd3b200.so (declared in include/d3b200.h).
+// Argument checking, launch configuration and template dispatch only; all
+// arithmetic lives in the kernel headers.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/d3b200.h"
+#include "d3_molecule.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", long b = 0, long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "CUDA error in %s: %s", where, cudaGetErrorString(e));
+  return D3B200_ECUDA;
+}
+
+constexpr size_t kSmemLimit = 227 * 1024;
+
+template <typename S>
+int max_atoms() {
+  int n = 4096;
+  while (n > 32 && d3::molecule_smem_bytes<S>(n) > kSmemLimit) n -= 32;
+  return n;
+}
+
+template <typename B>
+struct ModelOf;
+template <> struct ModelOf<double> { using type = d3b200_model_f64; };
+template <> struct ModelOf<float> { using type = d3b200_model_f32; };
+
+template <typename S, int FLAGS>
+int launch(const d3::MolArgs<S>& args, cudaStream_t stream) {
+  const int N = args.natoms;
+  const int threads = N >= d3::kMolThreads ? d3::kMolThreads : ((N + 31) / 32) * 32;
+  const size_t smem = d3::molecule_smem_bytes<S>(N);
+  auto kern = d3::molecule_kernel<S, FLAGS>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  }
+  kern<<<args.nbatch, threads, smem, stream>>>(args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "molecule_kernel launch");
+  return D3B200_OK;
+}
+
+template <typename S, typename B>
+int fill_common(d3::MolArgs<S>& a, int nbatch, int natoms, const int64_t* numbers,
+                const B* positions, const typename ModelOf<B>::type* m,
+                const d3b200_params* par, const d3b200_params* dpar) {
+  if (nbatch < 0 || natoms < 0) return fail(D3B200_EINVAL, "negative size%s");
+  if (!numbers || !positions || !m || !par) return fail(D3B200_EINVAL, "null argument%s");
+  if (!m->rcov || !m->r4r2 || !m->refcn || !m->refc6) return fail(D3B200_EINVAL, "null model table%s");
+  if (natoms > max_atoms<S>())
+    return fail(D3B200_ESIZE, "natoms = %s%ld exceeds the fused-kernel limit %ld", "", natoms, max_atoms<S>());
+  if (par->s9 != 0.0 && (m->rvdw_mode == 0 || !m->rvdw))
+    return fail(D3B200_EINVAL, "s9 != 0 needs rvdw%s");
+  memset(&a, 0, sizeof(a));
+  a.nbatch = nbatch;
+  a.natoms = natoms;
+  a.numbers = numbers;
+  a.positions = positions;
+  a.rcov = m->rcov;
+  a.r4r2 = m->r4r2;
+  a.rcov_per_element = m->rcov_per_element;
+  a.r4r2_per_element = m->r4r2_per_element;
+  a.refcn = m->refcn;
+  a.refc6 = m->refc6;
+  a.rvdw = m->rvdw;
+  a.rvdw_mode = m->rvdw_mode;
+  auto mk = [&](double v, double d) { return d3::make<S, B>((B)v, (B)d); };
+  a.s6 = mk(par->s6, dpar ? dpar->s6 : 0.0);
+  a.s8 = mk(par->s8, dpar ? dpar->s8 : 0.0);
+  a.a1 = mk(par->a1, dpar ? dpar->a1 : 0.0);
+  a.a2 = mk(par->a2, dpar ? dpar->a2 : 0.0);
+  a.s9 = mk(par->s9, dpar ? dpar->s9 : 0.0);
+  a.rs9 = mk(par->rs9, 0.0);
+  a.alp = mk(par->alp, 0.0);
+  // the reference compares distances in the working precision (disp.py:286)
+  B cut = (B)par->cutoff, cncut = (B)par->cn_cutoff;
+  a.cutoff2 = cut * cut;
+  a.cn_cutoff2 = cncut * cncut;
+  a.kcn = (B)par->kcn;
+  return D3B200_OK;
+}
+
+template <typename B>
+int energy_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
+                const typename ModelOf<B>::type* model, const d3b200_params* par,
+                B* energy, void* stream) {
+  d3::MolArgs<B> a;
+  int rc = fill_common<B, B>(a, nbatch, natoms, numbers, positions, model, par, nullptr);
+  if (rc) return rc;
+  if (!energy) return fail(D3B200_EINVAL, "null output%s");
+  if (nbatch == 0 || natoms == 0) return D3B200_OK;
+  a.energy = energy;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (par->s9 != 0.0) return launch<B, d3::kWantE | d3::kAtm>(a, s);
+  return launch<B, d3::kWantE>(a, s);
+}
+
+template <typename B>
+int vjp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
+             const typename ModelOf<B>::type* model, const d3b200_params* par, const B* g,
+             B* energy, B* grad, B* pgrad, void* stream) {
+  d3::MolArgs<B> a;
+  int rc = fill_common<B, B>(a, nbatch, natoms, numbers, positions, model, par, nullptr);
+  if (rc) return rc;
+  if (!g || !grad) return fail(D3B200_EINVAL, "null cotangent or gradient%s");
+  if (nbatch == 0 || natoms == 0) return D3B200_OK;
+  a.g = g;
+  a.energy = energy;
+  a.grad = grad;
+  a.pgrad = pgrad;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool atm = par->s9 != 0.0;
+  using namespace d3;
+  if (pgrad) {
+    if (atm) return launch<B, kWantE | kWantG | kWantP | kAtm>(a, s);
+    return launch<B, kWantE | kWantG | kWantP>(a, s);
+  }
+  if (energy) {
+    if (atm) return launch<B, kWantE | kWantG | kAtm>(a, s);
+    return launch<B, kWantE | kWantG>(a, s);
+  }
+  if (atm) return launch<B, kWantG | kAtm>(a, s);
+  return launch<B, kWantG>(a, s);
+}
+
+template <typename B>
+int hvp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
+             const B* dpositions, const typename ModelOf<B>::type* model,
+             const d3b200_params* par, const d3b200_params* dpar, const B* g, B* grad,
+             B* pgrad, B* denergy, B* dgrad, B* dpgrad, void* stream) {
+  using S = d3::Dual<B>;
+  d3::MolArgs<S> a;
+  int rc = fill_common<S, B>(a, nbatch, natoms, numbers, positions, model, par, dpar);
+  if (rc) return rc;
+  if (!g) return fail(D3B200_EINVAL, "null cotangent%s");
+  if (nbatch == 0 || natoms == 0) return D3B200_OK;
+  a.dpositions = dpositions;
+  a.g = g;
+  a.grad = grad;
+  a.pgrad = pgrad;
+  a.denergy = denergy;
+  a.dgrad = dgrad;
+  a.dpgrad = dpgrad;
+  cudaStream_t s = (cudaStream_t)stream;
+  using namespace d3;
+  if (par->s9 != 0.0) return launch<S, kWantE | kWantG | kWantP | kAtm>(a, s);
+  return launch<S, kWantE | kWantG | kWantP>(a, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int d3b200_abi_version(void) { return D3B200_ABI_VERSION; }
+const char* d3b200_last_error(void) { return g_err; }
+
+int d3b200_batch_max_atoms_f64(int order) {
+  return order ? max_atoms<d3::Dual<double>>() : max_atoms<double>();
+}
+int d3b200_batch_max_atoms_f32(int order) {
+  return order ? max_atoms<d3::Dual<float>>() : max_atoms<float>();
+}
+
+int d3b200_batch_energy_f64(int nbatch, int natoms, const int64_t* numbers,
+                            const double* positions, const d3b200_model_f64* model,
+                            const d3b200_params* par, double* energy, void* stream) {
+  return energy_impl<double>(nbatch, natoms, numbers, positions, model, par, energy, stream);
+}
+int d3b200_batch_energy_f32(int nbatch, int natoms, const int64_t* numbers,
+                            const float* positions, const d3b200_model_f32* model,
+                            const d3b200_params* par, float* energy, void* stream) {
+  return energy_impl<float>(nbatch, natoms, numbers, positions, model, par, energy, stream);
+}
+
+int d3b200_batch_vjp_f64(int nbatch, int natoms, const int64_t* numbers,
+                         const double* positions, const d3b200_model_f64* model,
+                         const d3b200_params* par, const double* g, double* energy,
+                         double* grad, double* pgrad, void* stream) {
+  return vjp_impl<double>(nbatch, natoms, numbers, positions, model, par, g, energy, grad, pgrad, stream);
+}
+int d3b200_batch_vjp_f32(int nbatch, int natoms, const int64_t* numbers,
+                         const float* positions, const d3b200_model_f32* model,
+                         const d3b200_params* par, const float* g, float* energy,
+                         float* grad, float* pgrad, void* stream) {
+  return vjp_impl<float>(nbatch, natoms, numbers, positions, model, par, g, energy, grad, pgrad, stream);
+}
+
+int d3b200_batch_hvp_f64(int nbatch, int natoms, const int64_t* numbers,
+                         const double* positions, const double* dpositions,
+                         const d3b200_model_f64* model, const d3b200_params* par,
+                         const d3b200_params* dpar, const double* g, double* grad,
+                         double* pgrad, double* denergy, double* dgrad,
+                         double* dpgrad, void* stream) {
+  return hvp_impl<double>(nbatch, natoms, numbers, positions, dpositions, model, par, dpar, g,
+                          grad, pgrad, denergy, dgrad, dpgrad, stream);
+}
+int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
+                         const float* positions, const float* dpositions,
+                         const d3b200_model_f32* model, const d3b200_params* par,
+                         const d3b200_params* dpar, const float* g, float* grad,
+                         float* pgrad, float* denergy, float* dgrad, float* dpgrad,
+                         void* stream) {
+  return hvp_impl<float>(nbatch, natoms, numbers, positions, dpositions, model, par, dpar, g,
+                         grad, pgrad, denergy, dgrad, dpgrad, stream);
+}
+
+}  // extern "C"

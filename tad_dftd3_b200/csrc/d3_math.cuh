@@ -1,0 +1,117 @@
+// Scalar layer of the D3 kernels: one set of device functions, instantiated on
+//   float, double                     (energies and analytic first derivatives)
+//   Dual<float>, Dual<double>         (value + one tangent: the second-order /
+//                                      Hessian-vector path is the directional
+//                                      derivative of the analytic gradient)
+//
+// Everything the pair kernels need is expressed through `+ - *`, `rcp`, `rsq`,
+// `sqr`, `ex` and `val`, so the kernels are written once.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace d3 {
+
+template <typename T>
+struct Dual {
+  T v, d;
+  __host__ __device__ Dual() {}
+  __host__ __device__ Dual(T v_) : v(v_), d(T(0)) {}
+  __host__ __device__ Dual(T v_, T d_) : v(v_), d(d_) {}
+};
+
+#define D3_HD __host__ __device__ __forceinline__
+
+template <typename T> D3_HD Dual<T> operator+(Dual<T> a, Dual<T> b) { return Dual<T>(a.v + b.v, a.d + b.d); }
+template <typename T> D3_HD Dual<T> operator-(Dual<T> a, Dual<T> b) { return Dual<T>(a.v - b.v, a.d - b.d); }
+template <typename T> D3_HD Dual<T> operator-(Dual<T> a) { return Dual<T>(-a.v, -a.d); }
+template <typename T> D3_HD Dual<T> operator*(Dual<T> a, Dual<T> b) { return Dual<T>(a.v * b.v, a.v * b.d + a.d * b.v); }
+template <typename T> D3_HD Dual<T> operator+(Dual<T> a, T b) { return Dual<T>(a.v + b, a.d); }
+template <typename T> D3_HD Dual<T> operator+(T a, Dual<T> b) { return Dual<T>(a + b.v, b.d); }
+template <typename T> D3_HD Dual<T> operator-(Dual<T> a, T b) { return Dual<T>(a.v - b, a.d); }
+template <typename T> D3_HD Dual<T> operator-(T a, Dual<T> b) { return Dual<T>(a - b.v, -b.d); }
+template <typename T> D3_HD Dual<T> operator*(Dual<T> a, T b) { return Dual<T>(a.v * b, a.d * b); }
+template <typename T> D3_HD Dual<T> operator*(T a, Dual<T> b) { return Dual<T>(a * b.v, a * b.d); }
+template <typename T> D3_HD Dual<T>& operator+=(Dual<T>& a, Dual<T> b) { a.v += b.v; a.d += b.d; return a; }
+template <typename T> D3_HD Dual<T>& operator-=(Dual<T>& a, Dual<T> b) { a.v -= b.v; a.d -= b.d; return a; }
+
+// ---- traits ---------------------------------------------------------------
+template <typename S> struct Traits;
+template <> struct Traits<float> {
+  using base = float; using wide = double; static constexpr bool dual = false;
+};
+template <> struct Traits<double> {
+  using base = double; using wide = double; static constexpr bool dual = false;
+};
+template <> struct Traits<Dual<float>> {
+  using base = float; using wide = Dual<double>; static constexpr bool dual = true;
+};
+template <> struct Traits<Dual<double>> {
+  using base = double; using wide = Dual<double>; static constexpr bool dual = true;
+};
+
+// machine epsilon of the base type (the reference clamps squared distances at
+// finfo(dtype).eps, tad-mctc storch.cdist)
+template <typename T> D3_HD T eps_of();
+template <> D3_HD float eps_of<float>() { return 1.1920928955078125e-07f; }
+template <> D3_HD double eps_of<double>() { return 2.220446049250313e-16; }
+
+// ---- value / tangent access -------------------------------------------------
+D3_HD float val(float a) { return a; }
+D3_HD double val(double a) { return a; }
+template <typename T> D3_HD T val(Dual<T> a) { return a.v; }
+
+D3_HD float tan_of(float) { return 0.f; }
+D3_HD double tan_of(double) { return 0.0; }
+template <typename T> D3_HD T tan_of(Dual<T> a) { return a.d; }
+
+template <typename S, typename T> D3_HD S make(T v, T d);
+template <> D3_HD float make<float, float>(float v, float) { return v; }
+template <> D3_HD double make<double, double>(double v, double) { return v; }
+template <> D3_HD Dual<float> make<Dual<float>, float>(float v, float d) { return Dual<float>(v, d); }
+template <> D3_HD Dual<double> make<Dual<double>, double>(double v, double d) { return Dual<double>(v, d); }
+
+// ---- elementary functions ---------------------------------------------------
+D3_HD float rcp(float a) { return 1.0f / a; }
+D3_HD double rcp(double a) { return 1.0 / a; }
+template <typename T> D3_HD Dual<T> rcp(Dual<T> a) {
+  T r = rcp(a.v);
+  return Dual<T>(r, -a.d * r * r);
+}
+
+D3_HD float rsq(float a) { return rsqrtf(a); }
+D3_HD double rsq(double a) { return rsqrt(a); }
+template <typename T> D3_HD Dual<T> rsq(Dual<T> a) {
+  T r = rsq(a.v);
+  return Dual<T>(r, T(-0.5) * a.d * r * r * r);
+}
+
+D3_HD float sqr(float a) { return sqrtf(a); }
+D3_HD double sqr(double a) { return sqrt(a); }
+template <typename T> D3_HD Dual<T> sqr(Dual<T> a) {
+  T s = sqr(a.v);
+  return Dual<T>(s, T(0.5) * a.d / s);
+}
+
+D3_HD float ex(float a) { return expf(a); }
+D3_HD double ex(double a) { return exp(a); }
+template <typename T> D3_HD Dual<T> ex(Dual<T> a) {
+  T e = ex(a.v);
+  return Dual<T>(e, e * a.d);
+}
+
+// conversions between working precision and the (float64) weight stage
+D3_HD double widen(float a) { return (double)a; }
+D3_HD double widen(double a) { return a; }
+D3_HD Dual<double> widen(Dual<float> a) { return Dual<double>((double)a.v, (double)a.d); }
+D3_HD Dual<double> widen(Dual<double> a) { return a; }
+
+template <typename S> D3_HD S narrow(typename Traits<S>::wide a);
+template <> D3_HD float narrow<float>(double a) { return (float)a; }
+template <> D3_HD double narrow<double>(double a) { return a; }
+template <> D3_HD Dual<float> narrow<Dual<float>>(Dual<double> a) { return Dual<float>((float)a.v, (float)a.d); }
+template <> D3_HD Dual<double> narrow<Dual<double>>(Dual<double> a) { return a; }
+
+// integer power by repeated squaring is written out at the call sites.
+
+}  // namespace d3

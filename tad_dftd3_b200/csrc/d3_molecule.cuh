@@ -1,0 +1,402 @@
+// Fused per-structure kernel for padded batches (BASELINE configs 1-3, 5b).
+//
+// One CTA owns one structure of the batch and runs the whole hot path of the
+// reference's `dftd3()` (disp.py:150-165) for it without touching HBM between
+// stages and without any N x N (or N x N x 7 x 7) temporary:
+//
+//   phase 0  load Z / x / per-atom data, counting-sort the atoms by element
+//   phase 1  CN sweep                      (tad-mctc cn_d3 + exp_count, r <= 25)
+//   phase 2  Gaussian reference weights w, dw/dCN   (model/weights.py:104-176)
+//   phase 3  pair sweep: C6_ij, dC6_ij/dCN_i, BJ energy, direct gradient,
+//            dL/dCN_i, parameter gradients  (model/c6.py, disp.py:276-302,
+//            damping/rational.py:68)
+//   phase 3b ATM triple sweep (optional; damping/atm.py:86-155)
+//   phase 4  CN-backward sweep (chain rule through the counting function)
+//
+// Thread t owns the atom at sorted position t and walks all partners j with a
+// warp-uniform j, so every shared-memory read in the inner loops is a
+// broadcast and nothing is scattered: no atomics, bitwise reproducible.
+// Atoms are sorted by element so that the 7x7 reference block K[Zi,Zj] is
+// contracted with the thread's own weights once per (atom, partner element):
+//   U[b] = sum_a w_ia K[Zi,Zj,a,b],  Ud[b] = sum_a dw_ia K[Zi,Zj,a,b]
+// after which C6_ij = U . w_j and dC6_ij/dCN_i = Ud . w_j cost 7 FMAs each
+// (the reference gathers 49 values per pair, model/c6.py:216).
+#pragma once
+#include "d3_math.cuh"
+
+namespace d3 {
+
+constexpr int kMaxZ = 104;   // reference defaults.MAX_ELEMENT
+constexpr int kNRef = 7;     // reference systems per element
+
+enum : int { kWantE = 1, kWantG = 2, kWantP = 4, kAtm = 8 };
+
+template <typename S>
+struct MolArgs {
+  using B = typename Traits<S>::base;
+  int nbatch, natoms;
+  const int64_t* numbers;   // [nbatch, natoms]
+  const B* positions;       // [nbatch, natoms, 3]
+  const B* dpositions;      // tangent of positions (Dual only) or null
+  const B* rcov;            // per atom [nbatch, natoms] or per element [>=104]
+  const B* r4r2;            // same convention
+  int rcov_per_element, r4r2_per_element;
+  const B* refcn;           // [104, 7]
+  const B* refc6;           // [104, 104, 7, 7]
+  const B* rvdw;            // mode 1: [104,104] table, mode 2: dense [nbatch,N,N]
+  int rvdw_mode;
+  const B* g;               // [nbatch, natoms] cotangent of the per-atom energy
+  S s6, s8, a1, a2, s9, rs9, alp;
+  B cutoff2, cn_cutoff2, kcn;
+  B* energy;                // [nbatch, natoms]
+  B* grad;                  // [nbatch, natoms, 3]
+  B* pgrad;                 // [nbatch, 5]  (s6, s8, a1, a2, s9)
+  B* denergy;               // tangents (Dual only)
+  B* dgrad;
+  B* dpgrad;
+};
+
+template <typename S> __device__ __forceinline__ S warp_sum(S v);
+template <> __device__ __forceinline__ float warp_sum<float>(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <> __device__ __forceinline__ double warp_sum<double>(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <> __device__ __forceinline__ Dual<float> warp_sum<Dual<float>>(Dual<float> v) {
+  return Dual<float>(warp_sum(v.v), warp_sum(v.d));
+}
+template <> __device__ __forceinline__ Dual<double> warp_sum<Dual<double>>(Dual<double> v) {
+  return Dual<double>(warp_sum(v.v), warp_sum(v.d));
+}
+
+// shared memory bytes needed by the fused kernel for `natoms` atoms
+template <typename S>
+__host__ __device__ inline size_t molecule_smem_bytes(int natoms) {
+  // S arrays: x y z rcov q sqrtq cn decn gx gy gz (11) + w[8] + dw[8] = 27 per atom
+  // base array: g (1)   int arrays: origZ, sortedZ, perm (3)
+  size_t n = (size_t)natoms;
+  size_t bytes = n * 27 * sizeof(S) + n * sizeof(typename Traits<S>::base) + n * 3 * sizeof(int);
+  bytes += (4 * kMaxZ + 8) * sizeof(int);          // cnt, zstart, gZ, gstart, counters
+  bytes += 32 * 5 * sizeof(S);                      // block reduction scratch
+  return bytes + 64;
+}
+
+// Gaussian weights of one atom and their CN derivative.
+// Reference: model/weights.py:104-176 -- the CN difference is formed in the
+// working precision, the exponentials and the normalisation in float64.
+template <typename S>
+__device__ __forceinline__ void reference_weights(
+    const typename Traits<S>::base* __restrict__ refcn_row, S cn, S* w, S* dw) {
+  using B = typename Traits<S>::base;
+  using W = typename Traits<S>::wide;
+  W gw[kNRef], dc[kNRef];
+  W norm = W(0.0);
+  B maxcn = B(-1e30);
+  bool valid[kNRef];
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) {
+    B rc = refcn_row[a];
+    valid[a] = rc >= B(0);
+    maxcn = rc > maxcn ? rc : maxcn;
+    S diff = rc - cn;                 // working precision, as the reference
+    dc[a] = widen(diff);
+    gw[a] = valid[a] ? ex(-(4.0 * (dc[a] * dc[a]))) : W(0.0);
+    norm += gw[a];
+  }
+  if (val(norm) == 0.0) {
+    // every Gaussian underflowed: weight 1 on the reference(s) with the largest
+    // reference CN, no CN dependence (weights.py:162-174)
+#pragma unroll
+    for (int a = 0; a < kNRef; ++a) {
+      w[a] = (valid[a] && refcn_row[a] == maxcn) ? S(B(1)) : S(B(0));
+      dw[a] = S(B(0));
+    }
+    return;
+  }
+  W inv = rcp(norm);
+  W wa[kNRef];
+  W mean = W(0.0);
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) {
+    wa[a] = gw[a] * inv;
+    mean += wa[a] * dc[a];
+  }
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) {
+    // d w_a / d CN = 8 w_a (dc_a - sum_b w_b dc_b),  dc = refcn - CN
+    W d = 8.0 * (wa[a] * (dc[a] - mean));
+    w[a] = narrow<S>(wa[a]);
+    dw[a] = narrow<S>(d);
+  }
+}
+
+constexpr int kMolThreads = 256;  // CTA size cap; larger structures loop over i
+
+template <typename S, int FLAGS>
+__global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
+  using B = typename Traits<S>::base;
+  constexpr bool DUAL = Traits<S>::dual;
+  constexpr bool WANT_E = FLAGS & kWantE;
+  constexpr bool WANT_G = FLAGS & kWantG;
+  constexpr bool WANT_P = FLAGS & kWantP;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = A.natoms;
+  const int b = blockIdx.x;
+  const int t = threadIdx.x;
+  const int nt = blockDim.x;
+
+  S* sx = reinterpret_cast<S*>(smem_raw);
+  S* sy = sx + N;
+  S* sz = sy + N;
+  S* srcov = sz + N;
+  S* sq = srcov + N;
+  S* ssq = sq + N;
+  S* scn = ssq + N;
+  S* sdecn = scn + N;
+  S* sgx = sdecn + N;
+  S* sgy = sgx + N;
+  S* sgz = sgy + N;
+  S* sw = sgz + N;              // [N][8]
+  S* sdw = sw + 8 * (size_t)N;  // [N][8]
+  S* sred = sdw + 8 * (size_t)N;  // [32][5]
+  B* sg = reinterpret_cast<B*>(sred + 32 * 5);
+  int* sorigZ = reinterpret_cast<int*>(sg + N);
+  int* sZ = sorigZ + N;
+  int* sperm = sZ + N;
+  int* cnt = sperm + N;
+  int* zstart = cnt + kMaxZ;
+  int* gZ = zstart + kMaxZ;
+  int* gstart = gZ + kMaxZ;     // [kMaxZ + 1]
+  int* misc = gstart + kMaxZ + 1;  // [0] = ngroups, [1] = nreal
+
+  const int64_t* numbers = A.numbers + (size_t)b * N;
+  const B* pos = A.positions + (size_t)b * N * 3;
+
+  // ---------------------------------------------------------------- phase 0
+  for (int k = t; k < kMaxZ; k += nt) cnt[k] = 0;
+  __syncthreads();
+  for (int k = t; k < N; k += nt) {
+    int Z = (int)numbers[k];
+    if (Z < 0 || Z >= kMaxZ) Z = 0;  // host validates; never index out of range
+    sorigZ[k] = Z;
+    if (Z > 0) {
+      atomicAdd(&cnt[Z], 1);
+    } else {
+      // padding / ghost atom: exact zeros in every output (reference: masks)
+      size_t o = (size_t)b * N + k;
+      if (WANT_E && A.energy) A.energy[o] = B(0);
+      if (WANT_E && DUAL && A.denergy) A.denergy[o] = B(0);
+      if (WANT_G) {
+        if (A.grad) { A.grad[3 * o] = B(0); A.grad[3 * o + 1] = B(0); A.grad[3 * o + 2] = B(0); }
+        if (DUAL && A.dgrad) { A.dgrad[3 * o] = B(0); A.dgrad[3 * o + 1] = B(0); A.dgrad[3 * o + 2] = B(0); }
+      }
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    int ng = 0, run = 0;
+    for (int z = 1; z < kMaxZ; ++z) {
+      zstart[z] = run;
+      if (cnt[z] > 0) { gZ[ng] = z; gstart[ng] = run; ++ng; run += cnt[z]; }
+    }
+    gstart[ng] = run;
+    misc[0] = ng;
+    misc[1] = run;
+  }
+  __syncthreads();
+  const int ng = misc[0];
+  const int n = misc[1];
+  for (int k = t; k < N; k += nt) {
+    const int Z = sorigZ[k];
+    if (Z == 0) continue;
+    int p = zstart[Z];
+    for (int m = 0; m < k; ++m) p += (sorigZ[m] == Z);
+    sperm[p] = k;
+    sZ[p] = Z;
+    B px = pos[3 * k], py = pos[3 * k + 1], pz = pos[3 * k + 2];
+    B dx = B(0), dy = B(0), dz = B(0);
+    if (DUAL && A.dpositions) {
+      const B* dp = A.dpositions + ((size_t)b * N + k) * 3;
+      dx = dp[0]; dy = dp[1]; dz = dp[2];
+    }
+    sx[p] = make<S, B>(px, dx);
+    sy[p] = make<S, B>(py, dy);
+    sz[p] = make<S, B>(pz, dz);
+    B rc = A.rcov_per_element ? A.rcov[Z] : A.rcov[(size_t)b * N + k];
+    B q = A.r4r2_per_element ? A.r4r2[Z] : A.r4r2[(size_t)b * N + k];
+    srcov[p] = S(rc);
+    sq[p] = S(q);
+    ssq[p] = S(sqr(q));
+    sg[p] = (WANT_G && A.g) ? A.g[(size_t)b * N + k] : B(1);
+  }
+  __syncthreads();
+
+  const B eps = eps_of<B>();
+
+  // ---------------------------------------------------------------- phase 1+2
+  // CN_i = sum_j [r_ij <= 25] / (1 + exp(-kcn (rc_ij / r_ij - 1))), then weights
+  for (int i = t; i < n; i += nt) {
+    const S xi = sx[i], yi = sy[i], zi = sz[i], rci = srcov[i];
+    S cn = S(B(0));
+    for (int j = 0; j < n; ++j) {
+      if (j == i) continue;
+      S dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
+      S r2 = dx * dx + dy * dy + dz * dz;
+      if (val(r2) > A.cn_cutoff2) continue;
+      if (val(r2) < eps) r2 = S(eps);
+      S rinv = rsq(r2);
+      S arg = A.kcn * ((rci + srcov[j]) * rinv - B(1));
+      cn += rcp(B(1) + ex(-arg));
+    }
+    scn[i] = cn;
+    S wi[kNRef], dwi[kNRef];
+    reference_weights<S>(A.refcn + sZ[i] * kNRef, cn, wi, dwi);
+#pragma unroll
+    for (int a = 0; a < kNRef; ++a) { sw[8 * i + a] = wi[a]; sdw[8 * i + a] = dwi[a]; }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 3
+  S p_s6 = S(B(0)), p_s8 = S(B(0)), p_a1 = S(B(0)), p_a2 = S(B(0));
+  for (int i = t; i < n; i += nt) {
+    const S xi = sx[i], yi = sy[i], zi = sz[i], qi = sq[i];
+    const int Zi = sZ[i];
+    S wi[kNRef], dwi[kNRef];
+#pragma unroll
+    for (int a = 0; a < kNRef; ++a) { wi[a] = sw[8 * i + a]; dwi[a] = sdw[8 * i + a]; }
+    S e_i = S(B(0)), gx = S(B(0)), gy = S(B(0)), gz = S(B(0)), decn = S(B(0));
+    const B gi = sg[i];
+    const S sa_i = A.a1 * sqr(B(3) * qi);   // a1 sqrt(3 q_i);  R0 = sa_i sqrt(q_j) + a2
+    const S q3_i = B(3) * qi;
+    for (int grp = 0; grp < ng; ++grp) {
+      const int Zj = gZ[grp];
+      const B* __restrict__ K = A.refc6 + ((size_t)Zi * kMaxZ + Zj) * (kNRef * kNRef);
+      S U[kNRef], Ud[kNRef];
+#pragma unroll
+      for (int bb = 0; bb < kNRef; ++bb) { U[bb] = S(B(0)); Ud[bb] = S(B(0)); }
+#pragma unroll
+      for (int a = 0; a < kNRef; ++a) {
+#pragma unroll
+        for (int bb = 0; bb < kNRef; ++bb) {
+          B k = __ldg(K + a * kNRef + bb);
+          U[bb] += wi[a] * k;
+          if (WANT_G) Ud[bb] += dwi[a] * k;
+        }
+      }
+      const int j1 = gstart[grp + 1];
+      for (int j = gstart[grp]; j < j1; ++j) {
+        if (j == i) continue;
+        S dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
+        S r2 = dx * dx + dy * dy + dz * dz;
+        if (val(r2) > A.cutoff2) continue;
+        if (val(r2) < eps) r2 = S(eps);
+        const S* wj = sw + 8 * j;
+        S c6 = U[0] * wj[0];
+#pragma unroll
+        for (int a = 1; a < kNRef; ++a) c6 += U[a] * wj[a];
+        S qq = q3_i * sq[j];
+        S r0 = sa_i * ssq[j] + A.a2;
+        S r02 = r0 * r0;
+        S r06 = r02 * r02 * r02;
+        S r08 = r06 * r02;
+        S r4 = r2 * r2;
+        S r6 = r4 * r2;
+        S r8 = r4 * r4;
+        S t6 = rcp(r6 + r06);
+        S t8 = rcp(r8 + r08);
+        S s8q = A.s8 * qq;
+        S P = A.s6 * t6 + s8q * t8;
+        if (WANT_E) e_i += c6 * P;   // scaled by -1/2 at the end
+        if (WANT_G) {
+          S dc6 = Ud[0] * wj[0];
+#pragma unroll
+          for (int a = 1; a < kNRef; ++a) dc6 += Ud[a] * wj[a];
+          B gam = B(0.5) * (gi + sg[j]);
+          // dL/dC6_ij = -gam P ;  dL/dCN_i += that * dC6_ij/dCN_i
+          decn -= (gam * P) * dc6;
+          // -dP/d(r^2) = 3 s6 r^4 t6^2 + 4 s8 qq r^6 t8^2
+          S t62 = t6 * t6, t82 = t8 * t8;
+          S dP = B(3) * (A.s6 * (r4 * t62)) + B(4) * (s8q * (r6 * t82));
+          // dL/dx_i = -gam C6 dP/dr2 * 2 d
+          S f = (B(2) * gam) * (c6 * dP);
+          gx += f * dx; gy += f * dy; gz += f * dz;
+          if (WANT_P) {
+            // each unordered pair is visited from both ends: weight 1/2
+            S hc = (B(-0.5) * gam) * c6;
+            p_s6 += hc * t6;
+            p_s8 += hc * (qq * t8);
+            // dP/dR0 = -(6 s6 R0^5 t6^2 + 8 s8 qq R0^7 t8^2)
+            S r05 = r02 * r02 * r0;
+            S dPr0 = B(-6) * (A.s6 * (r05 * t62)) - B(8) * (s8q * ((r05 * r02) * t82));
+            S h = hc * dPr0;
+            p_a2 += h;
+            p_a1 += h * sqr(qq);
+          }
+        }
+      }
+    }
+    if (WANT_E) {
+      size_t o = (size_t)b * N + sperm[i];
+      S e = B(-0.5) * e_i;
+      if (A.energy) A.energy[o] = val(e);
+      if (DUAL && A.denergy) A.denergy[o] = tan_of(e);
+    }
+    if (WANT_G) { sdecn[i] = decn; sgx[i] = gx; sgy[i] = gy; sgz[i] = gz; }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 4
+  // dL/dx_i += sum_j (dL/dCN_i + dL/dCN_j) df_ij/dx_i,
+  // df/dx_i = -kcn rc r^-3 f (1 - f) (x_i - x_j)
+  if (WANT_G) {
+    for (int i = t; i < n; i += nt) {
+      const S xi = sx[i], yi = sy[i], zi = sz[i], rci = srcov[i], decn = sdecn[i];
+      S gx = sgx[i], gy = sgy[i], gz = sgz[i];
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        S dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
+        S r2 = dx * dx + dy * dy + dz * dz;
+        if (val(r2) > A.cn_cutoff2) continue;
+        if (val(r2) < eps) continue;  // clamped distance: no position dependence
+        S rinv = rsq(r2);
+        S rc = rci + srcov[j];
+        S arg = A.kcn * (rc * rinv - B(1));
+        S e = ex(-arg);
+        S f = rcp(B(1) + e);
+        S df = (-A.kcn) * (rc * (rinv * rinv * rinv)) * (f * (e * f));  // f(1-f) = e f^2
+        S c = (decn + sdecn[j]) * df;
+        gx += c * dx; gy += c * dy; gz += c * dz;
+      }
+      size_t o = (size_t)b * N + sperm[i];
+      if (A.grad) { A.grad[3 * o] = val(gx); A.grad[3 * o + 1] = val(gy); A.grad[3 * o + 2] = val(gz); }
+      if (DUAL && A.dgrad) { A.dgrad[3 * o] = tan_of(gx); A.dgrad[3 * o + 1] = tan_of(gy); A.dgrad[3 * o + 2] = tan_of(gz); }
+    }
+  }
+
+  if (WANT_P) {
+    S v[4] = {p_s6, p_s8, p_a1, p_a2};
+    const int lane = t & 31, wid = t >> 5, nw = (nt + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      S s = warp_sum<S>(v[k]);
+      if (lane == 0) sred[wid * 5 + k] = s;
+    }
+    __syncthreads();
+    if (t < 4) {
+      S s = S(B(0));
+      for (int w = 0; w < nw; ++w) s += sred[w * 5 + t];
+      if (A.pgrad) A.pgrad[(size_t)b * 5 + t] = val(s);
+      if (DUAL && A.dpgrad) A.dpgrad[(size_t)b * 5 + t] = tan_of(s);
+    }
+    if (t == 4) {
+      if (A.pgrad) A.pgrad[(size_t)b * 5 + 4] = B(0);
+      if (DUAL && A.dpgrad) A.dpgrad[(size_t)b * 5 + 4] = B(0);
+    }
+  }
+}
+
+}  // namespace d3

@@ -1,0 +1,219 @@
+"""
+Dispersion energy: the drop-in for the reference's `disp.py`.
+
+`dftd3()` keeps the reference's signature, defaults and errors
+(disp.py:79-165) and dispatches the whole body -- coordination number,
+reference weights, C6 interpolation, Becke-Johnson two-body sum, optional
+Axilrod-Teller-Muto term, and their analytic first/second derivatives -- to
+the sm_100a kernels behind `libd3b200.so` (`ops.D3Energy`).
+
+There is no CPU path and no torch-eager fallback: non-CUDA inputs and
+non-default counting / weighting / damping callables raise.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Any
+
+import torch
+from torch import Tensor
+
+from . import data, defaults
+from .damping import rational_damping
+from .model import gaussian_weight
+from .ncoord import exp_count
+from .ops import NPAR, Settings, d3_energy
+from .reference import Reference
+
+__all__ = ["dftd3", "dispersion", "dispersion2", "dispersion3"]
+
+_Z2S_104 = "Rf"  # element 104, named in the reference's error message (disp.py:134)
+
+
+def _is_functorch(x: Tensor) -> bool:
+    f = torch._C._functorch
+    return bool(f.is_batchedtensor(x) or f.is_gradtrackingtensor(x))
+
+
+_checked = weakref.WeakKeyDictionary()
+
+
+def _check_numbers(numbers: Tensor) -> None:
+    """ValueError for Z >= 104 (disp.py:130-135); one device sync per distinct tensor."""
+    if _is_functorch(numbers) or numbers.numel() == 0:
+        return
+    try:
+        if _checked.get(numbers) == numbers._version:
+            return
+    except TypeError:  # pragma: no cover
+        pass
+    if int(torch.max(numbers)) >= defaults.MAX_ELEMENT:
+        raise ValueError(
+            f"No D3 parameters available for Z > {defaults.MAX_ELEMENT - 1} ({_Z2S_104})."
+        )
+    if int(torch.min(numbers)) < 0:
+        raise ValueError("Atomic numbers must be non-negative.")
+    try:
+        _checked[numbers] = numbers._version
+    except TypeError:  # pragma: no cover
+        pass
+
+
+_table_cache: dict = {}
+
+
+def _element_table(name: str, dtype, device) -> Tensor:
+    key = (name, dtype, str(device))
+    t = _table_cache.get(key)
+    if t is None:
+        t = getattr(data, name)(dtype=dtype, device=device).contiguous()
+        _table_cache[key] = t
+    return t
+
+
+def _scalar(v: Any) -> float:
+    return float(v.detach()) if isinstance(v, Tensor) else float(v)
+
+
+def _param_vector(param: dict, dtype) -> Tensor:
+    """(s6, s8, a1, a2, s9) with the reference's defaults; keeps the autograd graph."""
+    keys = ("s6", "s8", "a1", "a2", "s9")
+    dflt = (defaults.S6, defaults.S8, defaults.A1, defaults.A2, 0.0)
+    vals = [param.get(k, d) for k, d in zip(keys, dflt)]
+    live = [v for v in vals if isinstance(v, Tensor) and (v.requires_grad or _is_functorch(v))]
+    if not live:
+        return torch.tensor([_scalar(v) for v in vals], dtype=dtype)
+    dev = live[0].device
+    return torch.stack([
+        (v.to(device=dev, dtype=dtype) if isinstance(v, Tensor) else torch.tensor(v, dtype=dtype, device=dev)).reshape(())
+        for v in vals
+    ])
+
+
+def _atm_requested(param: dict) -> bool:
+    # reference disp.py:234 -- a data-dependent Python branch there as well
+    return "s9" in param and bool(param["s9"] != 0.0)
+
+
+def dftd3(
+    numbers: Tensor,
+    positions: Tensor,
+    param: dict,
+    *,
+    ref: Reference | None = None,
+    rcov: Tensor | None = None,
+    rvdw: Tensor | None = None,
+    r4r2: Tensor | None = None,
+    cutoff: Tensor | None = None,
+    counting_function=exp_count,
+    weighting_function=gaussian_weight,
+    damping_function=rational_damping,
+    chunk_size: int | None = None,
+) -> Tensor:
+    """
+    Atom-resolved DFT-D3 dispersion energy of a structure `(N,)` or a
+    zero-padded batch `(B, N)` -- same contract as the reference's
+    `tad_dftd3.dftd3` (disp.py:79-165).
+
+    `chunk_size` is accepted and ignored: no `N x N x 7 x 7` tensor exists.
+    """
+    if counting_function is not exp_count or weighting_function is not gaussian_weight \
+            or damping_function is not rational_damping:
+        raise NotImplementedError(
+            "tad_dftd3_b200 implements the default D3(BJ) model functions "
+            "(exp_count, gaussian_weight, rational_damping) as CUDA kernels; "
+            "custom callables are not supported."
+        )
+    if numbers.shape != positions.shape[:-1]:
+        raise ValueError(
+            f"Shape of positions ({tuple(positions.shape[:-1])}) is not consistent "
+            f"with atomic numbers ({tuple(numbers.shape)})."
+        )
+    if positions.shape[-1] != 3:
+        raise ValueError("positions must have shape (..., nat, 3)")
+    _check_numbers(numbers)
+
+    dtype, device = positions.dtype, positions.device
+    if device.type != "cuda":
+        raise RuntimeError(
+            "tad_dftd3_b200.dftd3 runs on CUDA devices only (no CPU fallback); "
+            f"positions are on {device}."
+        )
+
+    if ref is None:
+        ref = _default_reference(dtype, device)
+    refcn, refc6, symmetric = ref._prepared(device, dtype)
+    if not symmetric:
+        raise ValueError(
+            "reference C6 table must be symmetric: c6[z1,z2,a,b] == c6[z2,z1,b,a]"
+        )
+
+    if rcov is None:
+        rcov_t, rcov_pe = _element_table("COV_D3", dtype, device), True
+    else:
+        if rcov.shape != numbers.shape:
+            raise ValueError(
+                f"Shape of covalent radii {tuple(rcov.shape)} is not consistent with ({tuple(numbers.shape)})."
+            )
+        rcov_t, rcov_pe = rcov.detach().to(device=device, dtype=dtype), False
+    if r4r2 is None:
+        r4r2_t, r4r2_pe = _element_table("R4R2", dtype, device), True
+    else:
+        if r4r2.shape != numbers.shape:
+            raise ValueError("Shape of expectation values is not consistent with atomic numbers.")
+        r4r2_t, r4r2_pe = r4r2.detach().to(device=device, dtype=dtype), False
+
+    atm = _atm_requested(param)
+    rvdw_t, rvdw_mode = None, 0
+    if atm:
+        if rvdw is None:
+            rvdw_t, rvdw_mode = _element_table("VDW_PAIRWISE", dtype, device), 1
+        else:
+            if rvdw.shape != (*numbers.shape, numbers.shape[-1]):
+                raise ValueError("Shape of van-der-Waals radii is not consistent with atomic numbers.")
+            rvdw_t, rvdw_mode = rvdw.detach().to(device=device, dtype=dtype), 2
+
+    st = Settings(
+        rcov=rcov_t, r4r2=r4r2_t, rcov_per_element=rcov_pe, r4r2_per_element=r4r2_pe,
+        refcn=refcn, refc6=refc6, rvdw=rvdw_t, rvdw_mode=rvdw_mode,
+        cutoff=defaults.D3_DISP_CUTOFF if cutoff is None else _scalar(cutoff),
+        cn_cutoff=defaults.D3_CN_CUTOFF, kcn=defaults.D3_KCN,
+        alp=_scalar(param.get("alp", defaults.ALP)),
+    )
+    p = _param_vector(param, dtype)
+    if not atm:
+        # s9 present but zero (or absent): two-body only, and no gradient to s9
+        mask = torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0], dtype=dtype, device=p.device)
+        p = p * mask
+    return d3_energy(numbers, positions, p, st)
+
+
+_default_refs: dict = {}
+
+
+def _default_reference(dtype, device) -> Reference:
+    key = (dtype, str(device))
+    r = _default_refs.get(key)
+    if r is None:
+        r = Reference(dtype=dtype, device=device)
+        _default_refs[key] = r
+    return r
+
+
+def dispersion(numbers, positions, param, c6, rvdw=None, r4r2=None,
+               damping_function=rational_damping, cutoff=None, **kwargs):
+    from .stages import dispersion as _d
+
+    return _d(numbers, positions, param, c6, rvdw, r4r2, damping_function, cutoff, **kwargs)
+
+
+def dispersion2(numbers, positions, param, c6, r4r2, damping_function, cutoff, **kwargs):
+    from .stages import dispersion2 as _d
+
+    return _d(numbers, positions, param, c6, r4r2, damping_function, cutoff, **kwargs)
+
+
+def dispersion3(numbers, positions, param, c6, rvdw, cutoff, rs9=None):
+    from .stages import dispersion3 as _d
+
+    return _d(numbers, positions, param, c6, rvdw, cutoff, rs9)

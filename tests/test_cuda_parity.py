@@ -1,0 +1,203 @@
+"""
+GPU parity tests proper: the CUDA path (through the Python drop-in, which
+calls the C ABI) against
+
+  * the committed outputs of the unmodified reference (`reference_runs.npz`),
+  * the reference's own pinned values where the inputs exist in its tree,
+  * the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp64 1e-10 relative / 1e-12 Hartree
+absolute on per-atom energies and gradients; fp32 1e-5 relative against the
+float64 oracle (the reference's own fp32 path is only good to ~1e-4 because of
+its |x|^2+|y|^2-2x.y distances, so it is compared at 5e-4).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, case_inputs, oracle_energy, tables
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-10, 1e-12
+DEV = "cuda"
+
+
+def run_cuda(numbers, positions, param, cutoff, dtype, *, g=None, pgrad=False, explicit_tables=True):
+    import tad_dftd3_b200 as d3
+
+    refcn, refc6, rcov, r4r2, rvdw = tables(dtype, DEV)
+    numbers = numbers.to(DEV)
+    pos = positions.to(DEV).clone().requires_grad_(g is not None)
+    par = {k: v.to(DEV).clone().requires_grad_(pgrad and k in ("s6", "s8", "a1", "a2"))
+           for k, v in param.items()}
+    kw = dict(ref=d3.Reference(cn=refcn, c6=refc6), cutoff=torch.tensor(cutoff, dtype=dtype, device=DEV),
+              rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)])
+    if explicit_tables:
+        kw.update(rcov=rcov[numbers], r4r2=r4r2[numbers])
+    e = d3.dftd3(numbers, pos, par, **kw)
+    out = {"energy": e.detach().cpu().numpy()}
+    if g is not None:
+        wrt = [pos] + ([par[k] for k in ("s6", "s8", "a1", "a2") if k in par] if pgrad else [])
+        grads = torch.autograd.grad((e * g.to(DEV)).sum(), wrt)
+        out["grad"] = grads[0].cpu().numpy()
+        if pgrad:
+            out["pgrad"] = np.asarray([float(x) for x in grads[1:]])
+    return out
+
+
+def two_body_cases(runs):
+    return [c for c in runs.cases if not c.startswith("stages")]
+
+
+def is_atm(c):
+    keys = [str(k) for k in c["param_keys"]]
+    return "s9" in keys and float(c["param_vals"][keys.index("s9")]) != 0.0
+
+
+def _case_names():
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_runs.npz"))
+    return sorted({k.split("/")[0] for k in z.files if not k.startswith("stages")})
+
+
+@pytest.mark.parametrize("case", _case_names())
+def test_reference_runs(runs, case):
+    """Every committed reference run: energies, VJPs, parameter gradients."""
+    c = runs.case(case)
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    f32 = dtype == torch.float32
+    out = run_cuda(numbers, positions, param, cutoff, dtype, g=g, pgrad="pgrad" in c)
+    if f32:
+        # fp32: tight against the float64 oracle, loose against the fp32 reference
+        pos64 = positions.double().requires_grad_(True)
+        par64 = {k: v.double() for k, v in param.items()}
+        e64 = oracle_energy(numbers, pos64, par64, cutoff, torch.double)
+        (g64,) = torch.autograd.grad((e64 * g.double()).sum(), pos64)
+        assert_close(out["energy"], e64.detach(), 1e-5, 1e-9, case + " energy vs f64 oracle")
+        assert_close(out["grad"], g64, 1e-4, 2e-8, case + " grad vs f64 oracle")
+        assert_close(out["energy"], c["energy"], 5e-4, 1e-8, case + " energy vs f32 reference")
+    else:
+        assert_close(out["energy"], c["energy"], RTOL, ATOL, case + " energy")
+        assert_close(out["grad"], c["grad"], RTOL, ATOL, case + " grad")
+        if "pgrad" in c:
+            assert_close(out["pgrad"], c["pgrad"], RTOL, ATOL, case + " pgrad")
+    assert out["energy"].dtype == (np.float32 if f32 else np.float64)
+
+
+def test_padding_is_exact_zero(runs):
+    c = runs.case("c2_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    out = run_cuda(numbers, positions, param, cutoff, dtype, g=g)
+    pad = (numbers == 0).numpy()
+    assert pad.any()
+    assert (out["energy"][pad] == 0).all() and (out["grad"][pad] == 0).all()
+
+
+def test_batch_rows_equal_single_runs(runs):
+    """A padded batch row is bitwise the single-structure result."""
+    c = runs.case("mols6_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    full = run_cuda(numbers, positions, param, cutoff, dtype, g=g)
+    for b in range(numbers.shape[0]):
+        n = int((numbers[b] != 0).sum())
+        one = run_cuda(numbers[b, :n], positions[b, :n], param, cutoff, dtype, g=g[b, :n])
+        assert np.array_equal(one["energy"], full["energy"][b, :n])
+        assert np.array_equal(one["grad"], full["grad"][b, :n])
+
+
+def test_default_tables_equal_explicit(runs):
+    """rcov=None / r4r2=None gather from the element tables inside the kernel."""
+    c = runs.case("mols6_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    a = run_cuda(numbers, positions, param, cutoff, dtype, g=g, explicit_tables=True)
+    b = run_cuda(numbers, positions, param, cutoff, dtype, g=g, explicit_tables=False)
+    assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["grad"], b["grad"])
+
+
+@pytest.mark.parametrize("name", ["PbH4_BiH3", "C6H5I_CH3SH"])
+def test_pinned_cn_through_default_radii(pins, name):
+    """CN pinned by the reference's tests, through the product's own COV_D3 table:
+    total energy is insensitive, so check via d(E)/d(...)-free route: oracle CN
+    with product radii equals the pinned CN (validates data.COV_D3)."""
+    import d3_oracle as orc
+    from tad_dftd3_b200.data import COV_D3
+
+    c = pins.case(name)
+    numbers = torch.from_numpy(c["numbers"])
+    cn = orc.cn_d3(numbers, torch.from_numpy(c["positions"]), COV_D3(torch.double)[numbers])
+    assert_close(cn, c["cn"], 0, 5e-11, name)
+
+
+@pytest.mark.parametrize("case", ["pbh4_hess_f64", "two_atoms_f64", "pbh4_hess_atm_f64"])
+def test_hessian_jacrev(runs, case):
+    """examples/hessian.py:84-94 construction: jacrev(jacrev(E_total))."""
+    import tad_dftd3_b200 as d3
+
+    c = runs.case(case)
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    refcn, refc6, rcov, r4r2, rvdw = tables(dtype, DEV)
+    numbers = numbers.to(DEV)
+    par = {k: v.to(DEV) for k, v in param.items()}
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    rv = rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)]
+
+    def energy(pos):
+        return d3.dftd3(numbers, pos, par, ref=ref, rvdw=rv).sum(-1)
+
+    h = torch.func.jacrev(torch.func.jacrev(energy))(positions.to(DEV))
+    assert_close(h.cpu(), c["hessian"], 1e-9, 1e-12, case)
+
+
+def test_hessian_vmap_batch(runs):
+    """vmap(jacrev(jacrev)) over a padded batch (reference test_hessian.py:140-202)."""
+    import tad_dftd3_b200 as d3
+
+    c = runs.case("c2_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    refcn, refc6, rcov, r4r2, rvdw = tables(dtype, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    par = {k: v.to(DEV) for k, v in param.items()}
+
+    def energy(num, pos):
+        return d3.dftd3(num, pos, par, ref=ref).sum(-1)
+
+    hfn = torch.func.vmap(torch.func.jacrev(torch.func.jacrev(energy, argnums=1), argnums=1), in_dims=(0, 0))
+    h = hfn(numbers.to(DEV), positions.to(DEV)).cpu()
+    # oracle Hessian per structure
+    for b in range(numbers.shape[0]):
+        def f(p, b=b):
+            return oracle_energy(numbers[b], p, param, cutoff, dtype).sum(-1)
+
+        ho = torch.func.jacrev(torch.func.jacrev(f))(positions[b])
+        assert_close(h[b], ho, 1e-9, 1e-12, f"structure {b}")
+
+
+def test_gradcheck_positions_and_params(runs):
+    """gradcheck / gradgradcheck w.r.t. positions and (s6, s8, a1, a2)
+    (reference test_pos.py:63-90, test_param.py:62-83), tol 1e-8."""
+    import tad_dftd3_b200 as d3
+
+    c = runs.case("pbh4_hess_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    refcn, refc6, *_ = tables(dtype, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    numbers = numbers.to(DEV)
+    pos = positions.to(DEV).requires_grad_(True)
+    base = {k: v.to(DEV) for k, v in param.items()}
+
+    def f_pos(p):
+        return d3.dftd3(numbers, p, base, ref=ref)
+
+    assert torch.autograd.gradcheck(f_pos, (pos,), atol=1e-8, fast_mode=True)
+    assert torch.autograd.gradgradcheck(f_pos, (pos,), atol=1e-8, fast_mode=True)
+
+    keys = ("s6", "s8", "a1", "a2")
+    pv = tuple(base[k].clone().requires_grad_(True) for k in keys)
+
+    def f_par(*vals):
+        return d3.dftd3(numbers, pos.detach(), dict(base, **dict(zip(keys, vals))), ref=ref)
+
+    assert torch.autograd.gradcheck(f_par, pv, atol=1e-8, fast_mode=True)
+    assert torch.autograd.gradgradcheck(f_par, pv, atol=1e-8, fast_mode=True)
