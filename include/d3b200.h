@@ -29,6 +29,7 @@
 #ifndef D3B200_H
 #define D3B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -97,16 +98,24 @@ const char* d3b200_last_error(void);
 int d3b200_batch_max_atoms_f64(int order);
 int d3b200_batch_max_atoms_f32(int order);
 
+/* Scratch the batch entry points need (device memory, caller-allocated, no
+ * initialisation required): only the ATM term uses it, for the per-structure
+ * sqrt|C6_ij| matrix.  order: 0 = energy / vjp, 1 = hvp; atm: par->s9 != 0. */
+size_t d3b200_batch_workspace_bytes_f64(int nbatch, int natoms, int order, int atm);
+size_t d3b200_batch_workspace_bytes_f32(int nbatch, int natoms, int order, int atm);
+
 /* Atom-resolved D3(BJ)[+ATM] energies of a padded batch.
  * Replaces the body of `dftd3()`, reference disp.py:150-165 (+ disp.py:168-242).
  *   energy : `[nbatch][natoms]`, exact zeros on padding.
  * The ATM term is evaluated iff par->s9 != 0 (disp.py:234). */
 int d3b200_batch_energy_f64(int nbatch, int natoms, const int64_t* numbers,
                             const double* positions, const d3b200_model_f64* model,
-                            const d3b200_params* par, double* energy, void* stream);
+                            const d3b200_params* par, double* energy, void* workspace,
+                            size_t workspace_bytes, void* stream);
 int d3b200_batch_energy_f32(int nbatch, int natoms, const int64_t* numbers,
                             const float* positions, const d3b200_model_f32* model,
-                            const d3b200_params* par, float* energy, void* stream);
+                            const d3b200_params* par, float* energy, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* Vector-Jacobian product of the above: with L = sum_i g[i] * E[i],
  *   grad  : dL/dpositions `[nbatch][natoms][3]`
@@ -117,11 +126,13 @@ int d3b200_batch_energy_f32(int nbatch, int natoms, const int64_t* numbers,
 int d3b200_batch_vjp_f64(int nbatch, int natoms, const int64_t* numbers,
                          const double* positions, const d3b200_model_f64* model,
                          const d3b200_params* par, const double* g, double* energy,
-                         double* grad, double* pgrad, void* stream);
+                         double* grad, double* pgrad, void* workspace,
+                         size_t workspace_bytes, void* stream);
 int d3b200_batch_vjp_f32(int nbatch, int natoms, const int64_t* numbers,
                          const float* positions, const d3b200_model_f32* model,
                          const d3b200_params* par, const float* g, float* energy,
-                         float* grad, float* pgrad, void* stream);
+                         float* grad, float* pgrad, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* Second order: directional derivative of (E, grad, pgrad) along the tangent
  * (dpositions, dpar->{s6,s8,a1,a2,s9}).  Because grad = dL/dx, the tangent of
@@ -134,13 +145,14 @@ int d3b200_batch_hvp_f64(int nbatch, int natoms, const int64_t* numbers,
                          const d3b200_model_f64* model, const d3b200_params* par,
                          const d3b200_params* dpar, const double* g, double* grad,
                          double* pgrad, double* denergy, double* dgrad,
-                         double* dpgrad, void* stream);
+                         double* dpgrad, void* workspace, size_t workspace_bytes,
+                         void* stream);
 int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
                          const float* positions, const float* dpositions,
                          const d3b200_model_f32* model, const d3b200_params* par,
                          const d3b200_params* dpar, const float* g, float* grad,
                          float* pgrad, float* denergy, float* dgrad, float* dpgrad,
-                         void* stream);
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

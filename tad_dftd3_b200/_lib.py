@@ -47,12 +47,13 @@ _SIGNATURES = {
 }
 for _sfx in ("f64", "f32"):
     _SIGNATURES[f"d3b200_batch_energy_{_sfx}"] = (
-        [_I, _I, _P, _P, C.POINTER(Model), C.POINTER(Params), _P, _P], C.c_int)
+        [_I, _I, _P, _P, C.POINTER(Model), C.POINTER(Params), _P, _P, C.c_size_t, _P], C.c_int)
     _SIGNATURES[f"d3b200_batch_vjp_{_sfx}"] = (
-        [_I, _I, _P, _P, C.POINTER(Model), C.POINTER(Params), _P, _P, _P, _P, _P], C.c_int)
+        [_I, _I, _P, _P, C.POINTER(Model), C.POINTER(Params), _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int)
     _SIGNATURES[f"d3b200_batch_hvp_{_sfx}"] = (
         [_I, _I, _P, _P, _P, C.POINTER(Model), C.POINTER(Params), C.POINTER(Params),
-         _P, _P, _P, _P, _P, _P, _P], C.c_int)
+         _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int)
+    _SIGNATURES[f"d3b200_batch_workspace_bytes_{_sfx}"] = ([_I, _I, _I, _I], C.c_size_t)
 
 _lib = None
 

@@ -92,16 +92,34 @@ int fill_common(d3::MolArgs<S>& a, int nbatch, int natoms, const int64_t* number
   return D3B200_OK;
 }
 
+template <typename S>
+size_t workspace_bytes(int nbatch, int natoms, int atm) {
+  if (!atm || nbatch <= 0 || natoms <= 0) return 0;
+  return (size_t)nbatch * natoms * natoms * sizeof(S);
+}
+
+template <typename S>
+int set_workspace(d3::MolArgs<S>& a, const d3b200_params* par, void* workspace, size_t bytes) {
+  a.work = nullptr;
+  if (par->s9 == 0.0) return D3B200_OK;
+  size_t need = workspace_bytes<S>(a.nbatch, a.natoms, 1);
+  if (need && (!workspace || bytes < need))
+    return fail(D3B200_EINVAL, "ATM workspace too small%s: %ld < %ld bytes", "", (long)bytes, (long)need);
+  a.work = reinterpret_cast<S*>(workspace);
+  return D3B200_OK;
+}
+
 template <typename B>
 int energy_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
                 const typename ModelOf<B>::type* model, const d3b200_params* par,
-                B* energy, void* stream) {
+                B* energy, void* workspace, size_t wbytes, void* stream) {
   d3::MolArgs<B> a;
   int rc = fill_common<B, B>(a, nbatch, natoms, numbers, positions, model, par, nullptr);
   if (rc) return rc;
   if (!energy) return fail(D3B200_EINVAL, "null output%s");
   if (nbatch == 0 || natoms == 0) return D3B200_OK;
   a.energy = energy;
+  if ((rc = set_workspace(a, par, workspace, wbytes))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (par->s9 != 0.0) return launch<B, d3::kWantE | d3::kAtm>(a, s);
   return launch<B, d3::kWantE>(a, s);
@@ -110,7 +128,7 @@ int energy_impl(int nbatch, int natoms, const int64_t* numbers, const B* positio
 template <typename B>
 int vjp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
              const typename ModelOf<B>::type* model, const d3b200_params* par, const B* g,
-             B* energy, B* grad, B* pgrad, void* stream) {
+             B* energy, B* grad, B* pgrad, void* workspace, size_t wbytes, void* stream) {
   d3::MolArgs<B> a;
   int rc = fill_common<B, B>(a, nbatch, natoms, numbers, positions, model, par, nullptr);
   if (rc) return rc;
@@ -120,6 +138,7 @@ int vjp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
   a.energy = energy;
   a.grad = grad;
   a.pgrad = pgrad;
+  if ((rc = set_workspace(a, par, workspace, wbytes))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const bool atm = par->s9 != 0.0;
   using namespace d3;
@@ -139,7 +158,8 @@ template <typename B>
 int hvp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
              const B* dpositions, const typename ModelOf<B>::type* model,
              const d3b200_params* par, const d3b200_params* dpar, const B* g, B* grad,
-             B* pgrad, B* denergy, B* dgrad, B* dpgrad, void* stream) {
+             B* pgrad, B* denergy, B* dgrad, B* dpgrad, void* workspace, size_t wbytes,
+             void* stream) {
   using S = d3::Dual<B>;
   d3::MolArgs<S> a;
   int rc = fill_common<S, B>(a, nbatch, natoms, numbers, positions, model, par, dpar);
@@ -153,6 +173,7 @@ int hvp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
   a.denergy = denergy;
   a.dgrad = dgrad;
   a.dpgrad = dpgrad;
+  if ((rc = set_workspace(a, par, workspace, wbytes))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   using namespace d3;
   if (par->s9 != 0.0) return launch<S, kWantE | kWantG | kWantP | kAtm>(a, s);
@@ -173,28 +194,41 @@ int d3b200_batch_max_atoms_f32(int order) {
   return order ? max_atoms<d3::Dual<float>>() : max_atoms<float>();
 }
 
+size_t d3b200_batch_workspace_bytes_f64(int nbatch, int natoms, int order, int atm) {
+  return order ? workspace_bytes<d3::Dual<double>>(nbatch, natoms, atm)
+               : workspace_bytes<double>(nbatch, natoms, atm);
+}
+size_t d3b200_batch_workspace_bytes_f32(int nbatch, int natoms, int order, int atm) {
+  return order ? workspace_bytes<d3::Dual<float>>(nbatch, natoms, atm)
+               : workspace_bytes<float>(nbatch, natoms, atm);
+}
+
 int d3b200_batch_energy_f64(int nbatch, int natoms, const int64_t* numbers,
                             const double* positions, const d3b200_model_f64* model,
-                            const d3b200_params* par, double* energy, void* stream) {
-  return energy_impl<double>(nbatch, natoms, numbers, positions, model, par, energy, stream);
+                            const d3b200_params* par, double* energy, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return energy_impl<double>(nbatch, natoms, numbers, positions, model, par, energy, workspace, workspace_bytes, stream);
 }
 int d3b200_batch_energy_f32(int nbatch, int natoms, const int64_t* numbers,
                             const float* positions, const d3b200_model_f32* model,
-                            const d3b200_params* par, float* energy, void* stream) {
-  return energy_impl<float>(nbatch, natoms, numbers, positions, model, par, energy, stream);
+                            const d3b200_params* par, float* energy, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return energy_impl<float>(nbatch, natoms, numbers, positions, model, par, energy, workspace, workspace_bytes, stream);
 }
 
 int d3b200_batch_vjp_f64(int nbatch, int natoms, const int64_t* numbers,
                          const double* positions, const d3b200_model_f64* model,
                          const d3b200_params* par, const double* g, double* energy,
-                         double* grad, double* pgrad, void* stream) {
-  return vjp_impl<double>(nbatch, natoms, numbers, positions, model, par, g, energy, grad, pgrad, stream);
+                         double* grad, double* pgrad, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return vjp_impl<double>(nbatch, natoms, numbers, positions, model, par, g, energy, grad, pgrad, workspace, workspace_bytes, stream);
 }
 int d3b200_batch_vjp_f32(int nbatch, int natoms, const int64_t* numbers,
                          const float* positions, const d3b200_model_f32* model,
                          const d3b200_params* par, const float* g, float* energy,
-                         float* grad, float* pgrad, void* stream) {
-  return vjp_impl<float>(nbatch, natoms, numbers, positions, model, par, g, energy, grad, pgrad, stream);
+                         float* grad, float* pgrad, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return vjp_impl<float>(nbatch, natoms, numbers, positions, model, par, g, energy, grad, pgrad, workspace, workspace_bytes, stream);
 }
 
 int d3b200_batch_hvp_f64(int nbatch, int natoms, const int64_t* numbers,
@@ -202,18 +236,19 @@ int d3b200_batch_hvp_f64(int nbatch, int natoms, const int64_t* numbers,
                          const d3b200_model_f64* model, const d3b200_params* par,
                          const d3b200_params* dpar, const double* g, double* grad,
                          double* pgrad, double* denergy, double* dgrad,
-                         double* dpgrad, void* stream) {
+                         double* dpgrad, void* workspace, size_t workspace_bytes,
+                         void* stream) {
   return hvp_impl<double>(nbatch, natoms, numbers, positions, dpositions, model, par, dpar, g,
-                          grad, pgrad, denergy, dgrad, dpgrad, stream);
+                          grad, pgrad, denergy, dgrad, dpgrad, workspace, workspace_bytes, stream);
 }
 int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
                          const float* positions, const float* dpositions,
                          const d3b200_model_f32* model, const d3b200_params* par,
                          const d3b200_params* dpar, const float* g, float* grad,
                          float* pgrad, float* denergy, float* dgrad, float* dpgrad,
-                         void* stream) {
+                         void* workspace, size_t workspace_bytes, void* stream) {
   return hvp_impl<float>(nbatch, natoms, numbers, positions, dpositions, model, par, dpar, g,
-                         grad, pgrad, denergy, dgrad, dpgrad, stream);
+                         grad, pgrad, denergy, dgrad, dpgrad, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -100,6 +100,17 @@ template <typename T> D3_HD Dual<T> ex(Dual<T> a) {
   return Dual<T>(e, e * a.d);
 }
 
+D3_HD float lg(float a) { return logf(a); }
+D3_HD double lg(double a) { return log(a); }
+template <typename T> D3_HD Dual<T> lg(Dual<T> a) { return Dual<T>(lg(a.v), a.d / a.v); }
+
+D3_HD float ab(float a) { return fabsf(a); }
+D3_HD double ab(double a) { return fabs(a); }
+template <typename T> D3_HD Dual<T> ab(Dual<T> a) { return a.v < T(0) ? Dual<T>(-a.v, -a.d) : a; }
+
+// x^p for x > 0 and a plain (tangent-free) exponent
+template <typename S, typename B> D3_HD S pw(S x, B p) { return ex(p * lg(x)); }
+
 // conversions between working precision and the (float64) weight stage
 D3_HD double widen(float a) { return (double)a; }
 D3_HD double widen(double a) { return a; }

@@ -54,6 +54,7 @@ struct MolArgs {
   B* denergy;               // tangents (Dual only)
   B* dgrad;
   B* dpgrad;
+  S* work;                  // ATM scratch: sqrt|C6| per structure, [nbatch][N][N]
 };
 
 template <typename S> __device__ __forceinline__ S warp_sum(S v);
@@ -133,6 +134,29 @@ __device__ __forceinline__ void reference_weights(
   }
 }
 
+// One ATM term and its derivative with respect to a = r_ij^2
+// (reference damping/atm.py:93-153).
+//   a, b, c : r_ij^2, r_ik^2, r_jk^2      inva = 1/a
+//   c9      : s9 sqrt|C6_ij C6_ik C6_jk|  r0 = rs9^3 R_ij R_ik R_jk
+//   pexp    : (alp + 2) / 3
+template <typename S, typename B>
+__device__ __forceinline__ void atm_term(S a, S b, S c, S inva, S c9, S r0, B pexp, S& e, S& de_da) {
+  S r2 = a * b * c;
+  S r1inv = rsq(r2);
+  S r3inv = r1inv * r1inv * r1inv;
+  S r5inv = r3inv * (r1inv * r1inv);
+  S p = a + c - b, q = a - c + b, t = (c + b) - a;
+  S s = p * q * t;
+  S ang = B(0.375) * (s * r5inv) + r3inv;
+  S u = pw(r0 * r1inv, pexp);
+  S fd = rcp(B(1) + B(6) * u);
+  e = c9 * (ang * fd);
+  S ds = q * t + p * t - p * q;
+  S dang = B(0.375) * (ds * r5inv - B(2.5) * ((s * r5inv) * inva)) - B(1.5) * (r3inv * inva);
+  S dfd = (B(3) * pexp) * (u * (fd * fd) * inva);
+  de_da = c9 * (ang * dfd + fd * dang);
+}
+
 constexpr int kMolThreads = 256;  // CTA size cap; larger structures loop over i
 
 template <typename S, int FLAGS>
@@ -142,6 +166,7 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
   constexpr bool WANT_E = FLAGS & kWantE;
   constexpr bool WANT_G = FLAGS & kWantG;
   constexpr bool WANT_P = FLAGS & kWantP;
+  constexpr bool ATM = FLAGS & kAtm;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = A.natoms;
@@ -236,6 +261,7 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
   __syncthreads();
 
   const B eps = eps_of<B>();
+  S* hrow = ATM ? A.work + (size_t)b * N * N : nullptr;   // h[j*N + i] = sqrt|C6_ij|
 
   // ---------------------------------------------------------------- phase 1+2
   // CN_i = sum_j [r_ij <= 25] / (1 + exp(-kcn (rc_ij / r_ij - 1))), then weights
@@ -292,12 +318,17 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
         if (j == i) continue;
         S dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
         S r2 = dx * dx + dy * dy + dz * dz;
-        if (val(r2) > A.cutoff2) continue;
-        if (val(r2) < eps) r2 = S(eps);
+        if (!ATM && val(r2) > A.cutoff2) continue;
         const S* wj = sw + 8 * j;
         S c6 = U[0] * wj[0];
 #pragma unroll
         for (int a = 1; a < kNRef; ++a) c6 += U[a] * wj[a];
+        if (ATM) {
+          // the three-body term needs C6 of every pair (r_ik is not cut off)
+          hrow[(size_t)j * N + i] = sqr(ab(c6));
+          if (val(r2) > A.cutoff2) continue;
+        }
+        if (val(r2) < eps) r2 = S(eps);
         S qq = q3_i * sq[j];
         S r0 = sa_i * ssq[j] + A.a2;
         S r02 = r0 * r0;
@@ -349,6 +380,122 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
   }
   __syncthreads();
 
+  // ---------------------------------------------------------------- phase 3b
+  // Axilrod-Teller-Muto term (damping/atm.py:86-155) in ordered form:
+  //   E_i = 1/6 sum_j sum_k [r_ij<=c][r_jk<=c] e_ijk        (no test on r_ik)
+  // Thread i walks ordered (j, k); e_ijk is symmetric, so with
+  //   w_ijk = g_i m_jk(m_ij+m_ik) + g_j m_ik(m_ij+m_jk) + g_k m_ij(m_ik+m_jk)
+  //   dL/dx_i   = 1/6 sum_j [ sum_k w de/d(r_ij^2) ] 2 (x_i - x_j)
+  //   dL/dCN_i += 1/6 sum_j [ sum_k w e ] / (2 C6_ij) dC6_ij/dCN_i
+  // everything accumulates in registers of the owning thread.
+  S p_s9 = S(B(0));
+  if (ATM) {
+    const B pexp = (val(A.alp) + B(2)) / B(3);
+    const S rs93 = A.rs9 * A.rs9 * A.rs9;
+    const B sixth = B(1) / B(6);
+    for (int i = t; i < n; i += nt) {
+      const S xi = sx[i], yi = sy[i], zi = sz[i];
+      const int Zi = sZ[i];
+      const int oi = sperm[i];
+      const B gi = sg[i];
+      S wi[kNRef], dwi[kNRef];
+#pragma unroll
+      for (int a = 0; a < kNRef; ++a) { wi[a] = sw[8 * i + a]; dwi[a] = sdw[8 * i + a]; }
+      S e_atm = S(B(0)), gx = S(B(0)), gy = S(B(0)), gz = S(B(0)), decn = S(B(0));
+      for (int gj = 0; gj < ng; ++gj) {
+        const int Zj = gZ[gj];
+        S U[kNRef], Ud[kNRef];
+        if (WANT_G) {
+          const B* __restrict__ K = A.refc6 + ((size_t)Zi * kMaxZ + Zj) * (kNRef * kNRef);
+#pragma unroll
+          for (int bb = 0; bb < kNRef; ++bb) { U[bb] = S(B(0)); Ud[bb] = S(B(0)); }
+#pragma unroll
+          for (int a = 0; a < kNRef; ++a) {
+#pragma unroll
+            for (int bb = 0; bb < kNRef; ++bb) {
+              B k = __ldg(K + a * kNRef + bb);
+              U[bb] += wi[a] * k;
+              Ud[bb] += dwi[a] * k;
+            }
+          }
+        }
+        const B rij_tab = A.rvdw_mode == 1 ? A.rvdw[Zi * kMaxZ + Zj] : B(0);
+        for (int j = gstart[gj]; j < gstart[gj + 1]; ++j) {
+          if (j == i) continue;
+          const S xj = sx[j], yj = sy[j], zj = sz[j];
+          S dx = xi - xj, dy = yi - yj, dz = zi - zj;
+          S a = dx * dx + dy * dy + dz * dz;
+          if (val(a) < eps) a = S(eps);
+          const bool mij = val(a) <= A.cutoff2;
+          const S inva = rcp(a);
+          const S hij = hrow[(size_t)j * N + i];
+          const int oj = sperm[j];
+          const B gj_ = sg[j];
+          const B Rij = A.rvdw_mode == 1 ? rij_tab : A.rvdw[((size_t)b * N + oi) * N + oj];
+          S Fj = S(B(0)), Gj = S(B(0)), Ej = S(B(0));
+          for (int gk = 0; gk < ng; ++gk) {
+            const int Zk = gZ[gk];
+            const B rik_tab = A.rvdw_mode == 1 ? A.rvdw[Zi * kMaxZ + Zk] : B(0);
+            const B rjk_tab = A.rvdw_mode == 1 ? A.rvdw[Zj * kMaxZ + Zk] : B(0);
+            for (int k = gstart[gk]; k < gstart[gk + 1]; ++k) {
+              if (k == i || k == j) continue;
+              const S xk = sx[k], yk = sy[k], zk = sz[k];
+              S ex_ = xi - xk, ey = yi - yk, ez = zi - zk;
+              S bq = ex_ * ex_ + ey * ey + ez * ez;
+              S fx = xj - xk, fy = yj - yk, fz = zj - zk;
+              S cq = fx * fx + fy * fy + fz * fz;
+              if (val(bq) < eps) bq = S(eps);
+              if (val(cq) < eps) cq = S(eps);
+              const bool mik = val(bq) <= A.cutoff2, mjk = val(cq) <= A.cutoff2;
+              if ((int)mij + (int)mik + (int)mjk < 2) continue;
+              B Rik, Rjk;
+              if (A.rvdw_mode == 1) { Rik = rik_tab; Rjk = rjk_tab; }
+              else {
+                const int ok = sperm[k];
+                Rik = A.rvdw[((size_t)b * N + oi) * N + ok];
+                Rjk = A.rvdw[((size_t)b * N + oj) * N + ok];
+              }
+              S c9 = A.s9 * (hij * (hrow[(size_t)k * N + i] * hrow[(size_t)k * N + j]));
+              S r0 = rs93 * (Rij * Rik * Rjk);
+              S e, de;
+              atm_term<S, B>(a, bq, cq, inva, c9, r0, pexp, e, de);
+              if (mij && mjk) Ej += e;
+              if (WANT_G) {
+                B w = gi * (mjk ? B((int)mij + (int)mik) : B(0))
+                    + gj_ * (mik ? B((int)mij + (int)mjk) : B(0))
+                    + sg[k] * (mij ? B((int)mik + (int)mjk) : B(0));
+                Fj += w * de;
+                Gj += w * e;
+              }
+            }
+          }
+          e_atm += Ej;
+          if (WANT_G) {
+            S f = (B(2) * sixth) * Fj;
+            gx += f * dx; gy += f * dy; gz += f * dz;
+            // dC6_ij/dCN_i / (2 C6_ij);  C6_ij = U . w_j
+            const S* wj = sw + 8 * j;
+            S c6 = U[0] * wj[0], dc6 = Ud[0] * wj[0];
+#pragma unroll
+            for (int aa = 1; aa < kNRef; ++aa) { c6 += U[aa] * wj[aa]; dc6 += Ud[aa] * wj[aa]; }
+            decn += (B(0.5) * sixth) * (Gj * (dc6 * rcp(c6)));
+          }
+        }
+      }
+      S e3 = sixth * e_atm;
+      if (WANT_E) {
+        size_t o = (size_t)b * N + oi;
+        if (A.energy) A.energy[o] += val(e3);
+        if (DUAL && A.denergy) A.denergy[o] += tan_of(e3);
+      }
+      if (WANT_G) {
+        sdecn[i] += decn; sgx[i] += gx; sgy[i] += gy; sgz[i] += gz;
+        if (WANT_P) p_s9 += gi * (e3 * rcp(A.s9));
+      }
+    }
+    __syncthreads();
+  }
+
   // ---------------------------------------------------------------- phase 4
   // dL/dx_i += sum_j (dL/dCN_i + dL/dCN_j) df_ij/dx_i,
   // df/dx_i = -kcn rc r^-3 f (1 - f) (x_i - x_j)
@@ -378,23 +525,19 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
   }
 
   if (WANT_P) {
-    S v[4] = {p_s6, p_s8, p_a1, p_a2};
+    S v[5] = {p_s6, p_s8, p_a1, p_a2, p_s9};
     const int lane = t & 31, wid = t >> 5, nw = (nt + 31) >> 5;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 5; ++k) {
       S s = warp_sum<S>(v[k]);
       if (lane == 0) sred[wid * 5 + k] = s;
     }
     __syncthreads();
-    if (t < 4) {
+    if (t < 5) {
       S s = S(B(0));
       for (int w = 0; w < nw; ++w) s += sred[w * 5 + t];
       if (A.pgrad) A.pgrad[(size_t)b * 5 + t] = val(s);
       if (DUAL && A.dpgrad) A.dpgrad[(size_t)b * 5 + t] = tan_of(s);
-    }
-    if (t == 4) {
-      if (A.pgrad) A.pgrad[(size_t)b * 5 + 4] = B(0);
-      if (DUAL && A.dpgrad) A.dpgrad[(size_t)b * 5 + 4] = B(0);
     }
   }
 }

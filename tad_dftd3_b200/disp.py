@@ -22,7 +22,7 @@ from . import data, defaults
 from .damping import rational_damping
 from .model import gaussian_weight
 from .ncoord import exp_count
-from .ops import NPAR, Settings, d3_energy
+from .ops import Settings, d3_energy
 from .reference import Reference
 
 __all__ = ["dftd3", "dispersion", "dispersion2", "dispersion3"]
@@ -35,28 +35,40 @@ def _is_functorch(x: Tensor) -> bool:
     return bool(f.is_batchedtensor(x) or f.is_gradtrackingtensor(x))
 
 
-_checked = weakref.WeakKeyDictionary()
+def _plain(t: Tensor) -> Tensor:
+    """Strip functorch grad-tracking wrappers from a CONSTANT tensor before it
+    is cached (tensors created inside jacrev/vmap are wrapped at the live
+    levels; a cached wrapper would outlive its level)."""
+    f = torch._C._functorch
+    while f.is_gradtrackingtensor(t):
+        t = f.get_unwrapped(t)
+    if f.is_batchedtensor(t):
+        raise ValueError("model tables must not be batched under vmap")
+    return t
+
+
+_checked: dict = {}  # id(tensor) -> (weakref, version)
 
 
 def _check_numbers(numbers: Tensor) -> None:
     """ValueError for Z >= 104 (disp.py:130-135); one device sync per distinct tensor."""
     if _is_functorch(numbers) or numbers.numel() == 0:
         return
-    try:
-        if _checked.get(numbers) == numbers._version:
-            return
-    except TypeError:  # pragma: no cover
-        pass
-    if int(torch.max(numbers)) >= defaults.MAX_ELEMENT:
+    key = id(numbers)
+    hit = _checked.get(key)
+    if hit is not None and hit[0]() is numbers and hit[1] == numbers._version:
+        return
+    lo, hi = torch.aminmax(numbers)
+    if int(hi) >= defaults.MAX_ELEMENT:
         raise ValueError(
             f"No D3 parameters available for Z > {defaults.MAX_ELEMENT - 1} ({_Z2S_104})."
         )
-    if int(torch.min(numbers)) < 0:
+    if int(lo) < 0:
         raise ValueError("Atomic numbers must be non-negative.")
-    try:
-        _checked[numbers] = numbers._version
-    except TypeError:  # pragma: no cover
-        pass
+    if len(_checked) > 256:
+        for k in [k for k, v in _checked.items() if v[0]() is None]:
+            del _checked[k]
+    _checked[key] = (weakref.ref(numbers), numbers._version)
 
 
 _table_cache: dict = {}
@@ -66,7 +78,7 @@ def _element_table(name: str, dtype, device) -> Tensor:
     key = (name, dtype, str(device))
     t = _table_cache.get(key)
     if t is None:
-        t = getattr(data, name)(dtype=dtype, device=device).contiguous()
+        t = _plain(getattr(data, name)(dtype=dtype, device=device)).contiguous()
         _table_cache[key] = t
     return t
 
@@ -155,13 +167,13 @@ def dftd3(
             raise ValueError(
                 f"Shape of covalent radii {tuple(rcov.shape)} is not consistent with ({tuple(numbers.shape)})."
             )
-        rcov_t, rcov_pe = rcov.detach().to(device=device, dtype=dtype), False
+        rcov_t, rcov_pe = rcov, False
     if r4r2 is None:
         r4r2_t, r4r2_pe = _element_table("R4R2", dtype, device), True
     else:
         if r4r2.shape != numbers.shape:
             raise ValueError("Shape of expectation values is not consistent with atomic numbers.")
-        r4r2_t, r4r2_pe = r4r2.detach().to(device=device, dtype=dtype), False
+        r4r2_t, r4r2_pe = r4r2, False
 
     atm = _atm_requested(param)
     rvdw_t, rvdw_mode = None, 0
@@ -171,11 +183,10 @@ def dftd3(
         else:
             if rvdw.shape != (*numbers.shape, numbers.shape[-1]):
                 raise ValueError("Shape of van-der-Waals radii is not consistent with atomic numbers.")
-            rvdw_t, rvdw_mode = rvdw.detach().to(device=device, dtype=dtype), 2
+            rvdw_t, rvdw_mode = rvdw, 2
 
     st = Settings(
-        rcov=rcov_t, r4r2=r4r2_t, rcov_per_element=rcov_pe, r4r2_per_element=r4r2_pe,
-        refcn=refcn, refc6=refc6, rvdw=rvdw_t, rvdw_mode=rvdw_mode,
+        rcov_per_element=rcov_pe, r4r2_per_element=r4r2_pe, rvdw_mode=rvdw_mode,
         cutoff=defaults.D3_DISP_CUTOFF if cutoff is None else _scalar(cutoff),
         cn_cutoff=defaults.D3_CN_CUTOFF, kcn=defaults.D3_KCN,
         alp=_scalar(param.get("alp", defaults.ALP)),
@@ -183,9 +194,8 @@ def dftd3(
     p = _param_vector(param, dtype)
     if not atm:
         # s9 present but zero (or absent): two-body only, and no gradient to s9
-        mask = torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0], dtype=dtype, device=p.device)
-        p = p * mask
-    return d3_energy(numbers, positions, p, st)
+        p = p * torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0], dtype=dtype, device=p.device)
+    return d3_energy(numbers, positions, p, rcov_t, r4r2_t, rvdw_t, refcn, refc6, st)
 
 
 _default_refs: dict = {}

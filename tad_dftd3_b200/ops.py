@@ -5,9 +5,9 @@ Three levels, each a new-style Function (`forward` without ctx +
 `setup_context`) with a manual `vmap` rule, mirroring the reference's only
 custom op (`AtomicC6_V2`, model/c6.py:401-480):
 
-    D3Energy : (numbers, x, p)        -> E[..., N]          d3b200_batch_energy_*
-    D3Vjp    : (numbers, x, p, g)     -> dL/dx, dL/dp       d3b200_batch_vjp_*
-    D3Hvp    : (numbers, x, p, g, vx, vp) -> tangents       d3b200_batch_hvp_*
+    D3Energy : (numbers, x, p, tables...)          -> E[..., N]      d3b200_batch_energy_*
+    D3Vjp    : (numbers, x, p, g, tables...)       -> dL/dx, dL/dp   d3b200_batch_vjp_*
+    D3Hvp    : (numbers, x, p, g, vx, vp, tables...) -> tangents     d3b200_batch_hvp_*
 
 `D3Energy.backward` calls `D3Vjp`, `D3Vjp.backward` calls `D3Hvp`, so
 `.backward()`, `autograd.grad`, `gradcheck`, `gradgradcheck`,
@@ -15,14 +15,16 @@ custom op (`AtomicC6_V2`, model/c6.py:401-480):
 `vmap(jacrev(jacrev))` all run on the CUDA kernels: torch autograd never
 differentiates through the pair sums.  Third derivatives are not provided.
 
-`p` is the 5-vector (s6, s8, a1, a2, s9).  All tensor arguments may carry
+`p` is the 5-vector (s6, s8, a1, a2, s9).  Every tensor is passed as a
+Function argument (functorch unwraps arguments level by level; tensors hidden
+inside Python objects would stay wrapped).  All per-structure tensors may carry
 arbitrary leading batch dimensions; raw pointers are only taken inside
 `forward`, the `vmap` rules only move/expand dimensions and re-dispatch.
 """
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional
 
 import torch
@@ -35,24 +37,18 @@ __all__ = ["Settings", "D3Energy", "D3Vjp", "D3Hvp", "d3_energy"]
 NPAR = 5
 
 
-@dataclass
+@dataclass(frozen=True)
 class Settings:
-    """Non-differentiable inputs of one `dftd3` call (static under vmap)."""
+    """Plain-Python (non-tensor) settings of one `dftd3` call; static under vmap."""
 
-    rcov: Tensor
-    r4r2: Tensor
     rcov_per_element: bool
     r4r2_per_element: bool
-    refcn: Tensor
-    refc6: Tensor
-    rvdw: Optional[Tensor] = None
-    rvdw_mode: int = 0
+    rvdw_mode: int = 0  # 0 none, 1 element-pair table, 2 dense [..., N, N]
     cutoff: float = 50.0
     cn_cutoff: float = 25.0
     kcn: float = 16.0
     rs9: float = 1.3333333730697632  # float32(4/3), reference disp.py:312
     alp: float = 14.0
-    keep: list = field(default_factory=list)
 
 
 def _sfx(dtype: torch.dtype) -> str:
@@ -67,19 +63,6 @@ def _ptr(t: Optional[Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _model(st: Settings, nflat: int, natoms: int, dtype, device) -> _lib.Model:
-    m = _lib.Model()
-    m.rcov = st.rcov.data_ptr()
-    m.r4r2 = st.r4r2.data_ptr()
-    m.rcov_per_element = int(st.rcov_per_element)
-    m.r4r2_per_element = int(st.r4r2_per_element)
-    m.refcn = st.refcn.data_ptr()
-    m.refc6 = st.refc6.data_ptr()
-    m.rvdw = st.rvdw.data_ptr() if st.rvdw is not None else None
-    m.rvdw_mode = int(st.rvdw_mode)
-    return m
-
-
 def _params(vals, st: Settings) -> _lib.Params:
     p = _lib.Params()
     p.s6, p.s8, p.a1, p.a2, p.s9 = (float(v) for v in vals)
@@ -88,145 +71,174 @@ def _params(vals, st: Settings) -> _lib.Params:
     return p
 
 
-def _flatten(numbers: Tensor, positions: Tensor):
-    if positions.device.type != "cuda":
-        raise RuntimeError(
-            "tad_dftd3_b200 runs on CUDA devices only (there is no CPU path); "
-            f"got positions on {positions.device}"
-        )
-    lead = positions.shape[:-2]
-    n = positions.shape[-2]
-    x = positions.detach().reshape(-1, n, 3).contiguous()
-    z = numbers.detach().expand(*lead, n).reshape(-1, n).contiguous()
-    if z.dtype != torch.int64:
-        z = z.to(torch.int64)
-    return lead, n, z, x
-
-
-def _per_atom(t: Tensor, st_flag: bool, lead, n, nflat):
-    """Per-atom model arrays follow the batch shape of `numbers`."""
-    if st_flag:
-        return t
-    return t.detach().expand(*lead, n).reshape(nflat, n).contiguous()
-
-
-def _prep_settings(st: Settings, lead, n, nflat, dtype, device) -> Settings:
-    rcov = _per_atom(st.rcov, st.rcov_per_element, lead, n, nflat)
-    r4r2 = _per_atom(st.r4r2, st.r4r2_per_element, lead, n, nflat)
-    rvdw = st.rvdw
-    if st.rvdw_mode == 2 and rvdw is not None:
-        rvdw = rvdw.detach().expand(*lead, n, n).reshape(nflat, n, n).contiguous()
-    if rcov is st.rcov and r4r2 is st.r4r2 and rvdw is st.rvdw:
-        return st
-    return Settings(rcov, r4r2, st.rcov_per_element, st.r4r2_per_element, st.refcn, st.refc6,
-                    rvdw, st.rvdw_mode, st.cutoff, st.cn_cutoff, st.kcn, st.rs9, st.alp)
-
-
 def _pvals(p: Tensor):
     return p.detach().reshape(-1).tolist()
 
 
-def _run_energy(numbers, positions, p, st):
-    lead, n, z, x = _flatten(numbers, positions)
-    nflat = z.shape[0]
-    out = torch.empty(nflat, n, dtype=x.dtype, device=x.device)
-    if nflat and n:
-        st2 = _prep_settings(st, lead, n, nflat, x.dtype, x.device)
-        model = _model(st2, nflat, n, x.dtype, x.device)
-        par = _params(_pvals(p), st)
-        fn = getattr(_lib.lib(), f"d3b200_batch_energy_{_sfx(x.dtype)}")
-        with torch.cuda.device(x.device):
-            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(fn(nflat, n, _ptr(z), _ptr(x), C.byref(model), C.byref(par), _ptr(out), stream))
-    return out.reshape(*lead, n)
+class _Call:
+    """Flattened, contiguous device views of one call + the C structs."""
+
+    def __init__(self, numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st: Settings, order: int):
+        if positions.device.type != "cuda":
+            raise RuntimeError(
+                "tad_dftd3_b200 runs on CUDA devices only (there is no CPU path); "
+                f"got positions on {positions.device}"
+            )
+        self.lead = lead = positions.shape[:-2]
+        self.n = n = positions.shape[-2]
+        self.dtype, self.device = positions.dtype, positions.device
+        self.x = positions.detach().reshape(-1, n, 3).contiguous()
+        z = numbers.detach().expand(*lead, n).reshape(-1, n)
+        self.z = (z if z.dtype == torch.int64 else z.to(torch.int64)).contiguous()
+        self.nflat = nflat = self.x.shape[0]
+        self.st = st
+        dd = dict(device=self.device, dtype=self.dtype)
+        self.rcov = rcov.detach().to(**dd).contiguous() if st.rcov_per_element else \
+            rcov.detach().to(**dd).expand(*lead, n).reshape(nflat, n).contiguous()
+        self.r4r2 = r4r2.detach().to(**dd).contiguous() if st.r4r2_per_element else \
+            r4r2.detach().to(**dd).expand(*lead, n).reshape(nflat, n).contiguous()
+        self.rvdw = None
+        if st.rvdw_mode == 1:
+            self.rvdw = rvdw.detach().to(**dd).contiguous()
+        elif st.rvdw_mode == 2:
+            self.rvdw = rvdw.detach().to(**dd).expand(*lead, n, n).reshape(nflat, n, n).contiguous()
+        self.refcn = refcn.detach().to(**dd).contiguous()
+        self.refc6 = refc6.detach().to(**dd).contiguous()
+        self.pvals = _pvals(p)
+        self.par = _params(self.pvals, st)
+        m = _lib.Model()
+        m.rcov, m.r4r2 = self.rcov.data_ptr(), self.r4r2.data_ptr()
+        m.rcov_per_element, m.r4r2_per_element = int(st.rcov_per_element), int(st.r4r2_per_element)
+        m.refcn, m.refc6 = self.refcn.data_ptr(), self.refc6.data_ptr()
+        m.rvdw = self.rvdw.data_ptr() if self.rvdw is not None else None
+        m.rvdw_mode = int(st.rvdw_mode)
+        self.model = m
+        self.sfx = _sfx(self.dtype)
+        # ATM scratch (sqrt|C6| matrix per structure)
+        self.work = None
+        self.work_bytes = 0
+        if self.par.s9 != 0.0 and nflat and n:
+            fn = getattr(_lib.lib(), f"d3b200_batch_workspace_bytes_{self.sfx}")
+            self.work_bytes = int(fn(nflat, n, order, 1))
+            self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=self.device)
+
+    def per_atom(self, t: Tensor, trailing=()):
+        return t.detach().to(device=self.device, dtype=self.dtype).expand(*self.lead, self.n, *trailing) \
+            .reshape(self.nflat, self.n, *trailing).contiguous()
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def new(self, *shape, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(*shape, dtype=self.dtype, device=self.device)
 
 
-def _run_vjp(numbers, positions, p, g, st, want_p: bool):
-    lead, n, z, x = _flatten(numbers, positions)
-    nflat = z.shape[0]
-    grad = torch.empty(nflat, n, 3, dtype=x.dtype, device=x.device)
-    pgrad = torch.zeros(nflat, NPAR, dtype=x.dtype, device=x.device)
-    if nflat and n:
-        gg = g.detach().to(x.dtype).expand(*lead, n).reshape(nflat, n).contiguous()
-        st2 = _prep_settings(st, lead, n, nflat, x.dtype, x.device)
-        model = _model(st2, nflat, n, x.dtype, x.device)
-        par = _params(_pvals(p), st)
-        fn = getattr(_lib.lib(), f"d3b200_batch_vjp_{_sfx(x.dtype)}")
-        with torch.cuda.device(x.device):
-            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(fn(nflat, n, _ptr(z), _ptr(x), C.byref(model), C.byref(par), _ptr(gg), None,
-                          _ptr(grad), _ptr(pgrad) if want_p else None, stream))
-    return grad.reshape(*lead, n, 3), pgrad.reshape(*lead, NPAR)
+def _run_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st):
+    c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0)
+    out = c.new(c.nflat, c.n)
+    if c.nflat and c.n:
+        fn = getattr(_lib.lib(), f"d3b200_batch_energy_{c.sfx}")
+        with torch.cuda.device(c.device):
+            _lib.check(fn(c.nflat, c.n, _ptr(c.z), _ptr(c.x), C.byref(c.model), C.byref(c.par),
+                          _ptr(out), _ptr(c.work), C.c_size_t(c.work_bytes), c.stream()))
+    return out.reshape(*c.lead, c.n)
 
 
-def _run_hvp(numbers, positions, p, g, vx, vp, st):
-    lead, n, z, x = _flatten(numbers, positions)
-    nflat = z.shape[0]
-    de = torch.zeros(nflat, n, dtype=x.dtype, device=x.device)
-    dgrad = torch.zeros(nflat, n, 3, dtype=x.dtype, device=x.device)
-    dpgrad = torch.zeros(nflat, NPAR, dtype=x.dtype, device=x.device)
-    if nflat and n:
-        gg = g.detach().to(x.dtype).expand(*lead, n).reshape(nflat, n).contiguous()
-        dx = vx.detach().to(x.dtype).expand(*lead, n, 3).reshape(nflat, n, 3).contiguous()
-        st2 = _prep_settings(st, lead, n, nflat, x.dtype, x.device)
-        model = _model(st2, nflat, n, x.dtype, x.device)
-        par = _params(_pvals(p), st)
-        dvals = _pvals(vp)
-        dpar = _params(dvals, st)
-        fn = getattr(_lib.lib(), f"d3b200_batch_hvp_{_sfx(x.dtype)}")
-        with torch.cuda.device(x.device):
-            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(fn(nflat, n, _ptr(z), _ptr(x), _ptr(dx), C.byref(model), C.byref(par),
-                          C.byref(dpar), _ptr(gg), None, None, _ptr(de), _ptr(dgrad), _ptr(dpgrad),
-                          stream))
-    return de.reshape(*lead, n), dgrad.reshape(*lead, n, 3), dpgrad.reshape(*lead, NPAR)
+def _run_vjp(numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6, st, want_p: bool):
+    c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0)
+    grad = c.new(c.nflat, c.n, 3)
+    pgrad = c.new(c.nflat, NPAR, zero=True)
+    if c.nflat and c.n:
+        gg = c.per_atom(g)
+        fn = getattr(_lib.lib(), f"d3b200_batch_vjp_{c.sfx}")
+        with torch.cuda.device(c.device):
+            _lib.check(fn(c.nflat, c.n, _ptr(c.z), _ptr(c.x), C.byref(c.model), C.byref(c.par),
+                          _ptr(gg), None, _ptr(grad), _ptr(pgrad) if want_p else None,
+                          _ptr(c.work), C.c_size_t(c.work_bytes), c.stream()))
+    return grad.reshape(*c.lead, c.n, 3), pgrad.reshape(*c.lead, NPAR)
+
+
+def _run_hvp(numbers, positions, p, g, vx, vp, rcov, r4r2, rvdw, refcn, refc6, st):
+    c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 1)
+    de = c.new(c.nflat, c.n, zero=True)
+    dgrad = c.new(c.nflat, c.n, 3, zero=True)
+    dpgrad = c.new(c.nflat, NPAR, zero=True)
+    if c.nflat and c.n:
+        gg = c.per_atom(g)
+        dx = c.per_atom(vx, (3,))
+        dpar = _params(_pvals(vp), st)
+        fn = getattr(_lib.lib(), f"d3b200_batch_hvp_{c.sfx}")
+        with torch.cuda.device(c.device):
+            _lib.check(fn(c.nflat, c.n, _ptr(c.z), _ptr(c.x), _ptr(dx), C.byref(c.model),
+                          C.byref(c.par), C.byref(dpar), _ptr(gg), None, None, _ptr(de),
+                          _ptr(dgrad), _ptr(dpgrad), _ptr(c.work), C.c_size_t(c.work_bytes),
+                          c.stream()))
+    return de.reshape(*c.lead, c.n), dgrad.reshape(*c.lead, c.n, 3), dpgrad.reshape(*c.lead, NPAR)
 
 
 # --------------------------------------------------------------------------
-# vmap helper: move batch dims to the front / expand unbatched arguments
+# vmap helpers
 # --------------------------------------------------------------------------
-def _batched_params(in_dims, args, per_structure) -> bool:
-    return any(isinstance(a, Tensor) and d is not None and k not in per_structure
-               for k, (a, d) in enumerate(zip(args, in_dims)))
+def _roles(names, st: Settings):
+    """Role of every positional argument: 's' per-structure tensor, 'p' parameter
+    vector, 'c' constant table (must be unbatched), '-' non-tensor."""
+    role = {}
+    for k, name in enumerate(names):
+        if name in ("numbers", "positions", "g", "vx"):
+            role[k] = "s"
+        elif name in ("p", "vp"):
+            role[k] = "p"
+        elif name == "rcov":
+            role[k] = "c" if st.rcov_per_element else "s"
+        elif name == "r4r2":
+            role[k] = "c" if st.r4r2_per_element else "s"
+        elif name == "rvdw":
+            role[k] = "s" if st.rvdw_mode == 2 else "c"
+        elif name in ("refcn", "refc6"):
+            role[k] = "c"
+        else:
+            role[k] = "-"
+    return role
 
 
-def _loop(fn, info, in_dims, args):
-    """Fallback when a parameter vector is batched: one launch per element."""
-    outs = []
-    for c in range(info.batch_size):
-        sl = [a.select(d, c) if (isinstance(a, Tensor) and d is not None) else a
-              for a, d in zip(args, in_dims)]
-        outs.append(fn(*sl))
-    if isinstance(outs[0], tuple):
-        return tuple(torch.stack(o) for o in zip(*outs)), tuple(0 for _ in outs[0])
-    return torch.stack(outs), 0
-
-
-def _front(info, in_dims, args, per_structure):
-    """Returns args with a leading dim of size info.batch_size on every
-    per-structure tensor (index in `per_structure`); other tensors must be
-    unbatched."""
-    out = []
+def _vmap(fn, names, info, in_dims, args):
+    st = args[names.index("st")]
+    role = _roles(names, st)
+    batched_p = any(role[k] == "p" and isinstance(a, Tensor) and d is not None
+                    for k, (a, d) in enumerate(zip(args, in_dims)))
+    if batched_p:
+        # one parameter set per launch: loop over the batch (parameter Hessians
+        # under jacrev only; positions-only transforms never come here)
+        outs = []
+        for c in range(info.batch_size):
+            sl = [a.select(d, c) if (isinstance(a, Tensor) and d is not None) else a
+                  for a, d in zip(args, in_dims)]
+            outs.append(fn(*sl))
+        if isinstance(outs[0], tuple):
+            return tuple(torch.stack(o) for o in zip(*outs)), tuple(0 for _ in outs[0])
+        return torch.stack(outs), 0
+    new = []
     for k, (a, d) in enumerate(zip(args, in_dims)):
         if not isinstance(a, Tensor):
             if d is not None:
                 raise ValueError("non-tensor arguments must be static under vmap")
-            out.append(a)
-            continue
-        if k in per_structure:
-            if d is None:
-                a = a.unsqueeze(0).expand(info.batch_size, *a.shape)
-            else:
-                a = a.movedim(d, 0)
-            out.append(a)
+            new.append(a)
+        elif role[k] == "s":
+            new.append(a.unsqueeze(0).expand(info.batch_size, *a.shape) if d is None else a.movedim(d, 0))
         else:
             if d is not None:
-                raise ValueError(
-                    "damping parameters must not be batched under vmap "
-                    "(one parameter set per call)"
-                )
-            out.append(a)
-    return out
+                raise ValueError(f"`{names[k]}` must not be batched under vmap")
+            new.append(a)
+    out = fn(*new)
+    if isinstance(out, tuple):
+        return out, tuple(0 for _ in out)
+    return out, 0
+
+
+_E_NAMES = ("numbers", "positions", "p", "rcov", "r4r2", "rvdw", "refcn", "refc6", "st")
+_V_NAMES = ("numbers", "positions", "p", "g", "rcov", "r4r2", "rvdw", "refcn", "refc6", "st", "want_p")
+_H_NAMES = ("numbers", "positions", "p", "g", "vx", "vp", "rcov", "r4r2", "rvdw", "refcn", "refc6", "st")
 
 
 class D3Energy(torch.autograd.Function):
@@ -235,34 +247,32 @@ class D3Energy(torch.autograd.Function):
     generate_vmap_rule = False
 
     @staticmethod
-    def forward(numbers: Tensor, positions: Tensor, p: Tensor, st: Settings) -> Tensor:
-        return _run_energy(numbers, positions, p, st)
+    def forward(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st):
+        return _run_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st)
 
     @staticmethod
     def setup_context(ctx, inputs, output):
-        numbers, positions, p, st = inputs
-        ctx.save_for_backward(numbers, positions, p)
+        numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st = inputs
+        ctx.save_for_backward(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6)
         ctx.st = st
 
     @staticmethod
     def backward(ctx, gE):
-        numbers, positions, p = ctx.saved_tensors
+        numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6 = ctx.saved_tensors
         need_x, need_p = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        out = [None] * 9
         if not (need_x or need_p):
-            return None, None, None, None
-        gx, gp = D3Vjp.apply(numbers, positions, p, gE, ctx.st, bool(need_p))
-        gp_tot = None
+            return tuple(out)
+        gx, gp = D3Vjp.apply(numbers, positions, p, gE, rcov, r4r2, rvdw, refcn, refc6, ctx.st, bool(need_p))
+        if need_x:
+            out[1] = gx
         if need_p:
-            gp_tot = gp.reshape(-1, NPAR).sum(0).to(device=p.device, dtype=p.dtype)
-        return None, (gx if need_x else None), gp_tot, None
+            out[2] = gp.reshape(-1, NPAR).sum(0).to(device=p.device, dtype=p.dtype)
+        return tuple(out)
 
     @staticmethod
-    def vmap(info, in_dims, numbers, positions, p, st):
-        args = (numbers, positions, p, st)
-        if _batched_params(in_dims, args, {0, 1}):
-            return _loop(D3Energy.apply, info, in_dims, args)
-        numbers, positions, p, st = _front(info, in_dims, args, {0, 1})
-        return D3Energy.apply(numbers, positions, p, st), 0
+    def vmap(info, in_dims, *args):
+        return _vmap(D3Energy.apply, _E_NAMES, info, in_dims, args)
 
 
 class D3Vjp(torch.autograd.Function):
@@ -271,42 +281,38 @@ class D3Vjp(torch.autograd.Function):
     generate_vmap_rule = False
 
     @staticmethod
-    def forward(numbers, positions, p, g, st, want_p=True):
-        return _run_vjp(numbers, positions, p, g, st, want_p)
+    def forward(numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6, st, want_p=True):
+        return _run_vjp(numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6, st, want_p)
 
     @staticmethod
     def setup_context(ctx, inputs, output):
-        numbers, positions, p, g, st, _ = inputs
-        ctx.save_for_backward(numbers, positions, p, g)
+        numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6, st, _ = inputs
+        ctx.save_for_backward(numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6)
         ctx.st = st
 
     @staticmethod
     def backward(ctx, vx, vp):
-        numbers, positions, p, g = ctx.saved_tensors
-        lead = positions.shape[:-2]
-        n = positions.shape[-2]
+        numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6 = ctx.saved_tensors
         if vx is None:
             vx = torch.zeros_like(positions)
-        # a cotangent on the per-structure parameter gradients acts like one
-        # tangent on the (shared) parameters only if it is the same for every
-        # structure; D3Energy.backward sums over structures, so it is.
+        # The cotangent on the per-structure parameter gradients comes from the
+        # sum over structures in D3Energy.backward, so it is the same 5-vector
+        # for every structure: it acts as one tangent on the shared parameters.
         if vp is None:
             vp_shared = torch.zeros(NPAR, dtype=p.dtype, device=p.device)
         else:
-            flat = vp.reshape(-1, NPAR)
-            vp_shared = flat[0].to(device=p.device, dtype=p.dtype)
-        de, dgx, dgp = D3Hvp.apply(numbers, positions, p, g, vx, vp_shared, ctx.st)
-        gp_tot = dgp.reshape(-1, NPAR).sum(0).to(device=p.device, dtype=p.dtype)
-        return None, dgx, gp_tot, de, None, None
+            vp_shared = vp.reshape(-1, NPAR)[0].to(device=p.device, dtype=p.dtype)
+        de, dgx, dgp = D3Hvp.apply(numbers, positions, p, g, vx, vp_shared, rcov, r4r2, rvdw,
+                                   refcn, refc6, ctx.st)
+        out = [None] * 11
+        out[1] = dgx
+        out[2] = dgp.reshape(-1, NPAR).sum(0).to(device=p.device, dtype=p.dtype)
+        out[3] = de
+        return tuple(out)
 
     @staticmethod
-    def vmap(info, in_dims, numbers, positions, p, g, st, want_p):
-        args = (numbers, positions, p, g, st, want_p)
-        if _batched_params(in_dims, args, {0, 1, 3}):
-            return _loop(D3Vjp.apply, info, in_dims, args)
-        numbers, positions, p, g, st, want_p = _front(info, in_dims, args, {0, 1, 3})
-        gx, gp = D3Vjp.apply(numbers, positions, p, g, st, want_p)
-        return (gx, gp), (0, 0)
+    def vmap(info, in_dims, *args):
+        return _vmap(D3Vjp.apply, _V_NAMES, info, in_dims, args)
 
 
 class D3Hvp(torch.autograd.Function):
@@ -315,8 +321,8 @@ class D3Hvp(torch.autograd.Function):
     generate_vmap_rule = False
 
     @staticmethod
-    def forward(numbers, positions, p, g, vx, vp, st):
-        return _run_hvp(numbers, positions, p, g, vx, vp, st)
+    def forward(numbers, positions, p, g, vx, vp, rcov, r4r2, rvdw, refcn, refc6, st):
+        return _run_hvp(numbers, positions, p, g, vx, vp, rcov, r4r2, rvdw, refcn, refc6, st)
 
     @staticmethod
     def setup_context(ctx, inputs, output):
@@ -330,14 +336,9 @@ class D3Hvp(torch.autograd.Function):
         )
 
     @staticmethod
-    def vmap(info, in_dims, numbers, positions, p, g, vx, vp, st):
-        args = (numbers, positions, p, g, vx, vp, st)
-        if _batched_params(in_dims, args, {0, 1, 3, 4}):
-            return _loop(D3Hvp.apply, info, in_dims, args)
-        numbers, positions, p, g, vx, vp, st = _front(info, in_dims, args, {0, 1, 3, 4})
-        out = D3Hvp.apply(numbers, positions, p, g, vx, vp, st)
-        return out, (0, 0, 0)
+    def vmap(info, in_dims, *args):
+        return _vmap(D3Hvp.apply, _H_NAMES, info, in_dims, args)
 
 
-def d3_energy(numbers: Tensor, positions: Tensor, p: Tensor, st: Settings) -> Tensor:
-    return D3Energy.apply(numbers, positions, p, st)
+def d3_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st: Settings) -> Tensor:
+    return D3Energy.apply(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st)

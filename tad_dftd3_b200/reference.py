@@ -123,9 +123,11 @@ class Reference:
         key = (str(device), dtype)
         hit = self._cache.get(key)
         if hit is None:
-            cn = self.cn.detach().to(device=device, dtype=dtype).contiguous()
-            c6 = self.c6.detach().to(device=device, dtype=dtype).contiguous()
-            sym = bool(torch.equal(c6, c6.permute(1, 0, 3, 2)))
+            from .disp import _plain
+
+            cn = _plain(self.cn.detach()).to(device=device, dtype=dtype).contiguous()
+            c6 = _plain(self.c6.detach()).to(device=device, dtype=dtype).contiguous()
+            sym = bool(torch.allclose(c6, c6.permute(1, 0, 3, 2), rtol=1e-6 if dtype == torch.float32 else 1e-12, atol=0))
             hit = (cn, c6, sym)
             self._cache[key] = hit
         return hit

@@ -47,6 +47,7 @@ def synthetic_c6_table(dtype=torch.double, device=None, refcn=None) -> torch.Ten
     k = np.sqrt(c[:, None, :, None] * c[None, :, None, :]) * (
         1.0 + 0.05 * s[:, None, :, None] * s[None, :, None, :]
     )
+    k = 0.5 * (k + k.transpose(1, 0, 3, 2))  # exactly symmetric in floating point
     k[0] = 0.0
     k[:, 0] = 0.0
     return torch.from_numpy(k).to(dtype=dtype, device=device)

@@ -48,7 +48,7 @@ def test_argument_errors_without_gpu(lib):
     import ctypes as C
 
     par, model = _lib.Params(), _lib.Model()
-    rc = lib.d3b200_batch_energy_f64(1, 4, None, None, C.byref(model), C.byref(par), None, None)
+    rc = lib.d3b200_batch_energy_f64(1, 4, None, None, C.byref(model), C.byref(par), None, None, 0, None)
     assert rc == 1 and b"null" in lib.d3b200_last_error()
 
 
