@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""
+Benchmark of the D3(BJ) hot path (BASELINE.json metric: energy+gradient
+pair-terms/s, fp64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload c3|c4|c5a] [--nmol 4096]
+
+One "step" = one pass of the hot path (atom-resolved energies AND the complete
+analytic gradient) over one batch of synthetic structures.  Default workload
+(`c3`): BASELINE config 3, 4096 chain-grown drug-like molecules of 50..120
+atoms, zero-padded to 120, D3(BJ) two-body + CN, fp64; under torchrun every
+rank owns its own 4096-molecule shard (structures are independent: no
+data-path collective; weak scaling).
+
+Printed JSON line (rank 0):
+  value     pair-terms/s, inputs resident in HBM, one fused launch per step
+            (`d3b200_batch_vjp_f64` through the Python binding), CUDA events,
+            L2 flushed between steps, max over ranks;
+  e2e       the same metric through the public API (`dftd3()` +
+            `autograd.grad`) starting from pinned HOST buffers: H2D of numbers
+            and positions and D2H of energies and gradients inside the timed
+            region;
+  roofline  FP64 FMA pipe: algorithmic flops per launch (140 per
+            pair-term within 25 Bohr, 89 beyond) / event time of the kernel,
+            against an FP64 FMA-chain peak measured live on the same GPU;
+  cpu_baseline  the reference's own torch CPU path (unmodified reference
+            source over the tad-mctc stand-in when `baseline/_ref` travelled,
+            else the oracle port), on a bounded sample, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PARAM = {"s6": 1.0, "s8": 0.78981345, "a1": 0.49484001, "a2": 5.73083694}  # r2SCAN-D3(BJ)
+FLOPS_NEAR, FLOPS_FAR = 140.0, 89.0
+
+
+# ------------------------------------------------------------------ inputs
+def make_batch(nmol, seed):
+    from tad_dftd3_b200 import synthetic as syn
+
+    return syn.drug_like_batch(nmol, 50, 120, seed=seed)
+
+
+def count_pairs(numbers, positions, cutoff=50.0, cn_cutoff=25.0):
+    """Exact number of unordered real pairs within the cutoffs (on `positions.device`)."""
+    near = far = 0
+    for lo in range(0, numbers.shape[0], 512):
+        z, x = numbers[lo:lo + 512], positions[lo:lo + 512]
+        real = z != 0
+        m = real.unsqueeze(-1) & real.unsqueeze(-2)
+        d = torch.cdist(x, x)
+        iu = torch.triu(torch.ones(z.shape[-1], z.shape[-1], dtype=torch.bool, device=z.device), 1)
+        m = m & iu
+        near += int((m & (d <= cn_cutoff)).sum())
+        far += int((m & (d > cn_cutoff) & (d <= cutoff)).sum())
+    return near, far
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm
+def reference_step_fn(nmol_sample, seed=0):
+    """Callable running energy+gradient of the reference CPU path on a sample; returns
+    (fn, kind, pair_terms, sample description)."""
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    numbers, positions = make_batch(nmol_sample, seed)
+    near, far = count_pairs(numbers, positions)
+    dt = torch.double
+    c6 = syn.synthetic_c6_table(dt)
+    rcov, r4r2 = COV_D3(dt)[numbers], R4R2(dt)[numbers]
+    par = {k: torch.tensor(v, dtype=dt) for k, v in PARAM.items()}
+    from refimport import reference_available
+
+    if reference_available() is not None:
+        from refimport import import_reference
+
+        d3ref = import_reference()
+        from tad_dftd3.reference import Reference
+
+        refobj = Reference(cn=REFCN(dt), c6=c6)
+        kind = "reference"
+
+        def energy(pos):
+            return d3ref.dftd3(numbers, pos, par, ref=refobj, rcov=rcov, r4r2=r4r2)
+    else:
+        import d3_oracle as orc
+
+        refcn = REFCN(dt)
+        kind = "port"
+
+        def energy(pos):
+            return orc.dftd3(numbers, pos, par, refcn=refcn, refc6=c6, rcov=rcov, r4r2=r4r2)
+
+    def step():
+        pos = positions.clone().requires_grad_(True)
+        e = energy(pos)
+        (g,) = torch.autograd.grad(e.sum(), pos)
+        return float(e.sum()), g
+
+    desc = (f"{nmol_sample} molecules of the c3 batch (seed {seed}), energy + autograd gradient, "
+            f"torch {torch.__version__} CPU fp64")
+    return step, kind, near + far, desc
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    step, kind, pairs, desc = reference_step_fn(args.ref_nmol)
+    for _ in range(max(args.warmup, 1) if args.warmup < 3 else 1):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = pairs / dt
+    line = {
+        "impl": "reference", "metric": "D3(BJ) energy+grad pair-terms/s fp64", "value": v,
+        "unit": "pair-terms/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "c3: 4096 drug-like molecules (50-120 atoms, padded to 120), D3(BJ) two-body + CN, energy+grad fp64",
+                   "sample_per_step": desc},
+        "cpu_baseline": {"value": v, "unit": "pair-terms/s", "cores": torch.get_num_threads(), "kind": kind, "sample": desc},
+        "e2e": {"value": v, "unit": "pair-terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nmol", type=int, default=4096)
+    ap.add_argument("--ref-nmol", type=int, default=192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import _lib, ops
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+
+    lib = _lib.lib()
+    dt = torch.double
+    # ---- this rank's shard (weak scaling: every rank owns nmol structures)
+    numbers_h, positions_h = make_batch(args.nmol, seed=rank)
+    numbers_h, positions_h = numbers_h.pin_memory(), positions_h.pin_memory()
+    numbers, positions = numbers_h.to(dev), positions_h.to(dev)
+    near, far = count_pairs(numbers, positions)
+    pairs = near + far
+    flops = near * FLOPS_NEAR + far * FLOPS_FAR
+    ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
+    refcn, refc6, _ = ref._prepared(dev, dt)
+    par = {k: torch.tensor(v, dtype=dt) for k, v in PARAM.items()}
+    p = torch.tensor([PARAM["s6"], PARAM["s8"], PARAM["a1"], PARAM["a2"], 0.0], dtype=dt)
+    st = ops.Settings(rcov_per_element=True, r4r2_per_element=True)
+    rcov_t, r4r2_t = COV_D3(dt, dev), R4R2(dt, dev)
+    g = torch.ones(numbers.shape, dtype=dt, device=dev)
+
+    # ---- the hot path, inputs resident: one fused launch = energies + gradient
+    call = ops._Call(numbers, positions, p, rcov_t, r4r2_t, None, refcn, refc6, st, 0)
+    energy = torch.empty(numbers.shape, dtype=dt, device=dev)
+    grad = torch.empty(*numbers.shape, 3, dtype=dt, device=dev)
+    fn = lib.d3b200_batch_vjp_f64
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident():
+        _lib.launch_count += 1
+        _lib.check(fn(call.nflat, call.n, call.z.data_ptr(), call.x.data_ptr(), C.byref(call.model),
+                      C.byref(call.par), g.data_ptr(), energy.data_ptr(), grad.data_ptr(), None,
+                      None, 0, C.c_void_p(stream.cuda_stream)))
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches0 = _lib.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        # keep the GPU busy long enough for nvidia-smi to see loaded clocks
+        barrier()
+        for a, b in ev:
+            flush.zero_()
+            a.record(stream)
+            step_resident()
+            b.record(stream)
+        barrier()
+        t_steps = [a.elapsed_time(b) for a, b in ev]  # ms, kernel only
+        # ---- end-to-end through the public API from pinned host buffers
+        e_h = torch.empty(numbers.shape, dtype=dt).pin_memory()
+        g_h = torch.empty(*numbers.shape, 3, dtype=dt).pin_memory()
+
+        def step_e2e():
+            z = numbers_h.to(dev, non_blocking=True)
+            x = positions_h.to(dev, non_blocking=True).requires_grad_(True)
+            e = d3.dftd3(z, x, par, ref=ref)
+            (gx,) = torch.autograd.grad(e.sum(), x)
+            e_h.copy_(e.detach(), non_blocking=True)
+            g_h.copy_(gx, non_blocking=True)
+
+        for _ in range(args.warmup):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record(stream)
+        barrier()
+        t_e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    launches = _lib.launch_count - launches0
+
+    # ---- FP64 FMA-chain peak on this GPU (roofline denominator)
+    out = torch.zeros(1, dtype=dt, device=dev)
+    blocks, iters = 148 * 8, 4096
+    for _ in range(2):
+        lib.d3b200_probe_fma_f64(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record(stream)
+    lib.d3b200_probe_fma_f64(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+    pb.record(stream)
+    torch.cuda.synchronize(dev)
+    peak_tflops = blocks * 256 * iters * 128 / (pa.elapsed_time(pb) * 1e-3) / 1e12
+
+    ms = float(np.mean(t_steps))
+    t = torch.tensor([ms, t_e2e_ms], dtype=torch.double, device=dev)
+    tot = torch.tensor([float(pairs), float(flops)], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    pairs_all, flops_all = float(tot[0]), float(tot[1])
+
+    if rank == 0:
+        achieved = flops / (float(np.mean(t_steps)) * 1e-3) / 1e12  # this GPU's kernel
+        line = {
+            "metric": "D3(BJ) energy+grad pair-terms/s fp64",
+            "value": pairs_all / (ms * 1e-3),
+            "unit": "pair-terms/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"c3: {args.nmol} drug-like molecules per GPU (50-120 atoms, padded to 120), "
+                            "D3(BJ) two-body + CN, energy+grad fp64",
+                "pair_terms_per_gpu": pairs, "pairs_within_25_bohr": near,
+                "entry": "d3b200_batch_vjp_f64 (one fused launch: CN, weights, C6, BJ energy, analytic gradient)",
+                "l2": "256 MB buffer written between timed steps",
+                "timing": "CUDA events around each step on the launch stream, mean of steps, max over ranks",
+                "parallelism": f"structures sharded over {world} GPU(s), no data-path collective",
+                "tables": "synthetic C6 table (reference-c6.pt unavailable offline)",
+            },
+            "e2e": {
+                "value": pairs_all / (e2e_ms * 1e-3), "unit": "pair-terms/s",
+                "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * 8),
+                "d2h_bytes_per_step": int(e_h.numel() * 8 + g_h.numel() * 8),
+                "ms_per_step": e2e_ms,
+                "api": "tad_dftd3_b200.dftd3() + torch.autograd.grad, pinned host buffers",
+            },
+            "gpu_launches": launches,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved / peak_tflops, "traffic": None,
+                "kernel": "d3::molecule_kernel<double, E|G>",
+                "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "flops_model": "140/pair-term (r<=25 Bohr), 89 (25<r<=50), SURVEY.md 8(d)",
+                "hbm_gbs_measured_peak": _measured_hbm(),
+            },
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            stepf, kind, rp, desc = reference_step_fn(args.ref_nmol)
+            stepf()  # warm-up (thread pools, allocator)
+            t0 = time.perf_counter()
+            stepf()
+            dtc = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": rp / dtc, "unit": "pair-terms/s", "cores": torch.get_num_threads(),
+                                    "kind": kind, "sample": desc, "seconds": dtc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _measured_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+if __name__ == "__main__":
+    main()

@@ -154,6 +154,14 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
                          float* pgrad, float* denergy, float* dgrad, float* dpgrad,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement utility (bench.py): launches `blocks` CTAs of 256 threads, each
+ * thread running `iters` x 64 dependent-chain FMAs (8 independent chains), i.e.
+ * blocks * 256 * iters * 128 flops.  `out` is one device scalar (never written
+ * in practice).  Gives the sustained FP64 / FP32 FMA-pipe rate that the pair
+ * kernels' roofline is quoted against. */
+int d3b200_probe_fma_f64(int blocks, int iters, double* out, void* stream);
+int d3b200_probe_fma_f32(int blocks, int iters, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

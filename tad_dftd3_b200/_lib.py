@@ -55,7 +55,12 @@ for _sfx in ("f64", "f32"):
          _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int)
     _SIGNATURES[f"d3b200_batch_workspace_bytes_{_sfx}"] = ([_I, _I, _I, _I], C.c_size_t)
 
+    _SIGNATURES[f"d3b200_probe_fma_{_sfx}"] = ([_I, _I, _P, _P], C.c_int)
+
 _lib = None
+
+# number of kernel launches issued through this binding (bench.py reports it)
+launch_count = 0
 
 
 class D3LibraryError(RuntimeError):
