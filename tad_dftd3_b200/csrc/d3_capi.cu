@@ -7,6 +7,7 @@
 
 #include "../../include/d3b200.h"
 #include "d3_molecule.cuh"
+#include "d3_molecule_v2.cuh"
 
 namespace {
 
@@ -51,6 +52,27 @@ int launch(const d3::MolArgs<S>& args, cudaStream_t stream) {
   if (e != cudaSuccess) return cuda_fail(e, "molecule_kernel launch");
   return D3B200_OK;
 }
+
+// second-generation kernel (pairs evaluated once): energies / first derivatives,
+// two-body + CN, float or double
+template <typename B, bool WANT_G>
+int launch_v2(const d3::MolArgs<B>& args, cudaStream_t stream) {
+  const int N = args.natoms;
+  const int threads = 32 * d3::v2_warps(N);
+  const size_t smem = d3::molecule_v2_smem_bytes<B>(N);
+  auto kern = d3::molecule_kernel_v2<B, WANT_G>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  }
+  kern<<<args.nbatch, threads, smem, stream>>>(args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "molecule_kernel_v2 launch");
+  return D3B200_OK;
+}
+
+template <typename B>
+bool v2_fits(int natoms) { return d3::molecule_v2_smem_bytes<B>(natoms) <= kSmemLimit; }
 
 template <typename S, typename B>
 int fill_common(d3::MolArgs<S>& a, int nbatch, int natoms, const int64_t* numbers,
@@ -122,6 +144,7 @@ int energy_impl(int nbatch, int natoms, const int64_t* numbers, const B* positio
   if ((rc = set_workspace(a, par, workspace, wbytes))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (par->s9 != 0.0) return launch<B, d3::kWantE | d3::kAtm>(a, s);
+  if (v2_fits<B>(natoms)) return launch_v2<B, false>(a, s);
   return launch<B, d3::kWantE>(a, s);
 }
 
@@ -148,9 +171,11 @@ int vjp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
   }
   if (energy) {
     if (atm) return launch<B, kWantE | kWantG | kAtm>(a, s);
+    if (v2_fits<B>(natoms)) return launch_v2<B, true>(a, s);
     return launch<B, kWantE | kWantG>(a, s);
   }
   if (atm) return launch<B, kWantG | kAtm>(a, s);
+  if (v2_fits<B>(natoms)) return launch_v2<B, true>(a, s);
   return launch<B, kWantG>(a, s);
 }
 

@@ -111,6 +111,89 @@ template <typename T> D3_HD Dual<T> ab(Dual<T> a) { return a.v < T(0) ? Dual<T>(
 // x^p for x > 0 and a plain (tangent-free) exponent
 template <typename S, typename B> D3_HD S pw(S x, B p) { return ex(p * lg(x)); }
 
+// ---- fast, branch-free variants for the pair loops --------------------------
+// Arguments in the pair loops are positive, finite and far from the
+// denormal range, so the special-case handling of the library routines (which
+// costs about half of the issue slots, see profiles/r1a_summary.md) is dropped:
+//   frsq : MUFU.RSQ64H seed (2^-22) + one cubic step      -> 5 FP64 instructions
+//   frcp : MUFU.RCP64H seed (2^-22) + one cubic step      -> 3 FP64 instructions
+//   fex  : 2^n * P11(r), |r| <= ln2/2, Taylor degree 11   -> 16 FP64 instructions
+// each good to a few ulp (error of the cubic step ~ seed^3 = 2^-66).
+D3_HD float frsq(float a) { return rsqrtf(a); }
+D3_HD float frcp(float a) { return 1.0f / a; }
+D3_HD float fex(float a) { return expf(a); }
+
+D3_HD double frsq(double a) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double t = a * y;
+  double e = fma(-t, y, 1.0);
+  double p = fma(0.375, e, 0.5);
+  double q = e * y;
+  return fma(q, p, y);
+#else
+  return 1.0 / sqrt(a);
+#endif
+}
+
+D3_HD double frcp(double a) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  double f = fma(e, e, e);
+  return fma(y, f, y);
+#else
+  return 1.0 / a;
+#endif
+}
+
+// exp(x) for -700 <= x <= 700 (callers clamp)
+D3_HD double fex(double x) {
+#ifdef __CUDA_ARCH__
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52
+  double t = fma(x, 1.4426950408889634, magic);
+  int n = __double2loint(t);
+  double nf = t - magic;
+  double r = fma(nf, -6.93147180369123816490e-01, x);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double p = 2.505210838544172e-08;            // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);        // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);         // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);        // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);        // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);        // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+#else
+  return exp(x);
+#endif
+}
+
+template <typename T> D3_HD Dual<T> frcp(Dual<T> a) {
+  T r = frcp(a.v);
+  return Dual<T>(r, -a.d * r * r);
+}
+template <typename T> D3_HD Dual<T> frsq(Dual<T> a) {
+  T r = frsq(a.v);
+  return Dual<T>(r, T(-0.5) * a.d * r * r * r);
+}
+template <typename T> D3_HD Dual<T> fex(Dual<T> a) {
+  T e = fex(a.v);
+  return Dual<T>(e, e * a.d);
+}
+
+// max(a, lo) on the value (tangent follows the selected branch)
+D3_HD float fmx(float a, float lo) { return fmaxf(a, lo); }
+D3_HD double fmx(double a, double lo) { return fmax(a, lo); }
+template <typename T> D3_HD Dual<T> fmx(Dual<T> a, T lo) { return a.v < lo ? Dual<T>(lo) : a; }
+
 // conversions between working precision and the (float64) weight stage
 D3_HD double widen(float a) { return (double)a; }
 D3_HD double widen(double a) { return a; }

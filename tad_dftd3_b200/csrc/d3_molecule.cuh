@@ -142,14 +142,14 @@ __device__ __forceinline__ void reference_weights(
 template <typename S, typename B>
 __device__ __forceinline__ void atm_term(S a, S b, S c, S inva, S c9, S r0, B pexp, S& e, S& de_da) {
   S r2 = a * b * c;
-  S r1inv = rsq(r2);
+  S r1inv = frsq(r2);
   S r3inv = r1inv * r1inv * r1inv;
   S r5inv = r3inv * (r1inv * r1inv);
   S p = a + c - b, q = a - c + b, t = (c + b) - a;
   S s = p * q * t;
   S ang = B(0.375) * (s * r5inv) + r3inv;
   S u = pw(r0 * r1inv, pexp);
-  S fd = rcp(B(1) + B(6) * u);
+  S fd = frcp(B(1) + B(6) * u);
   e = c9 * (ang * fd);
   S ds = q * t + p * t - p * q;
   S dang = B(0.375) * (ds * r5inv - B(2.5) * ((s * r5inv) * inva)) - B(1.5) * (r3inv * inva);
@@ -274,9 +274,9 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
       S r2 = dx * dx + dy * dy + dz * dz;
       if (val(r2) > A.cn_cutoff2) continue;
       if (val(r2) < eps) r2 = S(eps);
-      S rinv = rsq(r2);
+      S rinv = frsq(r2);
       S arg = A.kcn * ((rci + srcov[j]) * rinv - B(1));
-      cn += rcp(B(1) + ex(-arg));
+      cn += frcp(B(1) + fex(fmx(-arg, B(-700))));
     }
     scn[i] = cn;
     S wi[kNRef], dwi[kNRef];
@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
         S r4 = r2 * r2;
         S r6 = r4 * r2;
         S r8 = r4 * r4;
-        S t6 = rcp(r6 + r06);
-        S t8 = rcp(r8 + r08);
+        S t6 = frcp(r6 + r06);
+        S t8 = frcp(r8 + r08);
         S s8q = A.s8 * qq;
         S P = A.s6 * t6 + s8q * t8;
         if (WANT_E) e_i += c6 * P;   // scaled by -1/2 at the end
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
           S a = dx * dx + dy * dy + dz * dz;
           if (val(a) < eps) a = S(eps);
           const bool mij = val(a) <= A.cutoff2;
-          const S inva = rcp(a);
+          const S inva = frcp(a);
           const S hij = hrow[(size_t)j * N + i];
           const int oj = sperm[j];
           const B gj_ = sg[j];
@@ -509,11 +509,11 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
         S r2 = dx * dx + dy * dy + dz * dz;
         if (val(r2) > A.cn_cutoff2) continue;
         if (val(r2) < eps) continue;  // clamped distance: no position dependence
-        S rinv = rsq(r2);
+        S rinv = frsq(r2);
         S rc = rci + srcov[j];
         S arg = A.kcn * (rc * rinv - B(1));
-        S e = ex(-arg);
-        S f = rcp(B(1) + e);
+        S e = fex(fmx(-arg, B(-700)));
+        S f = frcp(B(1) + e);
         S df = (-A.kcn) * (rc * (rinv * rinv * rinv)) * (f * (e * f));  // f(1-f) = e f^2
         S c = (decn + sdecn[j]) * df;
         gx += c * dx; gy += c * dy; gz += c * dz;
