@@ -149,27 +149,36 @@ D3_HD double frcp(double a) {
 #endif
 }
 
-// exp(x) for -700 <= x <= 700 (callers clamp)
+// exp(x) for -700 <= x <= 700 (callers clamp).  The Taylor coefficients live in
+// constant memory so that each DFMA takes its coefficient as a c[][] operand
+// (as literals they cost two UMOV each, 4 % of all issue slots in profile r1c).
+static __device__ __constant__ double kExpC[12] = {
+    2.505210838544172e-08,   // 1/11!
+    2.755731922398589e-07,   // 1/10!
+    2.7557319223985893e-06,  // 1/9!
+    2.48015873015873e-05,    // 1/8!
+    1.984126984126984e-04,   // 1/7!
+    1.388888888888889e-03,   // 1/6!
+    8.333333333333333e-03,   // 1/5!
+    4.1666666666666664e-02,  // 1/4!
+    1.6666666666666666e-01,  // 1/3!
+    0.5, 1.0, 1.0};
+static __device__ __constant__ double kExpR[4] = {
+    1.4426950408889634,            // log2(e)
+    6755399441055744.0,            // 1.5 * 2^52
+    -6.93147180369123816490e-01,   // -ln2 (high part)
+    -1.90821492927058770002e-10};  // -ln2 (low part)
+
 D3_HD double fex(double x) {
 #ifdef __CUDA_ARCH__
-  const double magic = 6755399441055744.0;  // 1.5 * 2^52
-  double t = fma(x, 1.4426950408889634, magic);
+  double t = fma(x, kExpR[0], kExpR[1]);
   int n = __double2loint(t);
-  double nf = t - magic;
-  double r = fma(nf, -6.93147180369123816490e-01, x);
-  r = fma(nf, -1.90821492927058770002e-10, r);
-  double p = 2.505210838544172e-08;            // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);        // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);         // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);        // 1/7!
-  p = fma(p, r, 1.388888888888889e-03);        // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);        // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  double nf = t - kExpR[1];
+  double r = fma(nf, kExpR[2], x);
+  r = fma(nf, kExpR[3], r);
+  double p = kExpC[0];
+#pragma unroll
+  for (int k = 1; k < 12; ++k) p = fma(p, r, kExpC[k]);
   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 #else
   return exp(x);
@@ -190,8 +199,13 @@ template <typename T> D3_HD Dual<T> fex(Dual<T> a) {
 }
 
 // max(a, lo) on the value (tangent follows the selected branch)
-D3_HD float fmx(float a, float lo) { return fmaxf(a, lo); }
-D3_HD double fmx(double a, double lo) { return fmax(a, lo); }
+D3_HD float fmx(float a, float lo) { return a < lo ? lo : a; }
+D3_HD double fmx(double a, double lo) { return a < lo ? lo : a; }
+
+// smallest addend that keeps 1/sqrt(r^2) finite for coincident atoms
+template <typename T> D3_HD T tiny_of();
+template <> D3_HD float tiny_of<float>() { return 1e-30f; }
+template <> D3_HD double tiny_of<double>() { return 1e-300; }
 template <typename T> D3_HD Dual<T> fmx(Dual<T> a, T lo) { return a.v < lo ? Dual<T>(lo) : a; }
 
 // conversions between working precision and the (float64) weight stage

@@ -6,16 +6,19 @@
 //
 //  * rows are processed in blocks of 16; a warp's two half-warps own the same
 //    16 rows i and split the partner range j > i by parity, so j is uniform per
-//    half-warp (shared-memory reads stay broadcasts) and the triangular waste
-//    is that of 16-row blocks (~85 % lane efficiency at N = 85);
-//  * the i-side contributions stay in registers; the j-side contributions of
-//    the 16 lanes are summed with a "transposed" shuffle reduction (V values
-//    in V-1+... shuffle-adds instead of 4V) and added by single lanes to
-//    per-warp private accumulators in shared memory: no atomics, fixed
-//    summation order, bitwise reproducible;
-//  * warps take row-block pairs (b, nb-1-b), which all carry the same work;
+//    half-warp (shared-memory reads are broadcasts) and the triangular waste is
+//    that of 16-row blocks (~85 % lane efficiency at N = 85);
+//  * the strict upper triangle, linearised row-block by row-block, is cut into
+//    four equal contiguous ranges, one per warp (fixed CTA of 4 warps): equal
+//    work per warp, and a summation order that depends on the structure only;
+//  * i-side contributions stay in registers; the j-side contributions of the 16
+//    lanes are transposed through a small shared-memory tile, summed in a fixed
+//    order by V lanes and added to per-warp private accumulators: no atomics,
+//    bitwise reproducible, ~3x fewer instructions than a shuffle tree;
+//  * per-atom data are AoS in shared memory ({x,y,z,kcn*rcov}, {sqrt q, g},
+//    w[8], dw[8]) so the broadcast reads are 128-bit;
 //  * rsqrt / reciprocal / exp are the branch-free MUFU-seeded versions of
-//    d3_math.cuh, the two BJ reciprocals share one MUFU seed, and the CN sweeps
+//    d3_math.cuh, the two BJ reciprocals share one MUFU seed, and the sweeps
 //    process several partners per iteration for instruction-level parallelism.
 #pragma once
 #include "d3_molecule.cuh"
@@ -25,93 +28,97 @@ namespace d3 {
 __device__ __forceinline__ float shx(float v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 __device__ __forceinline__ double shx(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 
-// Transposed reduction over the 16 lanes of a half-warp: on return the lane
-// holds the 16-lane total of v[which]; `valid` is false on lanes that hold a
-// duplicate.  C <= 16.
-template <int C, int OFF, typename S>
-struct Red16 {
-  static __device__ __forceinline__ S run(const S* v, int hl, int& which, bool& valid) {
-    constexpr int NC = (C + 1) / 2;
-    const bool bit = (hl & OFF) != 0;
-    S nv[NC];
-#pragma unroll
-    for (int m = 0; m < C / 2; ++m) {
-      S keep = bit ? v[2 * m + 1] : v[2 * m];
-      S send = bit ? v[2 * m] : v[2 * m + 1];
-      nv[m] = keep + shx(send, OFF);
-    }
-    if (C & 1) nv[NC - 1] = v[C - 1] + shx(v[C - 1], OFF);
-    S r = Red16<NC, OFF / 2, S>::run(nv, hl, which, valid);
-    if (which < C / 2) {
-      which = 2 * which + (bit ? 1 : 0);
-    } else {
-      which = C - 1;
-      if (bit) valid = false;
-    }
-    return r;
-  }
-};
-template <int C, typename S>
-struct Red16<C, 0, S> {
-  static __device__ __forceinline__ S run(const S* v, int, int& which, bool& valid) {
-    static_assert(C == 1, "Red16 handles at most 16 values");
-    which = 0;
-    valid = true;
-    return v[0];
-  }
-};
+template <typename S> struct alignas(4 * sizeof(S)) Atom4 { S x, y, z, rk; };
+template <typename S> struct alignas(2 * sizeof(S)) Pair2 { S a, b; };
 
-constexpr int kV2MaxWarps = 8;
-
-__host__ __device__ inline int v2_warps(int natoms) {
-  int nb = (natoms + 15) / 16;
-  int nu = (nb + 1) / 2;
-  return nu < 1 ? 1 : (nu > kV2MaxWarps ? kV2MaxWarps : nu);
-}
+constexpr int kV2Warps = 4;      // fixed CTA size (see above)
+constexpr int kRedV = 10;        // values per transposed reduction and half-warp
+constexpr int kRedStride = 18;   // 16 lanes + padding, keeps rows 16 B aligned
+__host__ __device__ inline int v2_warps(int) { return kV2Warps; }
 
 template <typename S>
 __host__ __device__ inline size_t molecule_v2_smem_bytes(int natoms) {
   size_t n = (size_t)natoms;
-  size_t bytes = n * 24 * sizeof(S);                 // x y z rk q sqrtq cn decn + w[8] + dw[8]
-  bytes += n * 5 * v2_warps(natoms) * sizeof(S);     // per-warp accumulators [nw][5][N]
-  bytes += n * sizeof(S);                            // g
-  bytes += n * 4 * sizeof(int);                      // origZ, sortedZ, perm, group
+  size_t bytes = n * (4 + 2 + 16) * sizeof(S);                // Atom4, Pair2 (later dL/dCN), w[8], dw[8]
+  bytes += n * 5 * kV2Warps * sizeof(S);                      // per-warp accumulators [nw][5][N]
+  bytes += (size_t)kV2Warps * 2 * kRedV * kRedStride * sizeof(S);  // reduction tiles
+  bytes += n * 5 + 16;                                        // origZ, sortedZ, group (u8), perm (u16)
   bytes += (5 * kMaxZ + 8) * sizeof(int);
-  return bytes + 64;
+  return bytes + 128;
+}
+
+// lanes that share one row of the reduction tile (2V rows, 32 lanes)
+__host__ __device__ constexpr int red_q(int V) { return 8 * V <= 32 ? 4 : (4 * V <= 32 ? 2 : 1); }
+
+// Sum vals[v] over the 16 lanes of each half-warp (both halves at once).
+// The values are transposed through this warp's tile [2][kRedV][kRedStride];
+// Q = red_q(V) lanes then share each row r = half * V + v (a shuffle or two
+// completes the row).  On return lanes with L % Q == 0 and L / Q < 2V hold the
+// total of row L / Q.  The summation order is fixed.
+template <int V, typename S>
+__device__ __forceinline__ S rows_reduce(const S (&vals)[V], S* redw, int lane) {
+  static_assert(V <= kRedV && 2 * V <= 32, "reduction tile too small");
+  const int hl = lane & 15, ph = lane >> 4;
+  S* mine = redw + ph * (kRedV * kRedStride);
+#pragma unroll
+  for (int v = 0; v < V; ++v) mine[v * kRedStride + hl] = vals[v];
+  __syncwarp();
+  S tot = S(0);
+  constexpr int Q = red_q(V);   // lanes per row
+  {
+    const int r = lane / Q, part = lane % Q;
+    if (r < 2 * V) {
+      const S* row = redw + (r / V) * (kRedV * kRedStride) + (r % V) * kRedStride + part * (16 / Q);
+      const Pair2<S>* rp = reinterpret_cast<const Pair2<S>*>(row);
+      S s0 = S(0), s1 = S(0);
+#pragma unroll
+      for (int k = 0; k < 8 / Q; ++k) { Pair2<S> p = rp[k]; s0 += p.a; s1 += p.b; }
+      tot = s0 + s1;
+    }
+  }
+  if (Q >= 2) tot += shx(tot, 1);
+  if (Q == 4) tot += shx(tot, 2);
+  __syncwarp();
+  return tot;
+}
+// decode helpers for the lanes that hold totals
+template <int V> __device__ __forceinline__ bool red_owner(int lane) {
+  constexpr int Q = red_q(V);
+  return (lane % Q) == 0 && (lane / Q) < 2 * V;
+}
+template <int V> __device__ __forceinline__ int red_row(int lane) {
+  constexpr int Q = red_q(V);
+  return lane / Q;
 }
 
 template <typename S, bool WANT_G>
-__global__ void __launch_bounds__(32 * kV2MaxWarps) molecule_kernel_v2(MolArgs<S> A) {
+__global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = A.natoms;
   const int b = blockIdx.x;
   const int t = threadIdx.x;
-  const int nt = blockDim.x;
-  const int lane = t & 31, wid = t >> 5, nw = nt >> 5;
+  constexpr int nt = 32 * kV2Warps;
+  constexpr int nw = kV2Warps;
+  const int lane = t & 31, wid = t >> 5;
   const int hl = lane & 15, ph = lane >> 4;
 
-  S* sx = reinterpret_cast<S*>(smem_raw);
-  S* sy = sx + N;
-  S* sz = sy + N;
-  S* srk = sz + N;              // kcn * rcov
-  S* sq = srk + N;
-  S* ssq = sq + N;
-  S* scn = ssq + N;
-  S* sdecn = scn + N;
-  S* sw = sdecn + N;            // [N][8]
-  S* sdw = sw + 8 * (size_t)N;  // [N][8]
-  S* acc = sdw + 8 * (size_t)N;  // [nw][5][N]
-  S* sg = acc + (size_t)nw * 5 * N;
-  int* sorigZ = reinterpret_cast<int*>(sg + N);
-  int* sZ = sorigZ + N;
-  int* sperm = sZ + N;
-  int* sgrp = sperm + N;
-  int* cnt = sgrp + N;
+  Atom4<S>* sA = reinterpret_cast<Atom4<S>*>(smem_raw);
+  Pair2<S>* sB = reinterpret_cast<Pair2<S>*>(sA + N);            // {sqrt(q), g}
+  S* sw = reinterpret_cast<S*>(sB + N);                          // [N][8]
+  S* sdw = sw + 8 * (size_t)N;                                   // [N][8]
+  S* red = sdw + 8 * (size_t)N;                                  // [nw][2][kRedV][kRedStride]
+  S* acc = red + (size_t)nw * 2 * kRedV * kRedStride;            // [nw][5][N]
+  S* sdecn = reinterpret_cast<S*>(sB);                           // aliases sB after phase 3
+  int* cnt = reinterpret_cast<int*>(acc + (size_t)nw * 5 * N);
   int* zstart = cnt + kMaxZ;
   int* gZ = zstart + kMaxZ;
   int* gstart = gZ + kMaxZ;
   int* zgrp = gstart + kMaxZ + 1;
   int* misc = zgrp + kMaxZ;
+  unsigned short* sperm = reinterpret_cast<unsigned short*>(misc + 4);
+  unsigned char* sorigZ = reinterpret_cast<unsigned char*>(sperm + N + (N & 1));
+  unsigned char* sZ = sorigZ + N;
+  unsigned char* sgrp = sZ + N;
 
   const int64_t* numbers = A.numbers + (size_t)b * N;
   const S* pos = A.positions + (size_t)b * N * 3;
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(32 * kV2MaxWarps) molecule_kernel_v2(MolArgs<S
   for (int k = t; k < N; k += nt) {
     int Z = (int)numbers[k];
     if (Z < 0 || Z >= kMaxZ) Z = 0;
-    sorigZ[k] = Z;
+    sorigZ[k] = (unsigned char)Z;
     if (Z > 0) {
       atomicAdd(&cnt[Z], 1);
     } else {
@@ -133,15 +140,34 @@ __global__ void __launch_bounds__(32 * kV2MaxWarps) molecule_kernel_v2(MolArgs<S
     }
   }
   __syncthreads();
-  if (t == 0) {
-    int ng = 0, run = 0;
-    for (int z = 1; z < kMaxZ; ++z) {
-      zstart[z] = run;
-      if (cnt[z] > 0) { gZ[ng] = z; gstart[ng] = run; zgrp[z] = ng; ++ng; run += cnt[z]; }
+  if (t < 32) {
+    // element histogram -> sorted offsets and group list, one warp, 4 elements per lane
+    int c[4], present = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int z = 4 * t + k;
+      c[k] = (z >= 1 && z < kMaxZ) ? cnt[z] : 0;
+      present += c[k] > 0;
+      total += c[k];
     }
-    gstart[ng] = run;
-    misc[0] = ng;
-    misc[1] = run;
+    int run = total, ng = present;          // inclusive scans over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int r2 = __shfl_up_sync(0xffffffffu, run, o), g2 = __shfl_up_sync(0xffffffffu, ng, o);
+      if (t >= o) { run += r2; ng += g2; }
+    }
+    const int ntot = __shfl_sync(0xffffffffu, run, 31), gtot = __shfl_sync(0xffffffffu, ng, 31);
+    run -= total;
+    ng -= present;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int z = 4 * t + k;
+      if (z >= 1 && z < kMaxZ) {
+        zstart[z] = run;
+        if (c[k] > 0) { gZ[ng] = z; gstart[ng] = run; zgrp[z] = ng; ++ng; run += c[k]; }
+      }
+    }
+    if (t == 0) { gstart[gtot] = ntot; misc[0] = gtot; misc[1] = ntot; }
   }
   __syncthreads();
   const int ng = misc[0];
@@ -151,71 +177,92 @@ __global__ void __launch_bounds__(32 * kV2MaxWarps) molecule_kernel_v2(MolArgs<S
     if (Z == 0) continue;
     int p = zstart[Z];
     for (int m = 0; m < k; ++m) p += (sorigZ[m] == Z);
-    sperm[p] = k;
-    sZ[p] = Z;
-    sgrp[p] = zgrp[Z];
-    sx[p] = pos[3 * k]; sy[p] = pos[3 * k + 1]; sz[p] = pos[3 * k + 2];
+    sperm[p] = (unsigned short)k;
+    sZ[p] = (unsigned char)Z;
+    sgrp[p] = (unsigned char)zgrp[Z];
     S rc = A.rcov_per_element ? A.rcov[Z] : A.rcov[(size_t)b * N + k];
     S q = A.r4r2_per_element ? A.r4r2[Z] : A.r4r2[(size_t)b * N + k];
-    srk[p] = A.kcn * rc;
-    sq[p] = q;
-    ssq[p] = sqr(q);
-    sg[p] = (WANT_G && A.g) ? A.g[(size_t)b * N + k] : S(1);
+    Atom4<S> a4;
+    a4.x = pos[3 * k]; a4.y = pos[3 * k + 1]; a4.z = pos[3 * k + 2]; a4.rk = A.kcn * rc;
+    sA[p] = a4;
+    Pair2<S> b2;
+    b2.a = sqr(q);
+    b2.b = (WANT_G && A.g) ? A.g[(size_t)b * N + k] : S(1);
+    sB[p] = b2;
   }
   __syncthreads();
 
+  const S tiny = tiny_of<S>();
   const S eps = eps_of<S>();
   const int nb = (n + 15) >> 4;
-  const int nunits = (nb + 1) >> 1;
   S* accw = acc + (size_t)wid * 5 * N;
+  S* redw = red + (size_t)wid * 2 * kRedV * kRedStride;
+
+  // Each warp takes a contiguous share of the linearised upper triangle (row
+  // block rb contributes its n-1-16rb partners j = 16rb+1 .. n-1, plus OVH
+  // units of fixed per-block overhead so that warps with many short row
+  // blocks -- more U contractions, more row epilogues -- get fewer partners).
+#define D3_PIECES_BEGIN(OVH)                                                    \
+  {                                                                             \
+    const int T_ = nb * (n - 1 + (OVH)) - 8 * nb * (nb - 1);                    \
+    const int wlo_ = min(T_, ((T_ * wid / nw) + 7) & ~7);                       \
+    const int whi_ = wid == nw - 1 ? T_ : min(T_, ((T_ * (wid + 1) / nw) + 7) & ~7); \
+    int pos_ = 0;                                                               \
+    for (int rb = 0; rb < nb; ++rb) {                                           \
+      const int i0 = rb << 4;                                                   \
+      const int len_ = n - 1 - i0;                                              \
+      const int a_ = max(wlo_, pos_ + (OVH)), b_ = min(whi_, pos_ + (OVH) + len_); \
+      const int j0 = i0 + 1 + (a_ - pos_ - (OVH)), j1 = i0 + 1 + (b_ - pos_ - (OVH)); \
+      pos_ += len_ + (OVH);                                                     \
+      if (a_ >= b_) continue;                                                   \
+      const int i = i0 + hl;                                                    \
+      const bool irow = i < n;                                                  \
+      const int ic = irow ? i : n - 1;
+#define D3_PIECES_END }}
 
   // ---------------------------------------------------------------- phase 1
   // CN_i = sum_j [r_ij <= 25] / (1 + exp(-kcn (rc_ij / r_ij - 1))), pairs once
   constexpr int CNB = 4;
-  for (int u = wid; u < nunits; u += nw) {
-    for (int side = 0; side < 2; ++side) {
-      const int rb = side == 0 ? u : nb - 1 - u;
-      if (side == 1 && rb == u) break;
-      const int i0 = rb << 4, i = i0 + hl;
-      const bool irow = i < n;
-      const int ic = irow ? i : n - 1;
-      const S xi = sx[ic], yi = sy[ic], zi = sz[ic], rki = srk[ic];
-      S cni = S(0);
-      for (int jb0 = i0 + 1; jb0 < n; jb0 += 2 * CNB) {  // warp-uniform trip count
-        const int jb = jb0 + ph;
-        S f[CNB];
+  D3_PIECES_BEGIN(2)
+  {
+    const Atom4<S> ai = sA[ic];
+    S cni = S(0);
+    for (int jb0 = j0; jb0 < j1; jb0 += 2 * CNB) {  // warp-uniform trip count
+      const int jb = jb0 + ph;
+      S f[CNB];
 #pragma unroll
-        for (int s = 0; s < CNB; ++s) {
-          const int j = jb + 2 * s;
-          const int jc = j < n ? j : n - 1;
-          S dx = xi - sx[jc], dy = yi - sy[jc], dz = zi - sz[jc];
-          S r2 = dx * dx + dy * dy + dz * dz;
-          const bool ok = irow && j < n && j > i && r2 <= A.cn_cutoff2;
-          r2 = fmx(r2, eps);
-          S rinv = frsq(r2);
-          S x = fmx(A.kcn - (rki + srk[jc]) * rinv, S(-700));
-          S v = frcp(S(1) + fex(x));
-          f[s] = ok ? v : S(0);
-          cni += f[s];
-        }
-        int which; bool valid;
-        S tot = Red16<CNB, 8, S>::run(f, hl, which, valid);
-        const int j = jb + 2 * which;
-        if (valid && j < n) accw[j] += tot;
+      for (int s = 0; s < CNB; ++s) {
+        const int j = jb + 2 * s;
+        const int jc = j < j1 ? j : j1 - 1;
+        const Atom4<S> aj = sA[jc];
+        S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+        S r2 = dx * dx + dy * dy + dz * dz;
+        const bool ok = irow && j < j1 && j > i && r2 <= A.cn_cutoff2;
+        S rinv = frsq(r2 + tiny);
+        S x = fmx(A.kcn - (ai.rk + aj.rk) * rinv, S(-700));
+        S v = frcp(S(1) + fex(x));
+        f[s] = ok ? v : S(0);
+        cni += f[s];
       }
-      cni += shx(cni, 16);
-      __syncwarp();
-      if (ph == 0 && irow) accw[i] += cni;
-      __syncwarp();
+      S tot = rows_reduce<CNB, S>(f, redw, lane);
+      {
+        const int r = red_row<CNB>(lane);
+        const int j = jb0 + r / CNB + 2 * (r % CNB);
+        if (red_owner<CNB>(lane) && j < j1) accw[j] += tot;
+      }
     }
+    cni += shx(cni, 16);
+    __syncwarp();
+    if (ph == 0 && irow) accw[i] += cni;
+    __syncwarp();
   }
+  D3_PIECES_END
   __syncthreads();
 
   // ---------------------------------------------------------------- phase 2
   for (int i = t; i < n; i += nt) {
     S cn = S(0);
     for (int w = 0; w < nw; ++w) { cn += acc[(size_t)w * 5 * N + i]; acc[(size_t)w * 5 * N + i] = S(0); }
-    scn[i] = cn;
     S wi[kNRef], dwi[kNRef];
     reference_weights<S>(A.refcn + sZ[i] * kNRef, cn, wi, dwi);
 #pragma unroll
@@ -225,62 +272,66 @@ __global__ void __launch_bounds__(32 * kV2MaxWarps) molecule_kernel_v2(MolArgs<S
   __syncthreads();
 
   // ---------------------------------------------------------------- phase 3
-  for (int u = wid; u < nunits; u += nw) {
-    for (int side = 0; side < 2; ++side) {
-      const int rb = side == 0 ? u : nb - 1 - u;
-      if (side == 1 && rb == u) break;
-      const int i0 = rb << 4, i = i0 + hl;
-      const bool irow = i < n;
-      const int ic = irow ? i : n - 1;
-      const S xi = sx[ic], yi = sy[ic], zi = sz[ic], qi = sq[ic];
-      const int Zi = sZ[ic];
-      const S gi = sg[ic];
-      const S sa_i = A.a1 * sqr(S(3) * qi);
-      const S q3_i = S(3) * qi;
-      S ei = S(0), gxi = S(0), gyi = S(0), gzi = S(0), di = S(0);
-      for (int grp = sgrp[i0]; grp < ng; ++grp) {
-        const int jlo = max(gstart[grp], i0 + 1), jhi = gstart[grp + 1];
-        if (jlo >= jhi) continue;
-        // U[b] = sum_a w_ia K[Zi,Zg,a,b],  Ud[b] = sum_a dw_ia K[Zi,Zg,a,b]:
-        // half 0 contracts the weights, half 1 their CN derivatives, then swap
-        const S* __restrict__ K = A.refc6 + ((size_t)Zi * kMaxZ + gZ[grp]) * (kNRef * kNRef);
-        S U[kNRef], Ud[kNRef];
-        {
-          const S* src = (WANT_G && ph == 1) ? sdw + 8 * ic : sw + 8 * ic;
-          S mine[kNRef];
+  constexpr int PB = 2;                     // partners per iteration and half-warp
+  constexpr int PV = WANT_G ? 5 : 1;        // j-side values per partner
+  D3_PIECES_BEGIN(10)
+  {
+    const Atom4<S> ai = sA[ic];
+    const Pair2<S> bi = sB[ic];
+    const int Zi = sZ[ic];
+    const S gi = bi.b;
+    const S s3qi = sqr(S(3)) * bi.a;        // sqrt(3 q_i)
+    S ei = S(0), gxi = S(0), gyi = S(0), gzi = S(0), di = S(0);
+    for (int grp = sgrp[j0]; grp < ng && gstart[grp] < j1; ++grp) {
+      const int jlo = max(gstart[grp], j0), jhi = min(gstart[grp + 1], j1);
+      // U[b] = sum_a w_ia K[Zi,Zg,a,b],  Ud[b] = sum_a dw_ia K[Zi,Zg,a,b]:
+      // half 0 contracts the weights, half 1 their CN derivatives, then swap
+      const S* __restrict__ K = A.refc6 + ((size_t)Zi * kMaxZ + gZ[grp]) * (kNRef * kNRef);
+      S U[kNRef], Ud[kNRef];
+      {
+        const S* src = (WANT_G && ph == 1) ? sdw + 8 * ic : sw + 8 * ic;
+        S mine[kNRef];
 #pragma unroll
-          for (int bb = 0; bb < kNRef; ++bb) mine[bb] = S(0);
+        for (int bb = 0; bb < kNRef; ++bb) mine[bb] = S(0);
 #pragma unroll
-          for (int a = 0; a < kNRef; ++a) {
-            const S wa = src[a];
+        for (int a = 0; a < kNRef; ++a) {
+          const S wa = src[a];
 #pragma unroll
-            for (int bb = 0; bb < kNRef; ++bb) mine[bb] += wa * __ldg(K + a * kNRef + bb);
-          }
+          for (int bb = 0; bb < kNRef; ++bb) mine[bb] += wa * __ldg(K + a * kNRef + bb);
+        }
 #pragma unroll
-          for (int bb = 0; bb < kNRef; ++bb) {
-            if (WANT_G) {
-              S other = shx(mine[bb], 16);
-              U[bb] = ph == 0 ? mine[bb] : other;
-              Ud[bb] = ph == 0 ? other : mine[bb];
-            } else {
-              U[bb] = mine[bb];
-            }
+        for (int bb = 0; bb < kNRef; ++bb) {
+          if (WANT_G) {
+            S other = shx(mine[bb], 16);
+            U[bb] = ph == 0 ? mine[bb] : other;
+            Ud[bb] = ph == 0 ? other : mine[bb];
+          } else {
+            U[bb] = mine[bb];
           }
         }
-        for (int j = jlo + ph; j < jhi + ph; j += 2) {
-          // (the loop bound keeps both halves in step; the last j of half 1 may be jhi)
+      }
+      for (int jb0 = jlo; jb0 < jhi; jb0 += 2 * PB) {
+        S vals[PV * PB];
+#pragma unroll
+        for (int s = 0; s < PB; ++s) {
+          const int j = jb0 + ph + 2 * s;
           const bool jin = j < jhi;
           const int jc = jin ? j : jhi - 1;
-          S dx = xi - sx[jc], dy = yi - sy[jc], dz = zi - sz[jc];
+          const Atom4<S> aj = sA[jc];
+          const Pair2<S> bj = sB[jc];
+          S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
           S r2 = dx * dx + dy * dy + dz * dz;
           const bool ok = irow && jin && jc > i && r2 <= A.cutoff2;
-          r2 = fmx(r2, eps);
-          const S* wj = sw + 8 * jc;
-          S c6 = U[0] * wj[0];
+          const Pair2<S>* wj = reinterpret_cast<const Pair2<S>*>(sw + 8 * jc);
+          S wv[8];
 #pragma unroll
-          for (int a = 1; a < kNRef; ++a) c6 += U[a] * wj[a];
-          S qq = q3_i * sq[jc];
-          S r0 = sa_i * ssq[jc] + A.a2;
+          for (int k = 0; k < 4; ++k) { Pair2<S> p = wj[k]; wv[2 * k] = p.a; wv[2 * k + 1] = p.b; }
+          S c6 = U[0] * wv[0];
+#pragma unroll
+          for (int a = 1; a < kNRef; ++a) c6 += U[a] * wv[a];
+          S tq = s3qi * bj.a;               // sqrt(3 q_i q_j)
+          S qq = tq * tq;
+          S r0 = A.a1 * tq + A.a2;          // R0 = a1 sqrt(3 q_i q_j) + a2
           S r02 = r0 * r0;
           S r06 = r02 * r02 * r02;
           S r08 = r06 * r02;
@@ -292,15 +343,18 @@ __global__ void __launch_bounds__(32 * kV2MaxWarps) molecule_kernel_v2(MolArgs<S
           S t6 = inv * d8, t8 = inv * d6;
           S s8q = A.s8 * qq;
           S P = A.s6 * t6 + s8q * t8;
-          S vals[5];
-          vals[0] = ok ? c6 * P : S(0);
-          ei += vals[0];
+          S ep = ok ? c6 * P : S(0);
+          vals[PV * s] = ep;
+          ei += ep;
           if (WANT_G) {
-            const S* dwj = sdw + 8 * jc;
-            S dci = Ud[0] * wj[0], dcj = U[0] * dwj[0];
+            const Pair2<S>* dwj = reinterpret_cast<const Pair2<S>*>(sdw + 8 * jc);
+            S dv[8];
 #pragma unroll
-            for (int a = 1; a < kNRef; ++a) { dci += Ud[a] * wj[a]; dcj += U[a] * dwj[a]; }
-            S gam = ok ? S(0.5) * (gi + sg[jc]) : S(0);
+            for (int k = 0; k < 4; ++k) { Pair2<S> p = dwj[k]; dv[2 * k] = p.a; dv[2 * k + 1] = p.b; }
+            S dci = Ud[0] * wv[0], dcj = U[0] * dv[0];
+#pragma unroll
+            for (int a = 1; a < kNRef; ++a) { dci += Ud[a] * wv[a]; dcj += U[a] * dv[a]; }
+            S gam = ok ? S(0.5) * (gi + bj.b) : S(0);
             S gP = gam * P;
             di -= gP * dci;
             S t62 = t6 * t6, t82 = t8 * t8;
@@ -308,31 +362,30 @@ __global__ void __launch_bounds__(32 * kV2MaxWarps) molecule_kernel_v2(MolArgs<S
             S f = (S(2) * gam) * (c6 * dP);
             S fx = f * dx, fy = f * dy, fz = f * dz;
             gxi += fx; gyi += fy; gzi += fz;
-            vals[1] = -fx; vals[2] = -fy; vals[3] = -fz;
-            vals[4] = -(gP * dcj);
-          } else {
-            vals[1] = vals[2] = vals[3] = vals[4] = S(0);
-          }
-          int which; bool valid;
-          if (WANT_G) {
-            S tot = Red16<5, 8, S>::run(vals, hl, which, valid);
-            if (valid && jin) accw[(size_t)which * N + jc] += tot;
-          } else {
-            S tot = Red16<1, 8, S>::run(vals, hl, which, valid);
-            if (valid && jin) accw[jc] += tot;
+            vals[PV * s + 1 % PV] = -fx; vals[PV * s + 2 % PV] = -fy; vals[PV * s + 3 % PV] = -fz;
+            vals[PV * s + 4 % PV] = -(gP * dcj);
           }
         }
+        S tot = rows_reduce<PV * PB, S>(vals, redw, lane);
+        {
+          constexpr int V = PV * PB;
+          const int r = red_row<V>(lane);
+          const int v = r % V;
+          const int j = jb0 + r / V + 2 * (v / PV);
+          if (red_owner<V>(lane) && j < jhi) accw[(size_t)(v % PV) * N + j] += tot;
+        }
       }
-      ei += shx(ei, 16);
-      if (WANT_G) { gxi += shx(gxi, 16); gyi += shx(gyi, 16); gzi += shx(gzi, 16); di += shx(di, 16); }
-      __syncwarp();
-      if (ph == 0 && irow) {
-        accw[i] += ei;
-        if (WANT_G) { accw[N + i] += gxi; accw[2 * N + i] += gyi; accw[3 * N + i] += gzi; accw[4 * N + i] += di; }
-      }
-      __syncwarp();
     }
+    ei += shx(ei, 16);
+    if (WANT_G) { gxi += shx(gxi, 16); gyi += shx(gyi, 16); gzi += shx(gzi, 16); di += shx(di, 16); }
+    __syncwarp();
+    if (ph == 0 && irow) {
+      accw[i] += ei;
+      if (WANT_G) { accw[N + i] += gxi; accw[2 * N + i] += gyi; accw[3 * N + i] += gzi; accw[4 * N + i] += di; }
+    }
+    __syncwarp();
   }
+  D3_PIECES_END
   __syncthreads();
   for (int i = t; i < n; i += nt) {
     S e = S(0), d = S(0);
@@ -346,48 +399,50 @@ __global__ void __launch_bounds__(32 * kV2MaxWarps) molecule_kernel_v2(MolArgs<S
   // ---------------------------------------------------------------- phase 4
   // CN chain: (dL/dCN_i + dL/dCN_j) df_ij/dx, df/dx_i = -kcn rc r^-3 f(1-f) (x_i - x_j)
   constexpr int GB = 2;
-  for (int u = wid; u < nunits; u += nw) {
-    for (int side = 0; side < 2; ++side) {
-      const int rb = side == 0 ? u : nb - 1 - u;
-      if (side == 1 && rb == u) break;
-      const int i0 = rb << 4, i = i0 + hl;
-      const bool irow = i < n;
-      const int ic = irow ? i : n - 1;
-      const S xi = sx[ic], yi = sy[ic], zi = sz[ic], rki = srk[ic], dci = sdecn[ic];
-      S gxi = S(0), gyi = S(0), gzi = S(0);
-      for (int jb0 = i0 + 1; jb0 < n; jb0 += 2 * GB) {  // warp-uniform trip count
-        const int jb = jb0 + ph;
-        S vals[3 * GB];
+  D3_PIECES_BEGIN(2)
+  {
+    const Atom4<S> ai = sA[ic];
+    const S dci = sdecn[ic];
+    S gxi = S(0), gyi = S(0), gzi = S(0);
+    for (int jb0 = j0; jb0 < j1; jb0 += 2 * GB) {  // warp-uniform trip count
+      const int jb = jb0 + ph;
+      S vals[3 * GB];
 #pragma unroll
-        for (int s = 0; s < GB; ++s) {
-          const int j = jb + 2 * s;
-          const int jc = j < n ? j : n - 1;
-          S dx = xi - sx[jc], dy = yi - sy[jc], dz = zi - sz[jc];
-          S r2 = dx * dx + dy * dy + dz * dz;
-          const bool ok = irow && j < n && j > i && r2 <= A.cn_cutoff2 && r2 >= eps;
-          r2 = fmx(r2, eps);
-          S rinv = frsq(r2);
-          S rk = rki + srk[jc];
-          S e = fex(fmx(A.kcn - rk * rinv, S(-700)));
-          S f = frcp(S(1) + e);
-          S df = -(rk * (rinv * rinv * rinv)) * (f * (e * f));
-          S c = ok ? (dci + sdecn[jc]) * df : S(0);
-          S cx = c * dx, cy = c * dy, cz = c * dz;
-          gxi += cx; gyi += cy; gzi += cz;
-          vals[3 * s] = -cx; vals[3 * s + 1] = -cy; vals[3 * s + 2] = -cz;
-        }
-        int which; bool valid;
-        S tot = Red16<3 * GB, 8, S>::run(vals, hl, which, valid);
-        const int j = jb + 2 * (which / 3);
-        if (valid && j < n) accw[(size_t)(1 + which % 3) * N + j] += tot;
+      for (int s = 0; s < GB; ++s) {
+        const int j = jb + 2 * s;
+        const int jc = j < j1 ? j : j1 - 1;
+        const Atom4<S> aj = sA[jc];
+        S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+        S r2 = dx * dx + dy * dy + dz * dz;
+        const bool ok = irow && j < j1 && j > i && r2 <= A.cn_cutoff2 && r2 >= eps;
+        S rinv = frsq(r2 + tiny);
+        S rk = ai.rk + aj.rk;
+        S e = fex(fmx(A.kcn - rk * rinv, S(-700)));
+        S f = frcp(S(1) + e);
+        S df = (rk * (rinv * rinv * rinv)) * (f * (e * f));
+        S c = ok ? (dci + sdecn[jc]) * df : S(0);   // = -(dL/dCN_i + dL/dCN_j) f'(r) / r
+        S cx = c * dx, cy = c * dy, cz = c * dz;
+        gxi -= cx; gyi -= cy; gzi -= cz;
+        vals[3 * s] = cx; vals[3 * s + 1] = cy; vals[3 * s + 2] = cz;
       }
-      gxi += shx(gxi, 16); gyi += shx(gyi, 16); gzi += shx(gzi, 16);
-      __syncwarp();
-      if (ph == 0 && irow) { accw[N + i] += gxi; accw[2 * N + i] += gyi; accw[3 * N + i] += gzi; }
-      __syncwarp();
+      S tot = rows_reduce<3 * GB, S>(vals, redw, lane);
+      {
+        constexpr int V = 3 * GB;
+        const int r = red_row<V>(lane);
+        const int v = r % V;
+        const int j = jb0 + r / V + 2 * (v / 3);
+        if (red_owner<V>(lane) && j < j1) accw[(size_t)(1 + v % 3) * N + j] += tot;
+      }
     }
+    gxi += shx(gxi, 16); gyi += shx(gyi, 16); gzi += shx(gzi, 16);
+    __syncwarp();
+    if (ph == 0 && irow) { accw[N + i] += gxi; accw[2 * N + i] += gyi; accw[3 * N + i] += gzi; }
+    __syncwarp();
   }
+  D3_PIECES_END
   __syncthreads();
+#undef D3_PIECES_BEGIN
+#undef D3_PIECES_END
   for (int i = t; i < n; i += nt) {
     S gx = S(0), gy = S(0), gz = S(0);
     for (int w = 0; w < nw; ++w) {
