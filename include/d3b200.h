@@ -154,6 +154,66 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
                          float* pgrad, float* denergy, float* dgrad, float* dpgrad,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * One large structure, tiled over the whole GPU and shardable by rows.
+ *
+ * Same path as above (reference disp.py:150-165) for structures too large for
+ * one CTA (BASELINE config 4: 50 k atoms) and for the i-row sharded multi-GPU
+ * mode.  The caller (tad_dftd3_b200/system.py) removes ghost atoms, sorts the
+ * atoms spatially and by element inside each 128-atom tile, pads to a multiple
+ * of 128 with far-away Z = 0 atoms and supplies:
+ *   atoms [natoms][4]  x, y, z, kcn * rcov          aux [natoms][2]  sqrt(r4r2), g
+ *   z     [natoms]     int32 atomic numbers          box [natoms/32][6]  min xyz, max xyz
+ * Sweeps (each writes only rows row_begin..row_end-1, multiples of 128; all
+ * other arrays are read for every atom, so on several GPUs `cn` and `decn`
+ * must be all-gathered between the sweeps):
+ *   _cn       cn[i]                              tad-mctc cn_d3, call site disp.py:150-152
+ *   _weights  w[i][8], dw[i][8] for ALL atoms    model/weights.py:104-176
+ *   _pair     energy[i], grad[i][3] (direct part), decn[i] = dL/dCN_i
+ *             (want_grad = 0: energy only)        model/c6.py + disp.py:276-302
+ *   _cnbwd    grad[i][3] += CN chain-rule term    (autograd through cn_d3)
+ * g (in aux) is the cotangent of the per-atom energies, L = sum g_i E_i. */
+typedef struct d3b200_system_f64 {
+  int natoms, row_begin, row_end;
+  const double* atoms;
+  const double* aux;
+  const int32_t* z;
+  const double* box;
+  const double* refcn;
+  const double* refc6;
+  double* cn;
+  double* w;
+  double* dw;
+  double* decn;
+  double* energy;
+  double* grad;
+} d3b200_system_f64;
+
+typedef struct d3b200_system_f32 {
+  int natoms, row_begin, row_end;
+  const float* atoms;
+  const float* aux;
+  const int32_t* z;
+  const float* box;
+  const float* refcn;
+  const float* refc6;
+  float* cn;
+  float* w;
+  float* dw;
+  float* decn;
+  float* energy;
+  float* grad;
+} d3b200_system_f32;
+
+int d3b200_system_cn_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
+int d3b200_system_weights_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
+int d3b200_system_pair_f64(const d3b200_system_f64* sys, const d3b200_params* par, int want_grad, void* stream);
+int d3b200_system_cnbwd_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
+int d3b200_system_cn_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
+int d3b200_system_weights_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
+int d3b200_system_pair_f32(const d3b200_system_f32* sys, const d3b200_params* par, int want_grad, void* stream);
+int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
+
 /* Measurement utility (bench.py): launches `blocks` CTAs of 256 threads, each
  * thread running `iters` x 64 dependent-chain FMAs (8 independent chains), i.e.
  * blocks * 256 * iters * 128 flops.  `out` is one device scalar (never written

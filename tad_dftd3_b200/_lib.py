@@ -37,6 +37,14 @@ class Model(C.Structure):
     ]
 
 
+class System(C.Structure):
+    """`d3b200_system_f64` / `_f32`."""
+
+    _fields_ = [("natoms", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int)] + [
+        (k, C.c_void_p) for k in
+        ("atoms", "aux", "z", "box", "refcn", "refc6", "cn", "w", "dw", "decn", "energy", "grad")]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _SIGNATURES = {
@@ -56,6 +64,9 @@ for _sfx in ("f64", "f32"):
     _SIGNATURES[f"d3b200_batch_workspace_bytes_{_sfx}"] = ([_I, _I, _I, _I], C.c_size_t)
 
     _SIGNATURES[f"d3b200_probe_fma_{_sfx}"] = ([_I, _I, _P, _P], C.c_int)
+    for _k in ("cn", "weights", "cnbwd"):
+        _SIGNATURES[f"d3b200_system_{_k}_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _P], C.c_int)
+    _SIGNATURES[f"d3b200_system_pair_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _I, _P], C.c_int)
 
 _lib = None
 

@@ -8,6 +8,7 @@
 #include "../../include/d3b200.h"
 #include "d3_molecule.cuh"
 #include "d3_molecule_v2.cuh"
+#include "d3_system.cuh"
 
 namespace {
 
@@ -205,9 +206,98 @@ int hvp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
   return launch<S, kWantE | kWantG | kWantP>(a, s);
 }
 
+// ---------------------------------------------------------------- tiled system
+template <typename B> struct SysOf;
+template <> struct SysOf<double> { using type = d3b200_system_f64; };
+template <> struct SysOf<float> { using type = d3b200_system_f32; };
+
+template <typename B>
+int sys_fill(d3::SysArgs<B>& a, const typename SysOf<B>::type* s, const d3b200_params* par) {
+  if (!s || !par) return fail(D3B200_EINVAL, "null argument%s");
+  if (s->natoms <= 0 || s->natoms % d3::kSysTile) return fail(D3B200_EINVAL, "natoms must be a positive multiple of 128%s");
+  if (s->row_begin < 0 || s->row_end > s->natoms || s->row_begin > s->row_end ||
+      s->row_begin % d3::kSysTile || s->row_end % d3::kSysTile)
+    return fail(D3B200_EINVAL, "row range must be tile aligned%s");
+  if (!s->atoms || !s->z || !s->box) return fail(D3B200_EINVAL, "null system array%s");
+  memset(&a, 0, sizeof(a));
+  a.natoms = s->natoms; a.row_begin = s->row_begin; a.row_end = s->row_end;
+  a.atoms = reinterpret_cast<const d3::Atom4<B>*>(s->atoms);
+  a.aux = reinterpret_cast<const d3::Pair2<B>*>(s->aux);
+  a.z = s->z; a.box = s->box; a.w = s->w; a.dw = s->dw; a.wout = s->w; a.dwout = s->dw;
+  a.refcn = s->refcn; a.refc6 = s->refc6;
+  a.cn = s->cn; a.decn = s->decn; a.energy = s->energy; a.grad = s->grad;
+  a.s6 = (B)par->s6; a.s8 = (B)par->s8; a.a1 = (B)par->a1; a.a2 = (B)par->a2;
+  B cut = (B)par->cutoff, cncut = (B)par->cn_cutoff;
+  a.cutoff2 = cut * cut; a.cn_cutoff2 = cncut * cncut; a.kcn = (B)par->kcn;
+  return D3B200_OK;
+}
+
+int launched(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? D3B200_OK : cuda_fail(e, what);
+}
+
+template <typename B>
+int sys_cn(const typename SysOf<B>::type* s, const d3b200_params* par, void* stream) {
+  d3::SysArgs<B> a;
+  int rc = sys_fill<B>(a, s, par);
+  if (rc) return rc;
+  if (!s->cn) return fail(D3B200_EINVAL, "null cn%s");
+  const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
+  if (nblk == 0) return D3B200_OK;
+  d3::system_cn_kernel<B><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  return launched("system_cn_kernel");
+}
+
+template <typename B>
+int sys_weights(const typename SysOf<B>::type* s, const d3b200_params* par, void* stream) {
+  d3::SysArgs<B> a;
+  int rc = sys_fill<B>(a, s, par);
+  if (rc) return rc;
+  if (!s->cn || !s->w || !s->dw || !s->refcn) return fail(D3B200_EINVAL, "null weights argument%s");
+  d3::system_weights_kernel<B><<<(a.natoms + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  return launched("system_weights_kernel");
+}
+
+template <typename B>
+int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int want_grad, void* stream) {
+  d3::SysArgs<B> a;
+  int rc = sys_fill<B>(a, s, par);
+  if (rc) return rc;
+  if (!s->aux || !s->w || !s->dw || !s->refc6) return fail(D3B200_EINVAL, "null pair argument%s");
+  if (want_grad && (!s->grad || !s->decn)) return fail(D3B200_EINVAL, "null gradient output%s");
+  const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
+  if (nblk == 0) return D3B200_OK;
+  if (want_grad) d3::system_pair_kernel<B, true><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  else d3::system_pair_kernel<B, false><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  return launched("system_pair_kernel");
+}
+
+template <typename B>
+int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* stream) {
+  d3::SysArgs<B> a;
+  int rc = sys_fill<B>(a, s, par);
+  if (rc) return rc;
+  if (!s->decn || !s->grad) return fail(D3B200_EINVAL, "null cnbwd argument%s");
+  const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
+  if (nblk == 0) return D3B200_OK;
+  d3::system_cnbwd_kernel<B><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  return launched("system_cnbwd_kernel");
+}
+
 }  // namespace
 
 extern "C" {
+
+int d3b200_system_cn_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_cn<double>(s, p, st); }
+int d3b200_system_weights_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_weights<double>(s, p, st); }
+int d3b200_system_pair_f64(const d3b200_system_f64* s, const d3b200_params* p, int g, void* st) { return sys_pair<double>(s, p, g, st); }
+int d3b200_system_cnbwd_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_cnbwd<double>(s, p, st); }
+int d3b200_system_cn_f32(const d3b200_system_f32* s, const d3b200_params* p, void* st) { return sys_cn<float>(s, p, st); }
+int d3b200_system_weights_f32(const d3b200_system_f32* s, const d3b200_params* p, void* st) { return sys_weights<float>(s, p, st); }
+int d3b200_system_pair_f32(const d3b200_system_f32* s, const d3b200_params* p, int g, void* st) { return sys_pair<float>(s, p, g, st); }
+int d3b200_system_cnbwd_f32(const d3b200_system_f32* s, const d3b200_params* p, void* st) { return sys_cnbwd<float>(s, p, st); }
+
 
 int d3b200_abi_version(void) { return D3B200_ABI_VERSION; }
 const char* d3b200_last_error(void) { return g_err; }

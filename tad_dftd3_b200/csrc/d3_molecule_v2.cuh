@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
   // ---------------------------------------------------------------- phase 1
   // CN_i = sum_j [r_ij <= 25] / (1 + exp(-kcn (rc_ij / r_ij - 1))), pairs once
   constexpr int CNB = 4;
-  D3_PIECES_BEGIN(2)
+  D3_PIECES_BEGIN(4)
   {
     const Atom4<S> ai = sA[ic];
     S cni = S(0);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
   // ---------------------------------------------------------------- phase 3
   constexpr int PB = 2;                     // partners per iteration and half-warp
   constexpr int PV = WANT_G ? 5 : 1;        // j-side values per partner
-  D3_PIECES_BEGIN(10)
+  D3_PIECES_BEGIN(18)
   {
     const Atom4<S> ai = sA[ic];
     const Pair2<S> bi = sB[ic];
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
   // ---------------------------------------------------------------- phase 4
   // CN chain: (dL/dCN_i + dL/dCN_j) df_ij/dx, df/dx_i = -kcn rc r^-3 f(1-f) (x_i - x_j)
   constexpr int GB = 2;
-  D3_PIECES_BEGIN(2)
+  D3_PIECES_BEGIN(4)
   {
     const Atom4<S> ai = sA[ic];
     const S dci = sdecn[ic];

@@ -1,0 +1,314 @@
+// Tiled kernels for one large structure (BASELINE config 4: 50 k atoms; any
+// structure too large for the fused one-CTA kernel), and the unit of work of the
+// i-row sharded multi-GPU path.
+//
+// The host sorts the real atoms spatially (Morton order), then by element
+// inside every 128-atom tile, packs them into AoS arrays and computes the
+// bounding box of every 32-atom sub-tile.  Three grid-wide sweeps follow, with
+// per-atom stages in between (the dependencies are global, so they are
+// separate launches; on several GPUs an all-gather sits between them):
+//
+//   cn_rows      CN_i                      (r <= 25 Bohr)
+//   weights      w_i, dw_i/dCN             (per atom)
+//   pair_rows    E_i, direct dL/dx_i, dL/dCN_i   (r <= cutoff)
+//   cnbwd_rows   dL/dx_i += sum_j (dL/dCN_i + dL/dCN_j) df_ij/dx_i
+//
+// Each CTA owns 128 consecutive rows i (thread = row) and walks the j-tiles
+// whose boxes are within the cutoff of its own box; a j-tile is staged through
+// shared memory once per CTA, every warp skips 32-atom sub-tiles out of reach
+// of its 32 rows, and j is warp-uniform so the shared-memory reads are
+// broadcasts.  Rows are complete ("full-row" form: every ordered pair is
+// visited, nothing is scattered), which is what lets ranks own disjoint row
+// ranges with no reduction of the gradient.
+#pragma once
+#include "d3_molecule_v2.cuh"
+
+namespace d3 {
+
+constexpr int kSysTile = 128;   // rows per CTA = atoms per staged j-tile
+constexpr int kSysSub = 32;     // culling granularity (one warp of rows)
+
+template <typename S>
+struct SysArgs {
+  int natoms;                 // padded to a multiple of kSysTile
+  int row_begin, row_end;     // rows owned by this launch (multiples of kSysTile)
+  const Atom4<S>* atoms;      // [natoms] x, y, z, kcn * rcov   (sorted order)
+  const Pair2<S>* aux;        // [natoms] sqrt(r4r2), cotangent g
+  const int* z;               // [natoms] atomic numbers (0 = padding)
+  const S* box;               // [natoms / 32][6] min xyz, max xyz of each sub-tile
+  const S* w;                 // [natoms][8]
+  const S* dw;                // [natoms][8]
+  const S* refcn;             // [104][7]
+  const S* refc6;             // [104][104][7][7]
+  S s6, s8, a1, a2;
+  S cutoff2, cn_cutoff2, kcn;
+  S* cn;                      // [natoms]
+  S* decn;                    // [natoms]
+  S* energy;                  // [natoms]
+  S* grad;                    // [natoms][3]
+  S* wout;                    // weights kernel outputs [natoms][8]
+  S* dwout;
+};
+
+template <typename S>
+__device__ __forceinline__ S box_dist2(const S* a, const S* b) {
+  S d2 = S(0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    S lo = a[k] - b[3 + k], hi = b[k] - a[3 + k];
+    S d = lo > hi ? lo : hi;
+    d = d > S(0) ? d : S(0);
+    d2 += d * d;
+  }
+  return d2;
+}
+
+template <typename S>
+__device__ __forceinline__ void tile_box(const S* box, int tile, S* out) {
+  // union of the four sub-tile boxes of a 128-atom tile
+  const S* b = box + (size_t)tile * (kSysTile / kSysSub) * 6;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) out[k] = b[k];
+#pragma unroll
+  for (int s = 1; s < kSysTile / kSysSub; ++s) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      S lo = b[6 * s + k], hi = b[6 * s + 3 + k];
+      out[k] = lo < out[k] ? lo : out[k];
+      out[3 + k] = hi > out[3 + k] ? hi : out[3 + k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- CN sweep
+template <typename S>
+__global__ void __launch_bounds__(kSysTile) system_cn_kernel(SysArgs<S> A) {
+  __shared__ Atom4<S> sj[kSysTile];
+  const int t = threadIdx.x, wsub = t >> 5;
+  const int itile = A.row_begin / kSysTile + blockIdx.x;
+  const int i = itile * kSysTile + t;
+  const Atom4<S> ai = A.atoms[i];
+  const bool real_i = A.z[i] != 0;
+  const S tiny = tiny_of<S>();
+  S ibox[6], wbox[6];
+  tile_box(A.box, itile, ibox);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) wbox[k] = A.box[((size_t)itile * 4 + wsub) * 6 + k];
+  const int ntiles = A.natoms / kSysTile;
+  S cn = S(0);
+  for (int jt = 0; jt < ntiles; ++jt) {
+    S jbox[6];
+    tile_box(A.box, jt, jbox);
+    if (box_dist2(ibox, jbox) > A.cn_cutoff2) continue;   // CTA-uniform
+    __syncthreads();
+    sj[t] = A.atoms[(size_t)jt * kSysTile + t];
+    __syncthreads();
+    for (int sub = 0; sub < kSysTile / kSysSub; ++sub) {
+      if (box_dist2(wbox, A.box + ((size_t)jt * 4 + sub) * 6) > A.cn_cutoff2) continue;  // warp-uniform
+#pragma unroll 4
+      for (int jj = 0; jj < kSysSub; ++jj) {
+        const int jl = sub * kSysSub + jj;
+        const Atom4<S> aj = sj[jl];
+        S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+        S r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 <= A.cn_cutoff2 && (jt * kSysTile + jl) != i) {
+          S rinv = frsq(r2 + tiny);
+          S x = fmx(A.kcn - (ai.rk + aj.rk) * rinv, S(-700));
+          cn += frcp(S(1) + fex(x));
+        }
+      }
+    }
+  }
+  A.cn[i] = real_i ? cn : S(0);
+}
+
+// ---------------------------------------------------------------- weights
+template <typename S>
+__global__ void system_weights_kernel(SysArgs<S> A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.natoms) return;
+  const int Z = A.z[i];
+  S wi[kNRef], dwi[kNRef];
+  if (Z > 0) {
+    reference_weights<S>(A.refcn + Z * kNRef, A.cn[i], wi, dwi);
+  } else {
+#pragma unroll
+    for (int a = 0; a < kNRef; ++a) { wi[a] = S(0); dwi[a] = S(0); }
+  }
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) { A.wout[8 * (size_t)i + a] = wi[a]; A.dwout[8 * (size_t)i + a] = dwi[a]; }
+  A.wout[8 * (size_t)i + 7] = S(0);
+  A.dwout[8 * (size_t)i + 7] = S(0);
+}
+
+// ---------------------------------------------------------------- pair sweep
+template <typename S, bool WANT_G>
+__global__ void __launch_bounds__(kSysTile) system_pair_kernel(SysArgs<S> A) {
+  __shared__ Atom4<S> sj[kSysTile];
+  __shared__ Pair2<S> sb[kSysTile];
+  __shared__ __align__(16) S swj[kSysTile * 8];
+  __shared__ int szj[kSysTile];
+  const int t = threadIdx.x, wsub = t >> 5;
+  const int itile = A.row_begin / kSysTile + blockIdx.x;
+  const int i = itile * kSysTile + t;
+  const Atom4<S> ai = A.atoms[i];
+  const Pair2<S> bi = A.aux[i];
+  const int Zi = A.z[i];
+  const S tiny = tiny_of<S>();
+  S wi[kNRef], dwi[kNRef];
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) { wi[a] = A.w[8 * (size_t)i + a]; dwi[a] = A.dw[8 * (size_t)i + a]; }
+  S ibox[6], wbox[6];
+  tile_box(A.box, itile, ibox);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) wbox[k] = A.box[((size_t)itile * 4 + wsub) * 6 + k];
+  const int ntiles = A.natoms / kSysTile;
+  const S gi = bi.b;
+  const S s3qi = sqr(S(3)) * bi.a;
+  S e_i = S(0), gx = S(0), gy = S(0), gz = S(0), decn = S(0);
+  S U[kNRef], Ud[kNRef];
+  int Zprev = -1;
+  for (int jt = 0; jt < ntiles; ++jt) {
+    S jbox[6];
+    tile_box(A.box, jt, jbox);
+    if (box_dist2(ibox, jbox) > A.cutoff2) continue;   // CTA-uniform
+    __syncthreads();
+    {
+      const size_t j = (size_t)jt * kSysTile + t;
+      sj[t] = A.atoms[j];
+      sb[t] = A.aux[j];
+      szj[t] = A.z[j];
+      const Pair2<S>* src = reinterpret_cast<const Pair2<S>*>(A.w + 8 * j);
+      Pair2<S>* dst = reinterpret_cast<Pair2<S>*>(swj + 8 * t);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[k] = src[k];
+    }
+    __syncthreads();
+    for (int sub = 0; sub < kSysTile / kSysSub; ++sub) {
+      if (box_dist2(wbox, A.box + ((size_t)jt * 4 + sub) * 6) > A.cutoff2) continue;  // warp-uniform
+      for (int jj = 0; jj < kSysSub; ++jj) {
+        const int jl = sub * kSysSub + jj;
+        const int Zj = szj[jl];
+        if (Zj == 0) continue;                      // padding (warp-uniform)
+        if (Zj != Zprev) {
+          // U[b] = sum_a w_ia K[Zi,Zj,a,b], Ud likewise with dw_i (once per element run)
+          Zprev = Zj;
+          const S* __restrict__ K = A.refc6 + ((size_t)Zi * kMaxZ + Zj) * (kNRef * kNRef);
+#pragma unroll
+          for (int bb = 0; bb < kNRef; ++bb) { U[bb] = S(0); Ud[bb] = S(0); }
+#pragma unroll
+          for (int a = 0; a < kNRef; ++a) {
+#pragma unroll
+            for (int bb = 0; bb < kNRef; ++bb) {
+              const S k = __ldg(K + a * kNRef + bb);
+              U[bb] += wi[a] * k;
+              if (WANT_G) Ud[bb] += dwi[a] * k;
+            }
+          }
+        }
+        const Atom4<S> aj = sj[jl];
+        S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+        S r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 <= A.cutoff2 && (jt * kSysTile + jl) != i) {
+          r2 = r2 + tiny;
+          const Pair2<S> bj = sb[jl];
+          const Pair2<S>* wj = reinterpret_cast<const Pair2<S>*>(swj + 8 * jl);
+          S wv[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { Pair2<S> p = wj[k]; wv[2 * k] = p.a; wv[2 * k + 1] = p.b; }
+          S c6 = U[0] * wv[0];
+#pragma unroll
+          for (int a = 1; a < kNRef; ++a) c6 += U[a] * wv[a];
+          S tq = s3qi * bj.a;
+          S qq = tq * tq;
+          S r0 = A.a1 * tq + A.a2;
+          S r02 = r0 * r0;
+          S r06 = r02 * r02 * r02;
+          S r08 = r06 * r02;
+          S r4 = r2 * r2;
+          S r6 = r4 * r2;
+          S r8 = r4 * r4;
+          S d6 = r6 + r06, d8 = r8 + r08;
+          S inv = frcp(d6 * d8);
+          S t6 = inv * d8, t8 = inv * d6;
+          S s8q = A.s8 * qq;
+          S P = A.s6 * t6 + s8q * t8;
+          e_i += c6 * P;
+          if (WANT_G) {
+            S dc6 = Ud[0] * wv[0];
+#pragma unroll
+            for (int a = 1; a < kNRef; ++a) dc6 += Ud[a] * wv[a];
+            S gam = S(0.5) * (gi + bj.b);
+            decn -= (gam * P) * dc6;
+            S t62 = t6 * t6, t82 = t8 * t8;
+            S dP = S(3) * (A.s6 * (r4 * t62)) + S(4) * (s8q * (r6 * t82));
+            S f = (S(2) * gam) * (c6 * dP);
+            gx += f * dx; gy += f * dy; gz += f * dz;
+          }
+        }
+      }
+    }
+  }
+  const bool real_i = Zi != 0;
+  if (A.energy) A.energy[i] = real_i ? S(-0.5) * e_i : S(0);
+  if (WANT_G) {
+    A.decn[i] = real_i ? decn : S(0);
+    A.grad[3 * (size_t)i] = real_i ? gx : S(0);
+    A.grad[3 * (size_t)i + 1] = real_i ? gy : S(0);
+    A.grad[3 * (size_t)i + 2] = real_i ? gz : S(0);
+  }
+}
+
+// ---------------------------------------------------------------- CN backward
+template <typename S>
+__global__ void __launch_bounds__(kSysTile) system_cnbwd_kernel(SysArgs<S> A) {
+  __shared__ Atom4<S> sj[kSysTile];
+  __shared__ S sd[kSysTile];
+  const int t = threadIdx.x, wsub = t >> 5;
+  const int itile = A.row_begin / kSysTile + blockIdx.x;
+  const int i = itile * kSysTile + t;
+  const Atom4<S> ai = A.atoms[i];
+  const S dci = A.decn[i];
+  const S tiny = tiny_of<S>(), eps = eps_of<S>();
+  S ibox[6], wbox[6];
+  tile_box(A.box, itile, ibox);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) wbox[k] = A.box[((size_t)itile * 4 + wsub) * 6 + k];
+  const int ntiles = A.natoms / kSysTile;
+  S gx = S(0), gy = S(0), gz = S(0);
+  for (int jt = 0; jt < ntiles; ++jt) {
+    S jbox[6];
+    tile_box(A.box, jt, jbox);
+    if (box_dist2(ibox, jbox) > A.cn_cutoff2) continue;
+    __syncthreads();
+    sj[t] = A.atoms[(size_t)jt * kSysTile + t];
+    sd[t] = A.decn[(size_t)jt * kSysTile + t];
+    __syncthreads();
+    for (int sub = 0; sub < kSysTile / kSysSub; ++sub) {
+      if (box_dist2(wbox, A.box + ((size_t)jt * 4 + sub) * 6) > A.cn_cutoff2) continue;
+#pragma unroll 2
+      for (int jj = 0; jj < kSysSub; ++jj) {
+        const int jl = sub * kSysSub + jj;
+        const Atom4<S> aj = sj[jl];
+        S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+        S r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 <= A.cn_cutoff2 && r2 >= eps && (jt * kSysTile + jl) != i) {
+          S rinv = frsq(r2 + tiny);
+          S rk = ai.rk + aj.rk;
+          S e = fex(fmx(A.kcn - rk * rinv, S(-700)));
+          S f = frcp(S(1) + e);
+          S df = (rk * (rinv * rinv * rinv)) * (f * (e * f));
+          S c = (dci + sd[jl]) * df;
+          gx -= c * dx; gy -= c * dy; gz -= c * dz;
+        }
+      }
+    }
+  }
+  if (A.z[i] != 0) {
+    A.grad[3 * (size_t)i] += gx;
+    A.grad[3 * (size_t)i + 1] += gy;
+    A.grad[3 * (size_t)i + 2] += gz;
+  }
+}
+
+}  // namespace d3

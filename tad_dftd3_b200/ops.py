@@ -24,6 +24,7 @@ arbitrary leading batch dimensions; raw pointers are only taken inside
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -135,8 +136,44 @@ class _Call:
         return f(*shape, dtype=self.dtype, device=self.device)
 
 
+def _tiled(c: "_Call", order: int) -> bool:
+    """Structures beyond the one-CTA limit go to the tiled `d3b200_system_*` sweeps."""
+    if not (c.nflat and c.n):
+        return False
+    if os.environ.get("TAD_DFTD3_B200_TILED") == "1":
+        return True
+    limit = getattr(_lib.lib(), f"d3b200_batch_max_atoms_{c.sfx}")(order)
+    return c.n > limit
+
+
+def _tiled_run(c: "_Call", g, want_grad: bool):
+    from .system import SystemPlan, SystemRunner
+
+    if c.par.s9 != 0.0:
+        raise NotImplementedError(
+            "the ATM term for structures beyond the fused-kernel limit "
+            f"({c.n} atoms) is not available yet"
+        )
+    es, gs = [], []
+    for b in range(c.nflat):
+        z = c.z[b]
+        rcov = c.rcov[z] if c.st.rcov_per_element else c.rcov[b]
+        r4r2 = c.r4r2[z] if c.st.r4r2_per_element else c.r4r2[b]
+        plan = SystemPlan(z, c.x[b], rcov, r4r2, c.st.kcn)
+        run = SystemRunner(plan, c.refcn, c.refc6, c.par, None if g is None else g[b])
+        if want_grad:
+            e, gr = run.run_vjp()
+            gs.append(gr)
+        else:
+            e = run.run_energy()
+        es.append(e)
+    return torch.stack(es), (torch.stack(gs) if want_grad else None)
+
+
 def _run_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st):
     c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0)
+    if _tiled(c, 0):
+        return _tiled_run(c, None, False)[0].reshape(*c.lead, c.n)
     out = c.new(c.nflat, c.n)
     if c.nflat and c.n:
         fn = getattr(_lib.lib(), f"d3b200_batch_energy_{c.sfx}")
@@ -148,6 +185,14 @@ def _run_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st):
 
 def _run_vjp(numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6, st, want_p: bool):
     c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0)
+    if _tiled(c, 0):
+        if want_p:
+            raise NotImplementedError(
+                "damping-parameter gradients for structures beyond the fused-kernel "
+                f"limit ({c.n} atoms) are not available yet"
+            )
+        _, gr = _tiled_run(c, c.per_atom(g), True)
+        return gr.reshape(*c.lead, c.n, 3), c.new(c.nflat, NPAR, zero=True).reshape(*c.lead, NPAR)
     grad = c.new(c.nflat, c.n, 3)
     pgrad = c.new(c.nflat, NPAR, zero=True)
     if c.nflat and c.n:

@@ -1,0 +1,168 @@
+"""
+Host side of the tiled large-structure path (`d3b200_system_*`).
+
+`SystemPlan` does what the kernels expect of their caller (see
+`include/d3b200.h`): drop ghost atoms, order the real atoms along a Morton
+curve so that 32-atom sub-tiles are spatially compact, sort by element inside
+every 128-atom tile (the pair kernel re-contracts the 7x7 reference block only
+when the partner element changes), pad to a multiple of 128 with far-away
+`Z = 0` atoms, pack the AoS arrays and the sub-tile bounding boxes.
+
+`SystemRunner` owns the per-atom work arrays and issues the sweeps; row ranges
+make it the unit of work of the i-row sharded multi-GPU mode
+(`tad_dftd3_b200.distributed`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+TILE = 128
+SUB = 32
+_FAR = 1.0e8
+
+
+def _part1by2(x: Tensor) -> Tensor:
+    x = x & 0x3FF
+    x = (x | (x << 16)) & 0x30000FF
+    x = (x | (x << 8)) & 0x300F00F
+    x = (x | (x << 4)) & 0x30C30C3
+    x = (x | (x << 2)) & 0x9249249
+    return x
+
+
+def morton_order(pos: Tensor) -> Tensor:
+    """argsort of the atoms along a 30-bit Morton curve (cells of >= 4 Bohr)."""
+    lo = pos.min(0).values
+    extent = float((pos.max(0).values - lo).max())
+    cell = max(extent / 1023.0, 4.0)
+    q = ((pos - lo) / cell).to(torch.int64).clamp_(0, 1023)
+    code = _part1by2(q[:, 0]) | (_part1by2(q[:, 1]) << 1) | (_part1by2(q[:, 2]) << 2)
+    return torch.argsort(code, stable=True)
+
+
+class SystemPlan:
+    """Sorted / padded / packed view of one structure."""
+
+    def __init__(self, numbers: Tensor, positions: Tensor, rcov: Tensor, r4r2: Tensor, kcn: float):
+        dev, dt = positions.device, positions.dtype
+        self.natoms_in = numbers.shape[0]
+        idx = torch.nonzero(numbers != 0).reshape(-1)
+        n = int(idx.numel())
+        self.n = n
+        self.npad = npad = max(TILE, -(-n // TILE) * TILE)
+        pos = positions.detach()[idx]
+        z = numbers[idx]
+        if n:
+            o1 = morton_order(pos)
+            tile = torch.arange(n, device=dev) // TILE
+            o2 = torch.argsort(tile * 128 + z[o1], stable=True)
+            order = o1[o2]
+        else:
+            order = idx
+        self.perm = idx[order]                      # sorted slot -> original atom index
+        ps = pos[order]
+        zs = z[order]
+        atoms = torch.empty(npad, 4, dtype=dt, device=dev)
+        far = _FAR + torch.arange(npad - n, device=dev, dtype=dt) * 100.0
+        atoms[:n, :3] = ps
+        atoms[:n, 3] = kcn * rcov.detach().to(dt)[self.perm]
+        atoms[n:, :3] = far.unsqueeze(-1)
+        atoms[n:, 3] = 0.0
+        self.atoms = atoms
+        self.z = torch.zeros(npad, dtype=torch.int32, device=dev)
+        self.z[:n] = zs.to(torch.int32)
+        self.sqrtq = torch.ones(npad, dtype=dt, device=dev)
+        self.sqrtq[:n] = torch.sqrt(r4r2.detach().to(dt)[self.perm])
+        # sub-tile boxes over the real atoms (all-padding sub-tiles sit far away)
+        xyz = atoms[:, :3].reshape(npad // SUB, SUB, 3)
+        real = (self.z != 0).reshape(npad // SUB, SUB, 1)
+        big = torch.finfo(dt).max
+        lo = torch.where(real, xyz, xyz.new_tensor(big)).amin(1)
+        hi = torch.where(real, xyz, xyz.new_tensor(-big)).amax(1)
+        empty = ~real.any(1)
+        lo = torch.where(empty, xyz[:, 0, :], lo)
+        hi = torch.where(empty, xyz[:, 0, :], hi)
+        self.box = torch.cat([lo, hi], 1).contiguous()
+        self.dtype, self.device = dt, dev
+
+    def aux(self, g: Tensor | None) -> Tensor:
+        """[npad, 2] = sqrt(r4r2), cotangent g (ones when None)."""
+        a = torch.ones(self.npad, 2, dtype=self.dtype, device=self.device)
+        a[:, 0] = self.sqrtq
+        if g is not None:
+            a[: self.n, 1] = g.detach().to(self.dtype)[self.perm]
+        return a
+
+    def scatter(self, sorted_vals: Tensor) -> Tensor:
+        """Sorted per-atom values -> original atom order (zeros on ghosts)."""
+        out = torch.zeros(self.natoms_in, *sorted_vals.shape[1:], dtype=sorted_vals.dtype, device=self.device)
+        out[self.perm] = sorted_vals[: self.n]
+        return out
+
+
+class SystemRunner:
+    """Work arrays + launches of the four sweeps for one plan."""
+
+    def __init__(self, plan: SystemPlan, refcn: Tensor, refc6: Tensor, par: _lib.Params, g: Tensor | None = None):
+        self.plan = plan
+        dt, dev, npad = plan.dtype, plan.device, plan.npad
+        self.par = par
+        self.sfx = "f64" if dt == torch.float64 else "f32"
+        self.auxt = plan.aux(g)
+        new = lambda *s: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
+        self.cn, self.decn, self.energy = new(npad), new(npad), new(npad)
+        self.w, self.dw, self.grad = new(npad, 8), new(npad, 8), new(npad, 3)
+        self.refcn, self.refc6 = refcn, refc6
+        s = _lib.System()
+        s.natoms = npad
+        s.atoms, s.aux, s.z, s.box = (t.data_ptr() for t in (plan.atoms, self.auxt, plan.z, plan.box))
+        s.refcn, s.refc6 = refcn.data_ptr(), refc6.data_ptr()
+        s.cn, s.w, s.dw, s.decn = (t.data_ptr() for t in (self.cn, self.w, self.dw, self.decn))
+        s.energy, s.grad = self.energy.data_ptr(), self.grad.data_ptr()
+        self.sys = s
+
+    def _call(self, name, rows, *extra):
+        self.sys.row_begin, self.sys.row_end = rows if rows is not None else (0, self.plan.npad)
+        fn = getattr(_lib.lib(), f"d3b200_system_{name}_{self.sfx}")
+        _lib.launch_count += 1
+        with torch.cuda.device(self.plan.device):
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(fn(C.byref(self.sys), C.byref(self.par), *extra, stream))
+
+    def sweep_cn(self, rows=None):
+        self._call("cn", rows)
+
+    def weights(self):
+        self._call("weights", None)
+
+    def sweep_pair(self, want_grad: bool, rows=None):
+        self._call("pair", rows, int(want_grad))
+
+    def sweep_cnbwd(self, rows=None):
+        self._call("cnbwd", rows)
+
+    # single-GPU drivers -----------------------------------------------------
+    def run_energy(self) -> Tensor:
+        self.sweep_cn()
+        self.weights()
+        self.sweep_pair(False)
+        return self.plan.scatter(self.energy)
+
+    def run_vjp(self):
+        self.sweep_cn()
+        self.weights()
+        self.sweep_pair(True)
+        self.sweep_cnbwd()
+        return self.plan.scatter(self.energy), self.plan.scatter(self.grad)
+
+
+def row_partition(npad: int, world: int):
+    """Tile-aligned contiguous row ranges, one per rank."""
+    ntiles = npad // TILE
+    bounds = [TILE * ((ntiles * r) // world) for r in range(world + 1)]
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]

@@ -201,3 +201,68 @@ def test_gradcheck_positions_and_params(runs):
 
     assert torch.autograd.gradcheck(f_par, pv, atol=1e-8, fast_mode=True)
     assert torch.autograd.gradgradcheck(f_par, pv, atol=1e-8, fast_mode=True)
+
+
+# ---------------------------------------------------------------------------
+# tiled large-structure path (d3b200_system_*), forced on small inputs
+# ---------------------------------------------------------------------------
+@pytest.fixture
+def force_tiled(monkeypatch):
+    monkeypatch.setenv("TAD_DFTD3_B200_TILED", "1")
+
+
+@pytest.mark.parametrize("case", ["c1_f64", "c2_f64", "c2_cut6_f64", "mols6_f64", "water64_f64",
+                                  "crowded_f64", "pbh4_hess_f64", "c2_tpss0_f64", "c2_f32"])
+def test_tiled_path_reference_runs(runs, case, force_tiled):
+    """Same fixtures through the tiled sweeps (ghost atoms removed, Morton + element
+    sort, padding to 128, box culling)."""
+    c = runs.case(case)
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    out = run_cuda(numbers, positions, param, cutoff, dtype, g=g)
+    if dtype == torch.float32:
+        assert_close(out["energy"], c["energy"], 5e-4, 1e-8, case + " energy")
+    else:
+        assert_close(out["energy"], c["energy"], RTOL, ATOL, case + " energy")
+        assert_close(out["grad"], c["grad"], RTOL, ATOL, case + " grad")
+
+
+def test_tiled_equals_fused_on_cluster(monkeypatch):
+    """700-atom water cluster (several tiles, culling active at cutoff 20):
+    tiled path vs fused one-CTA kernel vs CPU oracle."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+
+    dtype = torch.double
+    numbers, positions = syn.water_cluster(233, seed=2)
+    refcn, refc6, *_ = tables(dtype, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    param = {"s8": torch.tensor(0.78981345), "a1": torch.tensor(0.49484001), "a2": torch.tensor(5.73083694)}
+    g = torch.linspace(0.5, 1.5, numbers.shape[0], dtype=dtype)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TAD_DFTD3_B200_TILED", mode)
+        pos = positions.to(DEV).requires_grad_(True)
+        e = d3.dftd3(numbers.to(DEV), pos, param, ref=ref, cutoff=torch.tensor(20.0))
+        (gr,) = torch.autograd.grad((e * g.to(DEV)).sum(), pos)
+        res[mode] = (e.detach().cpu(), gr.cpu())
+    assert_close(res["1"][0], res["0"][0], 1e-12, 1e-15, "tiled vs fused energy")
+    assert_close(res["1"][1], res["0"][1], 1e-11, 1e-14, "tiled vs fused grad")
+    pos = positions.clone().requires_grad_(True)
+    par = {k: v.double() for k, v in param.items()}
+    e = oracle_energy(numbers, pos, par, 20.0, dtype)
+    (gr,) = torch.autograd.grad((e * g).sum(), pos)
+    assert_close(res["1"][0], e.detach(), RTOL, ATOL, "tiled vs oracle energy")
+    assert_close(res["1"][1], gr, RTOL, ATOL, "tiled vs oracle grad")
+
+
+def test_tiled_degenerate_sizes(force_tiled):
+    """One atom, and a structure that is all ghost atoms."""
+    import tad_dftd3_b200 as d3
+
+    refcn, refc6, *_ = tables(torch.double, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    for numbers in (torch.tensor([6]), torch.tensor([0, 0, 0])):
+        pos = torch.zeros(numbers.shape[0], 3, dtype=torch.double, device=DEV, requires_grad=True)
+        e = d3.dftd3(numbers.to(DEV), pos, {"a1": torch.tensor(0.4)}, ref=ref)
+        (gr,) = torch.autograd.grad(e.sum(), pos)
+        assert (e == 0).all() and (gr == 0).all()
