@@ -172,7 +172,11 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
  *   _pair     energy[i], grad[i][3] (direct part), decn[i] = dL/dCN_i
  *             (want_grad = 0: energy only)        model/c6.py + disp.py:276-302
  *   _cnbwd    grad[i][3] += CN chain-rule term    (autograd through cn_d3)
- * g (in aux) is the cotangent of the per-atom energies, L = sum g_i E_i. */
+ * g (in aux) is the cotangent of the per-atom energies, L = sum g_i E_i.
+ * jsplit >= 1 CTAs share each 128-row tile (the j-tiles are dealt round-robin
+ * among them, which is what fills the GPU when N / 128 is small compared with
+ * the SM count); their partial rows go through `scratch`
+ * (5 * jsplit * natoms reals) and are summed in a fixed order. */
 typedef struct d3b200_system_f64 {
   int natoms, row_begin, row_end;
   const double* atoms;
@@ -187,6 +191,8 @@ typedef struct d3b200_system_f64 {
   double* decn;
   double* energy;
   double* grad;
+  int jsplit;
+  double* scratch;
 } d3b200_system_f64;
 
 typedef struct d3b200_system_f32 {
@@ -203,6 +209,8 @@ typedef struct d3b200_system_f32 {
   float* decn;
   float* energy;
   float* grad;
+  int jsplit;
+  float* scratch;
 } d3b200_system_f32;
 
 int d3b200_system_cn_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);

@@ -42,7 +42,8 @@ class System(C.Structure):
 
     _fields_ = [("natoms", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int)] + [
         (k, C.c_void_p) for k in
-        ("atoms", "aux", "z", "box", "refcn", "refc6", "cn", "w", "dw", "decn", "energy", "grad")]
+        ("atoms", "aux", "z", "box", "refcn", "refc6", "cn", "w", "dw", "decn", "energy", "grad")] + [
+        ("jsplit", C.c_int), ("scratch", C.c_void_p)]
 
 
 _P = C.c_void_p

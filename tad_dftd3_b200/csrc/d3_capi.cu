@@ -226,6 +226,8 @@ int sys_fill(d3::SysArgs<B>& a, const typename SysOf<B>::type* s, const d3b200_p
   a.z = s->z; a.box = s->box; a.w = s->w; a.dw = s->dw; a.wout = s->w; a.dwout = s->dw;
   a.refcn = s->refcn; a.refc6 = s->refc6;
   a.cn = s->cn; a.decn = s->decn; a.energy = s->energy; a.grad = s->grad;
+  a.jsplit = s->jsplit; a.part = s->scratch;
+  if (s->jsplit < 1 || !s->scratch) return fail(D3B200_EINVAL, "system scratch / jsplit missing%s");
   a.s6 = (B)par->s6; a.s8 = (B)par->s8; a.a1 = (B)par->a1; a.a2 = (B)par->a2;
   B cut = (B)par->cutoff, cncut = (B)par->cn_cutoff;
   a.cutoff2 = cut * cut; a.cn_cutoff2 = cncut * cncut; a.kcn = (B)par->kcn;
@@ -245,8 +247,10 @@ int sys_cn(const typename SysOf<B>::type* s, const d3b200_params* par, void* str
   if (!s->cn) return fail(D3B200_EINVAL, "null cn%s");
   const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
   if (nblk == 0) return D3B200_OK;
-  d3::system_cn_kernel<B><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
-  return launched("system_cn_kernel");
+  d3::system_cn_kernel<B><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  if ((rc = launched("system_cn_kernel"))) return rc;
+  d3::system_reduce_kernel<B, 0><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  return launched("system_reduce_kernel");
 }
 
 template <typename B>
@@ -268,9 +272,12 @@ int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int wan
   if (want_grad && (!s->grad || !s->decn)) return fail(D3B200_EINVAL, "null gradient output%s");
   const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
   if (nblk == 0) return D3B200_OK;
-  if (want_grad) d3::system_pair_kernel<B, true><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
-  else d3::system_pair_kernel<B, false><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
-  return launched("system_pair_kernel");
+  if (!want_grad) a.grad = nullptr;
+  if (want_grad) d3::system_pair_kernel<B, true><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  else d3::system_pair_kernel<B, false><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  if ((rc = launched("system_pair_kernel"))) return rc;
+  d3::system_reduce_kernel<B, 1><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  return launched("system_reduce_kernel");
 }
 
 template <typename B>
@@ -281,8 +288,10 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
   if (!s->decn || !s->grad) return fail(D3B200_EINVAL, "null cnbwd argument%s");
   const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
   if (nblk == 0) return D3B200_OK;
-  d3::system_cnbwd_kernel<B><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
-  return launched("system_cnbwd_kernel");
+  d3::system_cnbwd_kernel<B><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  if ((rc = launched("system_cnbwd_kernel"))) return rc;
+  d3::system_reduce_kernel<B, 2><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  return launched("system_reduce_kernel");
 }
 
 }  // namespace

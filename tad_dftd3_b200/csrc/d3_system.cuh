@@ -48,7 +48,40 @@ struct SysArgs {
   S* grad;                    // [natoms][3]
   S* wout;                    // weights kernel outputs [natoms][8]
   S* dwout;
+  int jsplit;                 // CTAs per row tile (the j-tiles are dealt round-robin)
+  S* part;                    // [5][jsplit][natoms] partial sums: E|CN, dL/dCN, gx, gy, gz
 };
+
+// Sum the jsplit partial rows of quantity q into out (fixed order: reproducible).
+template <typename S, int MODE>   // 0: cn   1: energy (+ decn, grad = ...)   2: grad +=
+__global__ void system_reduce_kernel(SysArgs<S> A) {
+  const int i = A.row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.row_end) return;
+  const size_t n = A.natoms, js = A.jsplit;
+  auto sum = [&](int q) {
+    S s = S(0);
+    for (size_t k = 0; k < js; ++k) s += A.part[(q * js + k) * n + i];
+    return s;
+  };
+  const bool real_i = A.z[i] != 0;
+  if (MODE == 0) {
+    A.cn[i] = real_i ? sum(0) : S(0);
+  } else if (MODE == 1) {
+    if (A.energy) A.energy[i] = real_i ? S(-0.5) * sum(0) : S(0);
+    if (A.grad) {
+      A.decn[i] = real_i ? sum(1) : S(0);
+      A.grad[3 * (size_t)i] = real_i ? sum(2) : S(0);
+      A.grad[3 * (size_t)i + 1] = real_i ? sum(3) : S(0);
+      A.grad[3 * (size_t)i + 2] = real_i ? sum(4) : S(0);
+    }
+  } else {
+    if (real_i) {
+      A.grad[3 * (size_t)i] += sum(2);
+      A.grad[3 * (size_t)i + 1] += sum(3);
+      A.grad[3 * (size_t)i + 2] += sum(4);
+    }
+  }
+}
 
 template <typename S>
 __device__ __forceinline__ S box_dist2(const S* a, const S* b) {
@@ -88,7 +121,6 @@ __global__ void __launch_bounds__(kSysTile) system_cn_kernel(SysArgs<S> A) {
   const int itile = A.row_begin / kSysTile + blockIdx.x;
   const int i = itile * kSysTile + t;
   const Atom4<S> ai = A.atoms[i];
-  const bool real_i = A.z[i] != 0;
   const S tiny = tiny_of<S>();
   S ibox[6], wbox[6];
   tile_box(A.box, itile, ibox);
@@ -96,7 +128,7 @@ __global__ void __launch_bounds__(kSysTile) system_cn_kernel(SysArgs<S> A) {
   for (int k = 0; k < 6; ++k) wbox[k] = A.box[((size_t)itile * 4 + wsub) * 6 + k];
   const int ntiles = A.natoms / kSysTile;
   S cn = S(0);
-  for (int jt = 0; jt < ntiles; ++jt) {
+  for (int jt = blockIdx.y; jt < ntiles; jt += A.jsplit) {
     S jbox[6];
     tile_box(A.box, jt, jbox);
     if (box_dist2(ibox, jbox) > A.cn_cutoff2) continue;   // CTA-uniform
@@ -119,7 +151,7 @@ __global__ void __launch_bounds__(kSysTile) system_cn_kernel(SysArgs<S> A) {
       }
     }
   }
-  A.cn[i] = real_i ? cn : S(0);
+  A.part[(size_t)blockIdx.y * A.natoms + i] = cn;
 }
 
 // ---------------------------------------------------------------- weights
@@ -168,7 +200,7 @@ __global__ void __launch_bounds__(kSysTile) system_pair_kernel(SysArgs<S> A) {
   S e_i = S(0), gx = S(0), gy = S(0), gz = S(0), decn = S(0);
   S U[kNRef], Ud[kNRef];
   int Zprev = -1;
-  for (int jt = 0; jt < ntiles; ++jt) {
+  for (int jt = blockIdx.y; jt < ntiles; jt += A.jsplit) {
     S jbox[6];
     tile_box(A.box, jt, jbox);
     if (box_dist2(ibox, jbox) > A.cutoff2) continue;   // CTA-uniform
@@ -249,13 +281,13 @@ __global__ void __launch_bounds__(kSysTile) system_pair_kernel(SysArgs<S> A) {
       }
     }
   }
-  const bool real_i = Zi != 0;
-  if (A.energy) A.energy[i] = real_i ? S(-0.5) * e_i : S(0);
+  const size_t n = A.natoms, js = A.jsplit, o = (size_t)blockIdx.y * n + i;
+  A.part[o] = e_i;
   if (WANT_G) {
-    A.decn[i] = real_i ? decn : S(0);
-    A.grad[3 * (size_t)i] = real_i ? gx : S(0);
-    A.grad[3 * (size_t)i + 1] = real_i ? gy : S(0);
-    A.grad[3 * (size_t)i + 2] = real_i ? gz : S(0);
+    A.part[js * n + o] = decn;
+    A.part[2 * js * n + o] = gx;
+    A.part[3 * js * n + o] = gy;
+    A.part[4 * js * n + o] = gz;
   }
 }
 
@@ -276,7 +308,7 @@ __global__ void __launch_bounds__(kSysTile) system_cnbwd_kernel(SysArgs<S> A) {
   for (int k = 0; k < 6; ++k) wbox[k] = A.box[((size_t)itile * 4 + wsub) * 6 + k];
   const int ntiles = A.natoms / kSysTile;
   S gx = S(0), gy = S(0), gz = S(0);
-  for (int jt = 0; jt < ntiles; ++jt) {
+  for (int jt = blockIdx.y; jt < ntiles; jt += A.jsplit) {
     S jbox[6];
     tile_box(A.box, jt, jbox);
     if (box_dist2(ibox, jbox) > A.cn_cutoff2) continue;
@@ -304,11 +336,10 @@ __global__ void __launch_bounds__(kSysTile) system_cnbwd_kernel(SysArgs<S> A) {
       }
     }
   }
-  if (A.z[i] != 0) {
-    A.grad[3 * (size_t)i] += gx;
-    A.grad[3 * (size_t)i + 1] += gy;
-    A.grad[3 * (size_t)i + 2] += gz;
-  }
+  const size_t n = A.natoms, js = A.jsplit, o = (size_t)blockIdx.y * n + i;
+  A.part[2 * js * n + o] = gx;
+  A.part[3 * js * n + o] = gy;
+  A.part[4 * js * n + o] = gz;
 }
 
 }  // namespace d3

@@ -1,0 +1,119 @@
+"""
+i-row sharded evaluation of ONE large structure over several GPUs
+(BASELINE config 4).
+
+One process per GPU (torchrun), NCCL through `torch.distributed`.  Every rank
+holds the whole structure (x, Z: 1.2 MB for 50 k atoms), builds the same
+`SystemPlan`, and owns a contiguous, tile-aligned range of rows of the sorted
+atom list.  The sweeps are "full-row", so a rank produces complete CN_i, E_i,
+dL/dCN_i and dL/dx_i for its rows and nothing has to be reduced; the only
+exchange steps are the ones the data dependencies force:
+
+    sweep_cn(rows)      -> all-gather CN            (N reals)
+    weights()              per-atom, redundantly on every rank (cheaper than gathering w)
+    sweep_pair(rows)    -> all-gather dL/dCN        (N reals)
+    sweep_cnbwd(rows)   -> all-gather E, dL/dx      (4 N reals)
+
+The gathers are written as all-reduce(SUM) over arrays that are zero outside
+the rank's rows: row ranges differ by a tile between ranks, the messages are
+<= 1.6 MB, i.e. latency-bound, and all-reduce is the one collective that every
+backend (NCCL here, gloo in the CPU tests) supports for ragged ownership.
+
+`run_sharded` is independent of where the sweeps run: anything with the
+`SystemRunner` interface works, which is how the world_size-2 gloo tests drive
+it on CPU.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import defaults
+from .system import SystemPlan, SystemRunner, row_partition
+
+__all__ = ["run_sharded", "dftd3_sharded"]
+
+
+def _world(group):
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _gather_rows(t: Tensor, group) -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def run_sharded(runner, want_grad: bool, group=None):
+    """Drive the sweeps of `runner` on this rank's rows and exchange the
+    per-atom arrays.  Returns the rank's row range; afterwards `runner.energy`
+    (and `runner.grad`) are complete on every rank."""
+    rank, world = _world(group)
+    rows = row_partition(runner.plan.npad, world)[rank]
+    for t in (runner.cn, runner.decn, runner.energy, runner.grad):
+        t.zero_()
+    runner.sweep_cn(rows)
+    _gather_rows(runner.cn, group)
+    runner.weights()
+    runner.sweep_pair(want_grad, rows)
+    if want_grad:
+        _gather_rows(runner.decn, group)
+        runner.sweep_cnbwd(rows)
+        _gather_rows(runner.grad, group)
+    _gather_rows(runner.energy, group)
+    return rows
+
+
+class _ShardedD3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, numbers, positions, rcov, r4r2, refcn, refc6, par, group):
+        plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn)
+        runner = SystemRunner(plan, refcn, refc6, par, None, _world(group)[1])
+        run_sharded(runner, False, group)
+        ctx.save_for_backward(numbers, positions, rcov, r4r2, refcn, refc6)
+        ctx.par, ctx.group = par, group
+        return plan.scatter(runner.energy)
+
+    @staticmethod
+    def backward(ctx, gE):
+        numbers, positions, rcov, r4r2, refcn, refc6 = ctx.saved_tensors
+        plan = SystemPlan(numbers, positions, rcov, r4r2, ctx.par.kcn)
+        runner = SystemRunner(plan, refcn, refc6, ctx.par, gE, _world(ctx.group)[1])
+        run_sharded(runner, True, ctx.group)
+        return None, plan.scatter(runner.grad), None, None, None, None, None, None
+
+
+def dftd3_sharded(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, rcov=None,
+                  r4r2=None, cutoff=None, group=None) -> Tensor:
+    """
+    `dftd3()` for one structure `(N,)`, rows sharded over the ranks of `group`
+    (two-body + CN; every rank passes the same inputs and receives the full
+    atom-resolved energy; `.backward()` gives the full gradient on every rank).
+    """
+    from . import _lib, data
+    from .disp import _check_numbers, _default_reference, _scalar
+
+    if numbers.dim() != 1 or positions.shape != (numbers.shape[0], 3):
+        raise ValueError("dftd3_sharded expects one structure: numbers (N,), positions (N, 3)")
+    if "s9" in param and bool(param["s9"] != 0.0):
+        raise NotImplementedError("the sharded path covers the two-body + CN terms")
+    _check_numbers(numbers)
+    dt, dev = positions.dtype, positions.device
+    if ref is None:
+        ref = _default_reference(dt, dev)
+    refcn, refc6, _ = ref._prepared(dev, dt)
+    if rcov is None:
+        rcov = data.COV_D3(dt, dev)[numbers]
+    if r4r2 is None:
+        r4r2 = data.R4R2(dt, dev)[numbers]
+    par = _lib.Params()
+    par.s6 = _scalar(param.get("s6", defaults.S6))
+    par.s8 = _scalar(param.get("s8", defaults.S8))
+    par.a1 = _scalar(param.get("a1", defaults.A1))
+    par.a2 = _scalar(param.get("a2", defaults.A2))
+    par.s9, par.rs9, par.alp = 0.0, defaults.RS9, defaults.ALP
+    par.cutoff = defaults.D3_DISP_CUTOFF if cutoff is None else _scalar(cutoff)
+    par.cn_cutoff, par.kcn = defaults.D3_CN_CUTOFF, defaults.D3_KCN
+    return _ShardedD3.apply(numbers, positions, rcov, r4r2, refcn, refc6, par, group)

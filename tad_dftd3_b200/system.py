@@ -108,7 +108,11 @@ class SystemPlan:
 class SystemRunner:
     """Work arrays + launches of the four sweeps for one plan."""
 
-    def __init__(self, plan: SystemPlan, refcn: Tensor, refc6: Tensor, par: _lib.Params, g: Tensor | None = None):
+    # CTAs wanted per launch: enough to give every SM several waves of 128-thread CTAs
+    TARGET_CTAS = 148 * 12
+
+    def __init__(self, plan: SystemPlan, refcn: Tensor, refc6: Tensor, par: _lib.Params, g: Tensor | None = None,
+                 world: int = 1):
         self.plan = plan
         dt, dev, npad = plan.dtype, plan.device, plan.npad
         self.par = par
@@ -124,6 +128,11 @@ class SystemRunner:
         s.refcn, s.refc6 = refcn.data_ptr(), refc6.data_ptr()
         s.cn, s.w, s.dw, s.decn = (t.data_ptr() for t in (self.cn, self.w, self.dw, self.decn))
         s.energy, s.grad = self.energy.data_ptr(), self.grad.data_ptr()
+        ntiles = npad // TILE
+        rows_tiles = max(1, ntiles // max(world, 1))
+        self.jsplit = int(max(1, min(ntiles, -(-self.TARGET_CTAS // rows_tiles))))
+        self.scratch = torch.empty(5 * self.jsplit * npad, dtype=dt, device=dev)
+        s.jsplit, s.scratch = self.jsplit, self.scratch.data_ptr()
         self.sys = s
 
     def _call(self, name, rows, *extra):

@@ -1,0 +1,177 @@
+"""
+Multi-rank logic of the i-row sharded path on CPU: world_size 2 over gloo.
+
+The CUDA sweeps cannot run here, so `run_sharded` (the code that partitions the
+rows, orders the sweeps and exchanges CN / dL/dCN / E / gradient) is driven
+with a stand-in runner whose four sweeps are dense torch expressions built on
+the CPU oracle, restricted to the rank's rows exactly like the kernels.  The
+assembled energy and gradient must equal the oracle's full result.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleRunner:
+    """`SystemRunner` interface on CPU (rows of the full-row quantities)."""
+
+    def __init__(self, plan, refcn, refc6, par, g=None):
+        import d3_oracle as orc
+
+        self.orc, self.plan, self.par = orc, plan, par
+        n = plan.npad
+        self.z = plan.z.long()
+        self.x = plan.atoms[:, :3].clone()
+        self.rcov = plan.atoms[:, 3] / par.kcn
+        self.q = plan.sqrtq ** 2
+        self.g = plan.aux(g)[:, 1]
+        self.refcn, self.refc6 = refcn, refc6
+        z = lambda *s: torch.zeros(*s, dtype=torch.double)  # noqa: E731
+        self.cn, self.decn, self.energy, self.grad = z(n), z(n), z(n), z(n, 3)
+        self.w = None
+
+    def sweep_cn(self, rows):
+        full = self.orc.cn_d3(self.z, self.x, self.rcov)
+        self.cn[rows[0]:rows[1]] = full[rows[0]:rows[1]]
+
+    def weights(self):
+        self.w_ready = True  # weights are recomputed from the gathered CN below
+
+    def _pair_terms(self, x, cn):
+        w = self.orc.weight_references(self.z, cn, self.refcn)
+        c6 = self.orc.atomic_c6(self.z, w, self.refc6)
+        p = self.par
+        return self.orc.dispersion2(self.z, x, c6, self.q, p.s6, p.s8, p.a1, p.a2, p.cutoff)
+
+    def sweep_pair(self, want_grad, rows):
+        x = self.x.clone().requires_grad_(True)
+        cn = self.cn.clone().requires_grad_(True)
+        e = self._pair_terms(x, cn)
+        sl = slice(rows[0], rows[1])
+        self.energy[sl] = e.detach()[sl]
+        if want_grad:
+            gx, gcn = torch.autograd.grad((e * self.g).sum(), (x, cn))
+            self.grad[sl] = gx[sl]
+            self.decn[sl] = gcn[sl]
+
+    def sweep_cnbwd(self, rows):
+        x = self.x.clone().requires_grad_(True)
+        cn = self.orc.cn_d3(self.z, x, self.rcov)
+        (gx,) = torch.autograd.grad((cn * self.decn).sum(), x)
+        self.grad[rows[0]:rows[1]] += gx[rows[0]:rows[1]]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tad_dftd3_b200 import _lib, synthetic as syn
+        from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+        from tad_dftd3_b200.distributed import run_sharded
+        from tad_dftd3_b200.system import SystemPlan, row_partition
+
+        dt = torch.double
+        numbers, positions = syn.water_cluster(100, seed=4)       # 300 atoms -> 3 tiles of 128
+        numbers = numbers.clone()
+        numbers[[5, 17]] = 0                                       # ghost atoms
+        par = _lib.Params()
+        par.s6, par.s8, par.a1, par.a2 = 1.0, 0.78981345, 0.49484001, 5.73083694
+        par.cutoff, par.cn_cutoff, par.kcn = 30.0, 25.0, 16.0
+        g = torch.linspace(0.5, 1.5, numbers.shape[0], dtype=dt)
+        plan = SystemPlan(numbers, positions, COV_D3(dt)[numbers], R4R2(dt)[numbers], par.kcn)
+        runner = OracleRunner(plan, REFCN(dt), syn.synthetic_c6_table(dt), par, g)
+        rows = run_sharded(runner, True)
+        assert rows == row_partition(plan.npad, world)[rank]
+        e, gr = plan.scatter(runner.energy), plan.scatter(runner.grad)
+        # every rank holds the full result
+        gathered = [torch.zeros_like(e) for _ in range(world)]
+        dist.all_gather(gathered, e)
+        assert all(torch.equal(gathered[0], t) for t in gathered)
+        if rank == 0:
+            np.savez(out, energy=e.numpy(), grad=gr.numpy(), rows=np.asarray(rows), npad=plan.npad)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_two_ranks_matches_oracle(tmp_path):
+    import d3_oracle as orc
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+
+    out = str(tmp_path / "res.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = np.load(out)
+    assert res["npad"] == 384 and tuple(res["rows"]) == (0, 128)
+
+    dt = torch.double
+    numbers, positions = syn.water_cluster(100, seed=4)
+    numbers = numbers.clone()
+    numbers[[5, 17]] = 0
+    g = torch.linspace(0.5, 1.5, numbers.shape[0], dtype=dt)
+    pos = positions.clone().requires_grad_(True)
+    param = {"s6": 1.0, "s8": 0.78981345, "a1": 0.49484001, "a2": 5.73083694}
+    e = orc.dftd3(numbers, pos, param, refcn=REFCN(dt), refc6=syn.synthetic_c6_table(dt),
+                  rcov=COV_D3(dt)[numbers], r4r2=R4R2(dt)[numbers], cutoff=30.0)
+    (gr,) = torch.autograd.grad((e * g).sum(), pos)
+    np.testing.assert_allclose(res["energy"], e.detach().numpy(), rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(res["grad"], gr.numpy(), rtol=1e-10, atol=1e-13)
+    assert (res["energy"][[5, 17]] == 0).all()
+
+
+def test_row_partition_is_tile_aligned_and_complete():
+    from tad_dftd3_b200.system import row_partition
+
+    for npad in (128, 384, 50048):
+        for world in (1, 2, 3, 4, 8):
+            parts = row_partition(npad, world)
+            assert parts[0][0] == 0 and parts[-1][1] == npad
+            for (a, b), (c, d) in zip(parts, parts[1:]):
+                assert b == c
+            assert all(a % 128 == 0 and b % 128 == 0 for a, b in parts)
+
+
+def test_plan_sorting_and_padding():
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2
+    from tad_dftd3_b200.system import SystemPlan
+
+    dt = torch.double
+    numbers, positions = syn.water_cluster(60, seed=1)
+    numbers = numbers.clone()
+    numbers[3] = 0
+    plan = SystemPlan(numbers, positions, COV_D3(dt)[numbers], R4R2(dt)[numbers], 16.0)
+    assert plan.n == 179 and plan.npad == 256
+    # permutation covers exactly the real atoms
+    assert sorted(plan.perm.tolist()) == [i for i in range(180) if i != 3]
+    # elements are sorted inside each 128-atom tile
+    z = plan.z[: plan.n].reshape(-1).tolist()
+    assert z[:128] == sorted(z[:128]) and z[128:] == sorted(z[128:])
+    # boxes bound their real atoms; padding sits far away
+    xyz = plan.atoms[:, :3].reshape(-1, 32, 3)
+    for s in range(plan.npad // 32):
+        real = plan.z.reshape(-1, 32)[s] != 0
+        if real.any():
+            assert (xyz[s][real] >= plan.box[s, :3] - 1e-12).all()
+            assert (xyz[s][real] <= plan.box[s, 3:] + 1e-12).all()
+    assert (plan.atoms[plan.n:, 0] > 1e7).all()
+    # scatter puts sorted values back and zeros on ghosts
+    vals = torch.arange(plan.npad, dtype=dt)
+    back = plan.scatter(vals)
+    assert back[3] == 0 and torch.equal(back[plan.perm], vals[: plan.n])
