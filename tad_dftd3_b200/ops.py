@@ -287,27 +287,60 @@ _V_NAMES = ("numbers", "positions", "p", "g", "rcov", "r4r2", "rvdw", "refcn", "
 _H_NAMES = ("numbers", "positions", "p", "g", "vx", "vp", "rcov", "r4r2", "rvdw", "refcn", "refc6", "st")
 
 
+def _is_functorch(x) -> bool:
+    f = torch._C._functorch
+    return isinstance(x, Tensor) and bool(f.is_batchedtensor(x) or f.is_gradtrackingtensor(x))
+
+
 class D3Energy(torch.autograd.Function):
-    """Atom-resolved D3 energies (body of the reference's dftd3(), disp.py:150-165)."""
+    """Atom-resolved D3 energies (body of the reference's dftd3(), disp.py:150-165).
+
+    When the positions require grad, forward already runs the fused
+    energy + gradient kernel with a unit cotangent and keeps dE_total/dx; a
+    backward pass whose cotangent is a broadcast scalar (`energy.sum().backward()`,
+    every stride 0) then costs one elementwise multiply instead of a second
+    sweep over the pairs.  Any other cotangent, `create_graph=True` and
+    functorch transforms take the general D3Vjp path.
+    """
 
     generate_vmap_rule = False
 
     @staticmethod
     def forward(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st):
-        return _run_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st)
+        speculate = (positions.requires_grad and not p.requires_grad and not _is_functorch(positions)
+                     and float(p.reshape(-1)[4]) == 0.0 and os.environ.get("TAD_DFTD3_B200_SPECULATE", "1") == "1")
+        if speculate:
+            c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0)
+            if c.nflat and c.n and not _tiled(c, 0):
+                energy, grad = c.new(c.nflat, c.n), c.new(c.nflat, c.n, 3)
+                ones = torch.ones(c.nflat, c.n, dtype=c.dtype, device=c.device)
+                fn = getattr(_lib.lib(), f"d3b200_batch_vjp_{c.sfx}")
+                with torch.cuda.device(c.device):
+                    _lib.check(fn(c.nflat, c.n, _ptr(c.z), _ptr(c.x), C.byref(c.model), C.byref(c.par),
+                                  _ptr(ones), _ptr(energy), _ptr(grad), None, None, C.c_size_t(0), c.stream()))
+                return energy.reshape(*c.lead, c.n), grad.reshape(*c.lead, c.n, 3)
+        e = _run_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st)
+        return e, e.new_empty(0)
 
     @staticmethod
     def setup_context(ctx, inputs, output):
         numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st = inputs
         ctx.save_for_backward(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6)
         ctx.st = st
+        ctx.grad1 = output[1] if output[1].numel() else None
+        ctx.mark_non_differentiable(output[1])
 
     @staticmethod
-    def backward(ctx, gE):
+    def backward(ctx, gE, _unused=None):
         numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6 = ctx.saved_tensors
         need_x, need_p = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         out = [None] * 9
         if not (need_x or need_p):
+            return tuple(out)
+        if (ctx.grad1 is not None and need_x and not need_p and not torch.is_grad_enabled()
+                and gE.numel() > 1 and all(s == 0 for s in gE.stride()) and not _is_functorch(gE)):
+            # uniform cotangent c: dL/dx = c * d(sum E)/dx, already computed in forward
+            out[1] = ctx.grad1 * gE.reshape(-1)[0]
             return tuple(out)
         gx, gp = D3Vjp.apply(numbers, positions, p, gE, rcov, r4r2, rvdw, refcn, refc6, ctx.st, bool(need_p))
         if need_x:
@@ -318,7 +351,8 @@ class D3Energy(torch.autograd.Function):
 
     @staticmethod
     def vmap(info, in_dims, *args):
-        return _vmap(D3Energy.apply, _E_NAMES, info, in_dims, args)
+        (e, _), _dims = _vmap(lambda *a: D3Energy.apply(*a), _E_NAMES, info, in_dims, args)
+        return (e, e.new_empty(info.batch_size, 0)), (0, 0)
 
 
 class D3Vjp(torch.autograd.Function):
@@ -387,4 +421,4 @@ class D3Hvp(torch.autograd.Function):
 
 
 def d3_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st: Settings) -> Tensor:
-    return D3Energy.apply(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st)
+    return D3Energy.apply(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st)[0]
