@@ -222,6 +222,16 @@ int d3b200_system_weights_f32(const d3b200_system_f32* sys, const d3b200_params*
 int d3b200_system_pair_f32(const d3b200_system_f32* sys, const d3b200_params* par, int want_grad, void* stream);
 int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
 
+/* ATM three-body term of the tiled path (reference damping/atm.py:86-155, ordered
+ * cutoff rule kept).  Run after `_pair` and before `_cnbwd`: ADDS (fp64 atomics,
+ * once per short edge) the three-body parts to energy[], grad[] and decn[] for
+ * the triples whose owner edge (i, j), i < j, has i in row_begin..row_end-1
+ * (any multiple of 1 here).  rvdw: `[104][104]` element-pair table. */
+int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par,
+                          const double* rvdw, int want_grad, void* stream);
+int d3b200_system_atm_f32(const d3b200_system_f32* sys, const d3b200_params* par,
+                          const float* rvdw, int want_grad, void* stream);
+
 /* Measurement utility (bench.py): launches `blocks` CTAs of 256 threads, each
  * thread running `iters` x 64 dependent-chain FMAs (8 independent chains), i.e.
  * blocks * 256 * iters * 128 flops.  `out` is one device scalar (never written

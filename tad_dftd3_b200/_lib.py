@@ -68,6 +68,7 @@ for _sfx in ("f64", "f32"):
     for _k in ("cn", "weights", "cnbwd"):
         _SIGNATURES[f"d3b200_system_{_k}_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _P], C.c_int)
     _SIGNATURES[f"d3b200_system_pair_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _I, _P], C.c_int)
+    _SIGNATURES[f"d3b200_system_atm_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _P, _I, _P], C.c_int)
 
 _lib = None
 

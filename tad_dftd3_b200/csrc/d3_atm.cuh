@@ -37,7 +37,7 @@ __device__ __forceinline__ void atm_term3(S a, S b, S c, S c9, S r0, B pexp, boo
   S s = p * q * t;
   S sr5 = s * r5inv;
   S ang = B(0.375) * sr5 + r3inv;
-  S u = pw(r0 * r1inv, pexp);
+  S u = fex(fmx(pexp * lg(r0 * r1inv), B(-700)));   // (r0 / r1)^pexp
   S fd = frcp(B(1) + B(6) * u);
   e = c9 * (ang * fd);
   S dfd0 = (B(3) * pexp) * (u * (fd * fd));       // dfd/dx = dfd0 / x

@@ -9,6 +9,7 @@
 #include "d3_molecule.cuh"
 #include "d3_molecule_v2.cuh"
 #include "d3_system.cuh"
+#include "d3_atm.cuh"
 
 namespace {
 
@@ -294,10 +295,28 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
   return launched("system_reduce_kernel");
 }
 
+template <typename B>
+int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int want_grad, void* stream) {
+  d3::AtmArgs<B> p;
+  int rc = sys_fill<B>(p.sys, s, par);
+  if (rc) return rc;
+  if (!rvdw || !s->aux || !s->w || !s->dw || !s->refc6 || !s->energy) return fail(D3B200_EINVAL, "null ATM argument%s");
+  if (want_grad && (!s->grad || !s->decn)) return fail(D3B200_EINVAL, "null ATM gradient output%s");
+  p.rvdw = rvdw;
+  p.s9 = (B)par->s9; p.rs9 = (B)par->rs9; p.pexp = (B)((par->alp + 2.0) / 3.0);
+  const int rows = p.sys.row_end - p.sys.row_begin;
+  if (rows == 0 || par->s9 == 0.0) return D3B200_OK;
+  if (want_grad) d3::system_atm_kernel<B, true><<<rows, 32 * d3::kAtmWarps, 0, (cudaStream_t)stream>>>(p);
+  else d3::system_atm_kernel<B, false><<<rows, 32 * d3::kAtmWarps, 0, (cudaStream_t)stream>>>(p);
+  return launched("system_atm_kernel");
+}
+
 }  // namespace
 
 extern "C" {
 
+int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, const double* r, int g, void* st) { return sys_atm<double>(s, p, r, g, st); }
+int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int g, void* st) { return sys_atm<float>(s, p, r, g, st); }
 int d3b200_system_cn_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_cn<double>(s, p, st); }
 int d3b200_system_weights_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_weights<double>(s, p, st); }
 int d3b200_system_pair_f64(const d3b200_system_f64* s, const d3b200_params* p, int g, void* st) { return sys_pair<double>(s, p, g, st); }

@@ -21,7 +21,8 @@ import os
 import numpy as np
 import torch
 
-__all__ = ["R4R2", "COV_D3", "VDW_PAIRWISE", "REFCN", "COV_2009_ANGSTROM", "ANGSTROM_TO_BOHR"]
+__all__ = ["R4R2", "COV_D3", "VDW_PAIRWISE", "REFCN", "COV_2009_ANGSTROM", "ANGSTROM_TO_BOHR",
+           "set_vdw_pairwise"]
 
 ANGSTROM_TO_BOHR = 1.0 / 0.529177210903
 
@@ -75,7 +76,28 @@ def REFCN(dtype: torch.dtype | None = None, device: torch.device | None = None) 
     return torch.tensor(_TABLES["refcn"], device=device, dtype=_dt(dtype))
 
 
+_registered_vdw = None
+
+
+def set_vdw_pairwise(table: torch.Tensor | None) -> None:
+    """Register the `[>=104, >=104]` D3 r0ab table that `VDW_PAIRWISE()` returns
+    (the table is not bundled; see the module docstring)."""
+    global _registered_vdw
+    if table is not None and (table.dim() != 2 or table.shape[0] < 104 or table.shape[0] != table.shape[1]):
+        raise ValueError("expected a square [>=104, >=104] table")
+    _registered_vdw = None if table is None else table.detach().clone()
+    try:  # drop cached device copies
+        from .. import disp
+
+        for k in [k for k in disp._table_cache if k[0] == "VDW_PAIRWISE"]:
+            del disp._table_cache[k]
+    except ImportError:  # pragma: no cover
+        pass
+
+
 def VDW_PAIRWISE(dtype: torch.dtype | None = None, device: torch.device | None = None) -> torch.Tensor:
+    if _registered_vdw is not None:
+        return _registered_vdw[:104, :104].to(device=device, dtype=_dt(dtype)).contiguous()
     path = os.environ.get("TAD_DFTD3_B200_R0AB", os.path.join(_HERE, "r0ab.pt"))
     if os.path.isfile(path):
         return torch.load(path, map_location=device, weights_only=True).to(_dt(dtype))

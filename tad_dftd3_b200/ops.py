@@ -149,10 +149,11 @@ def _tiled(c: "_Call", order: int) -> bool:
 def _tiled_run(c: "_Call", g, want_grad: bool):
     from .system import SystemPlan, SystemRunner
 
-    if c.par.s9 != 0.0:
+    if c.par.s9 != 0.0 and c.st.rvdw_mode != 1:
         raise NotImplementedError(
-            "the ATM term for structures beyond the fused-kernel limit "
-            f"({c.n} atoms) is not available yet"
+            "the tiled path evaluates the ATM term from the [104,104] element-pair "
+            "rvdw table only (pass rvdw=None); a dense per-pair rvdw is limited to "
+            "structures that fit the fused kernel"
         )
     es, gs = [], []
     for b in range(c.nflat):
@@ -160,7 +161,7 @@ def _tiled_run(c: "_Call", g, want_grad: bool):
         rcov = c.rcov[z] if c.st.rcov_per_element else c.rcov[b]
         r4r2 = c.r4r2[z] if c.st.r4r2_per_element else c.r4r2[b]
         plan = SystemPlan(z, c.x[b], rcov, r4r2, c.st.kcn)
-        run = SystemRunner(plan, c.refcn, c.refc6, c.par, None if g is None else g[b])
+        run = SystemRunner(plan, c.refcn, c.refc6, c.par, None if g is None else g[b], 1, c.rvdw)
         if want_grad:
             e, gr = run.run_vjp()
             gs.append(gr)

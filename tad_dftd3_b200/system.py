@@ -112,8 +112,9 @@ class SystemRunner:
     TARGET_CTAS = 148 * 12
 
     def __init__(self, plan: SystemPlan, refcn: Tensor, refc6: Tensor, par: _lib.Params, g: Tensor | None = None,
-                 world: int = 1):
+                 world: int = 1, rvdw: Tensor | None = None):
         self.plan = plan
+        self.rvdw = rvdw                      # [104, 104] element-pair table (ATM only)
         dt, dev, npad = plan.dtype, plan.device, plan.npad
         self.par = par
         self.sfx = "f64" if dt == torch.float64 else "f32"
@@ -155,17 +156,27 @@ class SystemRunner:
     def sweep_cnbwd(self, rows=None):
         self._call("cnbwd", rows)
 
+    def sweep_atm(self, want_grad: bool, rows=None):
+        """Three-body term (adds to energy / grad / decn); no-op when s9 == 0."""
+        if self.par.s9 == 0.0:
+            return
+        if self.rvdw is None:
+            raise ValueError("the ATM term needs the [104,104] rvdw table")
+        self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), int(want_grad))
+
     # single-GPU drivers -----------------------------------------------------
     def run_energy(self) -> Tensor:
         self.sweep_cn()
         self.weights()
         self.sweep_pair(False)
+        self.sweep_atm(False)
         return self.plan.scatter(self.energy)
 
     def run_vjp(self):
         self.sweep_cn()
         self.weights()
         self.sweep_pair(True)
+        self.sweep_atm(True)
         self.sweep_cnbwd()
         return self.plan.scatter(self.energy), self.plan.scatter(self.grad)
 

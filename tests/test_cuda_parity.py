@@ -23,7 +23,8 @@ RTOL, ATOL = 1e-10, 1e-12
 DEV = "cuda"
 
 
-def run_cuda(numbers, positions, param, cutoff, dtype, *, g=None, pgrad=False, explicit_tables=True):
+def run_cuda(numbers, positions, param, cutoff, dtype, *, g=None, pgrad=False, explicit_tables=True,
+             rvdw_table=False):
     import tad_dftd3_b200 as d3
 
     refcn, refc6, rcov, r4r2, rvdw = tables(dtype, DEV)
@@ -35,7 +36,14 @@ def run_cuda(numbers, positions, param, cutoff, dtype, *, g=None, pgrad=False, e
               rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)])
     if explicit_tables:
         kw.update(rcov=rcov[numbers], r4r2=r4r2[numbers])
-    e = d3.dftd3(numbers, pos, par, **kw)
+    if rvdw_table:   # element-pair table registered with the data module, rvdw=None
+        d3.data.set_vdw_pairwise(rvdw.cpu())
+        kw.pop("rvdw")
+    try:
+        e = d3.dftd3(numbers, pos, par, **kw)
+    finally:
+        if rvdw_table:
+            d3.data.set_vdw_pairwise(None)
     out = {"energy": e.detach().cpu().numpy()}
     if g is not None:
         wrt = [pos] + ([par[k] for k in ("s6", "s8", "a1", "a2") if k in par] if pgrad else [])
@@ -266,3 +274,27 @@ def test_tiled_degenerate_sizes(force_tiled):
         e = d3.dftd3(numbers.to(DEV), pos, {"a1": torch.tensor(0.4)}, ref=ref)
         (gr,) = torch.autograd.grad(e.sum(), pos)
         assert (e == 0).all() and (gr == 0).all()
+
+
+@pytest.mark.parametrize("case", ["c1_atm_f64", "c2_atm_f64", "c2_atm_cut8_f64", "mols6_atm_f64",
+                                  "mols6_atm_cut12_f64", "water64_cut20_atm_f64", "close_f64", "ghost_f64",
+                                  "two_atoms_f64", "one_atom_f64", "c2_atm_f32"])
+def test_tiled_atm_reference_runs(runs, case, force_tiled):
+    """Three-body term of the tiled path (edge-owner enumeration, ordered cutoff rule)."""
+    c = runs.case(case)
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    out = run_cuda(numbers, positions, param, cutoff, dtype, g=g, rvdw_table=True)
+    if dtype == torch.float32:
+        assert_close(out["energy"], c["energy"], 5e-4, 1e-8, case + " energy")
+    else:
+        assert_close(out["energy"], c["energy"], RTOL, ATOL, case + " energy")
+        assert_close(out["grad"], c["grad"], RTOL, ATOL, case + " grad")
+
+
+def test_rvdw_table_equals_dense(runs):
+    """rvdw=None with a registered element-pair table == dense per-pair rvdw (fused kernel)."""
+    c = runs.case("mols6_atm_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    a = run_cuda(numbers, positions, param, cutoff, dtype, g=g)
+    b = run_cuda(numbers, positions, param, cutoff, dtype, g=g, rvdw_table=True)
+    assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["grad"], b["grad"])
