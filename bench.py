@@ -203,7 +203,8 @@ def main():
     ap.add_argument("--nmol", type=int, default=4096)
     ap.add_argument("--ref-nmol", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
+    ap.add_argument("--cutoff", type=float, default=25.0, help="c5a: dispersion/triple cutoff in Bohr")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5a", "c5b"],
                     help="c3: 4096-molecule batch (default, the headline metric); "
                          "c4: one 50k-atom water cluster, rows sharded over the GPUs")
     ap.add_argument("--nwater", type=int, default=16667)
@@ -231,6 +232,12 @@ def main():
 
     lib = _lib.lib()
     dt = torch.double
+    if args.workload == "c5a":
+        run_c5a(args, rank, local, world, dev)
+        return
+    if args.workload == "c5b":
+        run_c5b(args, rank, local, world, dev)
+        return
     if args.workload == "c4":
         run_c4(args, rank, local, world, dev)
         if world > 1:
@@ -518,6 +525,121 @@ def run_c4(args, rank, local, world, dev):
             "clocks": clocks.summary(),
         }
         print(json.dumps(line))
+
+
+def count_triples(positions, cutoff):
+    """Unordered triples with at least two edges <= cutoff (the ones the reference's
+    ordered rule includes for some ordering): sum_i C(n_i, 2) - 2 * #triangles."""
+    n = positions.shape[0]
+    adj = (torch.cdist(positions, positions) <= cutoff)
+    adj.fill_diagonal_(False)
+    deg = adj.sum(1).double()
+    wedges = float((deg * (deg - 1) / 2).sum())
+    a = adj.float()
+    tri = 0.0
+    for lo in range(0, n, 2048):
+        tri += float(((a[lo:lo + 2048] @ a) * a[lo:lo + 2048]).double().sum())
+    tri /= 6.0
+    return int(round(wedges - 2.0 * tri)), int(round(tri)), int(adj.sum().item() // 2)
+
+
+def run_c5a(args, rank, local, world, dev):
+    """BASELINE config 5a: ATM three-body term on a 10k-atom water cluster with a triple cutoff."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import _lib
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+    from tad_dftd3_b200.system import SystemPlan, SystemRunner
+
+    if rank != 0:
+        return
+    dt = torch.double
+    lib = _lib.lib()
+    stream = torch.cuda.current_stream(dev)
+    nwater = 3334 if args.nwater == 16667 else args.nwater
+    numbers, positions = syn.water_cluster(nwater, seed=0)
+    numbers, positions = numbers.to(dev), positions.to(dev)
+    triples, triangles, edges = count_triples(positions, args.cutoff)
+    ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
+    refcn, refc6, _ = ref._prepared(dev, dt)
+    rcov, r4r2 = COV_D3(dt, dev)[numbers], R4R2(dt, dev)[numbers]
+    rvdw = syn.synthetic_rvdw_table(dt, dev)
+    par = _lib.Params()
+    par.s6, par.s8, par.a1, par.a2 = PARAM["s6"], PARAM["s8"], PARAM["a1"], PARAM["a2"]
+    par.s9, par.rs9, par.alp = 1.0, 1.3333333730697632, 14.0
+    par.cutoff, par.cn_cutoff, par.kcn = args.cutoff, 25.0, 16.0
+    g = torch.ones(numbers.shape[0], dtype=dt, device=dev)
+    t_atm, t_all = [], []
+    with ClockSampler(local) as clocks:
+        for it in range(args.warmup + args.steps):
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record(stream)
+            plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn)
+            run = SystemRunner(plan, refcn, refc6, par, g, 1, rvdw)
+            run.sweep_cn(); run.weights(); run.sweep_pair(True)
+            e1.record(stream)
+            run.sweep_atm(True)
+            e2.record(stream)
+            run.sweep_cnbwd()
+            energy, grad = plan.scatter(run.energy), plan.scatter(run.grad)
+            e3.record(stream)
+            torch.cuda.synchronize(dev)
+            if it >= args.warmup:
+                t_atm.append(e1.elapsed_time(e2)); t_all.append(e0.elapsed_time(e3))
+    ms_atm, ms_all = float(np.mean(t_atm)), float(np.mean(t_all))
+    peak = fp64_peak(lib, dev, stream)
+    achieved = triples * 140.0 / (ms_atm * 1e-3) / 1e12
+    line = {
+        "metric": "ATM energy+grad triples/s fp64", "value": triples / (ms_atm * 1e-3), "unit": "triples/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_atm,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"c5a: ATM (s9=1) on a {numbers.shape[0]}-atom water cluster, triple cutoff {args.cutoff} Bohr, energy+grad fp64",
+                   "triples": triples, "all_short_triangles": triangles, "short_edges": edges,
+                   "entry": "d3b200_system_atm_f64 (timed alone with CUDA events); whole dftd3 step in whole_step_ms",
+                   "whole_step_ms": ms_all, "total_energy": float(energy.sum())},
+        "gpu_launches": 5 * (args.steps + args.warmup),
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "d3::system_atm_kernel<double, true>",
+                     "flops_model": "140 per unordered triple (SURVEY.md 8d)"},
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line))
+
+
+def run_c5b(args, rank, local, world, dev):
+    """BASELINE config 5b: Hessian of a 200-atom molecule by the examples/hessian.py construction."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import REFCN
+
+    if rank != 0:
+        return
+    dt = torch.double
+    numbers, positions = syn.drug_like_batch(1, 200, 200, seed=1)
+    numbers, positions = numbers[0].to(dev), positions[0].to(dev)
+    ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
+    param = {k: torch.tensor(v, dtype=dt) for k, v in PARAM.items()}
+
+    def energy(pos):
+        return d3.dftd3(numbers, pos, param, ref=ref).sum(-1)
+
+    hess = torch.func.jacrev(torch.func.jacrev(energy))
+    times = []
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        h = hess(positions)
+        torch.cuda.synchronize(dev)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    sym = float((h.reshape(600, 600) - h.reshape(600, 600).T).abs().max())
+    line = {"metric": "Hessian (jacrev o jacrev) wall time, 200 atoms, two-body + CN, fp64", "value": float(np.mean(times)),
+            "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c5b: examples/hessian.py construction on one 200-atom chain-grown molecule",
+                       "hessian_shape": list(h.shape), "max_asymmetry": sym,
+                       "reference_cpu_seconds_survey": 10.6}}
+    print(json.dumps(line))
 
 
 def _measured_hbm():

@@ -232,6 +232,40 @@ int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par
 int d3b200_system_atm_f32(const d3b200_system_f32* sys, const d3b200_params* par,
                           const float* rvdw, int want_grad, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Stage-level entry points (forward only): the reference's operator API keeps
+ * the intermediates as dense tensors (README.rst:238-261, test/test_disp/
+ * test_disp.py feeds an external c6).  Padded-batch layout as above.
+ *   _stage_cn      cn[B][N]          tad-mctc cn_d3 / exp_count (rcov per atom [B][N])
+ *   _stage_weights w[n][7]           model/weights.py:104-176 (n = B*N atoms, flat)
+ *   _stage_c6      c6[B][N][N]       model/c6.py:186-217
+ *   _stage_disp2   energy[B][N]      disp.py:276-302 with dense c6 and per-atom r4r2
+ *   _stage_atm     energy[B][N]      damping/atm.py:86-155 with dense c6 and rvdw [B][N][N] */
+int d3b200_stage_cn_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
+                        const double* rcov, double cutoff, double kcn, double* cn, void* stream);
+int d3b200_stage_weights_f64(size_t n, const int64_t* numbers, const double* cn, const double* refcn,
+                             double* weights, void* stream);
+int d3b200_stage_c6_f64(int nbatch, int natoms, const int64_t* numbers, const double* weights,
+                        const double* refc6, double* c6, void* stream);
+int d3b200_stage_disp2_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
+                           const double* c6, const double* r4r2, const d3b200_params* par,
+                           double* energy, void* stream);
+int d3b200_stage_atm_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
+                         const double* c6, const double* rvdw, const d3b200_params* par,
+                         double* energy, void* stream);
+int d3b200_stage_cn_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
+                        const float* rcov, double cutoff, double kcn, float* cn, void* stream);
+int d3b200_stage_weights_f32(size_t n, const int64_t* numbers, const float* cn, const float* refcn,
+                             float* weights, void* stream);
+int d3b200_stage_c6_f32(int nbatch, int natoms, const int64_t* numbers, const float* weights,
+                        const float* refc6, float* c6, void* stream);
+int d3b200_stage_disp2_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
+                           const float* c6, const float* r4r2, const d3b200_params* par,
+                           float* energy, void* stream);
+int d3b200_stage_atm_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
+                         const float* c6, const float* rvdw, const d3b200_params* par,
+                         float* energy, void* stream);
+
 /* Measurement utility (bench.py): launches `blocks` CTAs of 256 threads, each
  * thread running `iters` x 64 dependent-chain FMAs (8 independent chains), i.e.
  * blocks * 256 * iters * 128 flops.  `out` is one device scalar (never written

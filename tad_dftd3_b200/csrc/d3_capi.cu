@@ -10,6 +10,7 @@
 #include "d3_molecule_v2.cuh"
 #include "d3_system.cuh"
 #include "d3_atm.cuh"
+#include "d3_stages.cuh"
 
 namespace {
 
@@ -311,9 +312,67 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
   return launched("system_atm_kernel");
 }
 
+// ---------------------------------------------------------------- stages
+template <typename B>
+int stage_cn(int nb, int n, const int64_t* z, const B* x, const B* rcov, double cutoff, double kcn, B* cn, void* st) {
+  if (nb < 0 || n < 0 || !z || !x || !rcov || !cn) return fail(D3B200_EINVAL, "bad stage_cn argument%s");
+  if (!nb || !n) return D3B200_OK;
+  B c = (B)cutoff;
+  d3::stage_cn_kernel<B><<<dim3((n + 127) / 128, nb), 128, 0, (cudaStream_t)st>>>(n, z, x, rcov, c * c, (B)kcn, cn);
+  return launched("stage_cn_kernel");
+}
+template <typename B>
+int stage_weights(size_t n, const int64_t* z, const B* cn, const B* refcn, B* w, void* st) {
+  if (!z || !cn || !refcn || !w) return fail(D3B200_EINVAL, "bad stage_weights argument%s");
+  if (!n) return D3B200_OK;
+  d3::stage_weights_kernel<B><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)st>>>(n, z, cn, refcn, w);
+  return launched("stage_weights_kernel");
+}
+template <typename B>
+int stage_c6(int nb, int n, const int64_t* z, const B* w, const B* refc6, B* c6, void* st) {
+  if (nb < 0 || n < 0 || !z || !w || !refc6 || !c6) return fail(D3B200_EINVAL, "bad stage_c6 argument%s");
+  if (!nb || !n) return D3B200_OK;
+  if (nb > 65535 || n > 65535) return fail(D3B200_ESIZE, "stage_c6: batch or structure too large%s");
+  d3::stage_c6_kernel<B><<<dim3((n + 127) / 128, n, nb), 128, 0, (cudaStream_t)st>>>(n, z, w, refc6, c6);
+  return launched("stage_c6_kernel");
+}
+template <typename B>
+int stage_disp2(int nb, int n, const int64_t* z, const B* x, const B* c6, const B* q, const d3b200_params* p, B* e, void* st) {
+  if (nb < 0 || n < 0 || !z || !x || !c6 || !q || !p || !e) return fail(D3B200_EINVAL, "bad stage_disp2 argument%s");
+  if (!nb || !n) return D3B200_OK;
+  B c = (B)p->cutoff;
+  d3::stage_disp2_kernel<B><<<dim3((n + 127) / 128, nb), 128, 0, (cudaStream_t)st>>>(
+      n, z, x, c6, q, (B)p->s6, (B)p->s8, (B)p->a1, (B)p->a2, c * c, e);
+  return launched("stage_disp2_kernel");
+}
+template <typename B>
+int stage_atm(int nb, int n, const int64_t* z, const B* x, const B* c6, const B* rvdw, const d3b200_params* p, B* e, void* st) {
+  if (nb < 0 || n < 0 || !z || !x || !c6 || !rvdw || !p || !e) return fail(D3B200_EINVAL, "bad stage_atm argument%s");
+  if (!nb || !n) return D3B200_OK;
+  B c = (B)p->cutoff;
+  d3::stage_atm_kernel<B><<<dim3((n + 63) / 64, nb), 64, 0, (cudaStream_t)st>>>(
+      n, z, x, c6, rvdw, c * c, (B)p->s9, (B)p->rs9, (B)((p->alp + 2.0) / 3.0), e);
+  return launched("stage_atm_kernel");
+}
+
 }  // namespace
 
 extern "C" {
+
+#define D3_STAGE_API(SFX, T)                                                                                  \
+  int d3b200_stage_cn_##SFX(int nb, int n, const int64_t* z, const T* x, const T* rcov, double cutoff,       \
+                            double kcn, T* cn, void* st) { return stage_cn<T>(nb, n, z, x, rcov, cutoff, kcn, cn, st); } \
+  int d3b200_stage_weights_##SFX(size_t n, const int64_t* z, const T* cn, const T* refcn, T* w, void* st) {  \
+    return stage_weights<T>(n, z, cn, refcn, w, st); }                                                        \
+  int d3b200_stage_c6_##SFX(int nb, int n, const int64_t* z, const T* w, const T* refc6, T* c6, void* st) {  \
+    return stage_c6<T>(nb, n, z, w, refc6, c6, st); }                                                         \
+  int d3b200_stage_disp2_##SFX(int nb, int n, const int64_t* z, const T* x, const T* c6, const T* q,         \
+                               const d3b200_params* p, T* e, void* st) { return stage_disp2<T>(nb, n, z, x, c6, q, p, e, st); } \
+  int d3b200_stage_atm_##SFX(int nb, int n, const int64_t* z, const T* x, const T* c6, const T* rvdw,        \
+                             const d3b200_params* p, T* e, void* st) { return stage_atm<T>(nb, n, z, x, c6, rvdw, p, e, st); }
+D3_STAGE_API(f64, double)
+D3_STAGE_API(f32, float)
+#undef D3_STAGE_API
 
 int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, const double* r, int g, void* st) { return sys_atm<double>(s, p, r, g, st); }
 int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int g, void* st) { return sys_atm<float>(s, p, r, g, st); }

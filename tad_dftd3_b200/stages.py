@@ -1,22 +1,215 @@
-"""Stage-level drop-ins (cn_d3, weight_references, atomic_c6, dispersion*).
+"""
+Stage-level drop-ins: the reference's operator API
+(`ncoord.cn_d3`, `model.weight_references`, `model.atomic_c6`,
+`disp.dispersion/dispersion2/dispersion3`, `damping.dispersion_atm`), each on
+its own CUDA kernel (`d3b200_stage_*`), with the reference's shapes, defaults
+and `ValueError`s (README.rst:238-261, disp.py:168-347, damping/atm.py:43-155).
 
-Filled in after the fused path; each raises until its kernel exists so that
-nothing silently falls back to torch-eager arithmetic.
+These keep the dense intermediates (`c6 [..., N, N]`) that the fused `dftd3()`
+path never materialises, and they are FORWARD ONLY: differentiable use goes
+through `dftd3()`, whose analytic derivatives cover the whole chain.  Inputs
+that require grad are rejected instead of being silently detached.
 """
 from __future__ import annotations
 
+import ctypes as C
 
-def _todo(name):
-    def f(*a, **k):
-        raise NotImplementedError(f"tad_dftd3_b200.{name}: stage-level kernel not built yet")
+import torch
+from torch import Tensor
 
-    return f
+from . import _lib, data, defaults
+
+__all__ = ["cn_d3", "weight_references", "atomic_c6", "dispersion", "dispersion2", "dispersion3",
+           "dispersion_atm"]
 
 
-cn_d3 = _todo("ncoord.cn_d3")
-weight_references = _todo("model.weight_references")
-atomic_c6 = _todo("model.atomic_c6")
-dispersion = _todo("disp.dispersion")
-dispersion2 = _todo("disp.dispersion2")
-dispersion3 = _todo("disp.dispersion3")
-dispersion_atm = _todo("damping.dispersion_atm")
+def _sfx(dtype):
+    if dtype == torch.float64:
+        return "f64"
+    if dtype == torch.float32:
+        return "f32"
+    raise TypeError(f"float32 or float64 expected, got {dtype}")
+
+
+def _cuda(t: Tensor, what: str):
+    if t.device.type != "cuda":
+        raise RuntimeError(f"tad_dftd3_b200 runs on CUDA devices only (no CPU fallback); {what} is on {t.device}")
+
+
+def _no_grad(*tensors):
+    for t in tensors:
+        if isinstance(t, Tensor) and t.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "the stage-level functions of tad_dftd3_b200 are forward only; "
+                "use dftd3() for derivatives (or wrap the call in torch.no_grad())"
+            )
+
+
+def _stream(dev):
+    _lib.launch_count += 1
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _z(numbers: Tensor) -> Tensor:
+    return (numbers if numbers.dtype == torch.int64 else numbers.to(torch.int64)).contiguous()
+
+
+def _scalar(v, default=None) -> float:
+    if v is None:
+        return float(default)
+    return float(v.detach()) if isinstance(v, Tensor) else float(v)
+
+
+def _check_z(numbers: Tensor):
+    from .disp import _check_numbers
+
+    _check_numbers(numbers)
+
+
+def cn_d3(numbers, positions, *, counting_function=None, rcov=None, cutoff=None, **kwargs):
+    from .ncoord import exp_count
+
+    if counting_function is not None and counting_function is not exp_count:
+        raise NotImplementedError("only the default exp_count counting function is implemented")
+    _cuda(positions, "positions")
+    _no_grad(positions, rcov)
+    dt, dev = positions.dtype, positions.device
+    if rcov is None:
+        rcov = data.COV_D3(dt, dev)[numbers]
+    if numbers.shape != rcov.shape:
+        raise ValueError(f"Shape of covalent radii {tuple(rcov.shape)} is not consistent with ({tuple(numbers.shape)}).")
+    if numbers.shape != positions.shape[:-1]:
+        raise ValueError(
+            f"Shape of positions ({tuple(positions.shape[:-1])}) is not consistent with atomic numbers ({tuple(numbers.shape)})."
+        )
+    n = numbers.shape[-1]
+    z = _z(numbers).reshape(-1, n)
+    x = positions.detach().reshape(-1, n, 3).contiguous()
+    rc = rcov.detach().to(dt).reshape(-1, n).contiguous()
+    out = torch.empty(z.shape, dtype=dt, device=dev)
+    fn = getattr(_lib.lib(), f"d3b200_stage_cn_{_sfx(dt)}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(rc), _scalar(cutoff, defaults.D3_CN_CUTOFF),
+                      float(kwargs.get("kcn", defaults.D3_KCN)), _p(out), _stream(dev)))
+    return out.reshape(numbers.shape)
+
+
+def weight_references(numbers, cn, reference, weighting_function=None, **kwargs):
+    from .model import gaussian_weight
+
+    if weighting_function is not None and weighting_function is not gaussian_weight or kwargs:
+        raise NotImplementedError("only the default gaussian_weight (factor 4) is implemented")
+    _cuda(cn, "cn")
+    _no_grad(cn)
+    dt, dev = cn.dtype, cn.device
+    refcn, _, _ = reference._prepared(dev, dt)
+    z = _z(numbers).reshape(-1)
+    c = cn.detach().reshape(-1).contiguous()
+    out = torch.empty(z.shape[0], 7, dtype=dt, device=dev)
+    fn = getattr(_lib.lib(), f"d3b200_stage_weights_{_sfx(dt)}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(C.c_size_t(z.shape[0]), _p(z), _p(c), _p(refcn), _p(out), _stream(dev)))
+    return out.reshape(*numbers.shape, 7)
+
+
+def atomic_c6(numbers, weights, reference, chunk_size=None):
+    """Dense `[..., N, N]` C6 matrix.  `chunk_size` is accepted and ignored: the
+    kernel never builds the reference's `N x N x 7 x 7` gather."""
+    _cuda(weights, "weights")
+    _no_grad(weights)
+    dt, dev = weights.dtype, weights.device
+    _, refc6, _ = reference._prepared(dev, dt)
+    n = numbers.shape[-1]
+    z = _z(numbers).reshape(-1, n)
+    w = weights.detach().reshape(-1, n, 7).contiguous()
+    out = torch.empty(z.shape[0], n, n, dtype=dt, device=dev)
+    fn = getattr(_lib.lib(), f"d3b200_stage_c6_{_sfx(dt)}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(z.shape[0], n, _p(z), _p(w), _p(refc6), _p(out), _stream(dev)))
+    return out.reshape(*numbers.shape, n)
+
+
+def _params(param: dict, cutoff, dt) -> _lib.Params:
+    p = _lib.Params()
+    p.s6 = _scalar(param.get("s6"), defaults.S6)
+    p.s8 = _scalar(param.get("s8"), defaults.S8)
+    p.a1 = _scalar(param.get("a1"), defaults.A1)
+    p.a2 = _scalar(param.get("a2"), defaults.A2)
+    p.s9 = _scalar(param.get("s9"), defaults.S9)
+    p.alp = _scalar(param.get("alp"), defaults.ALP)
+    p.rs9 = float(torch.tensor(defaults.RS9))  # float32(4/3), reference disp.py:312
+    p.cutoff = _scalar(cutoff, defaults.D3_DISP_CUTOFF)
+    p.cn_cutoff, p.kcn = defaults.D3_CN_CUTOFF, defaults.D3_KCN
+    return p
+
+
+def _prep(numbers, positions, c6):
+    _cuda(positions, "positions")
+    dt, dev = positions.dtype, positions.device
+    n = numbers.shape[-1]
+    z = _z(numbers).reshape(-1, n)
+    x = positions.detach().reshape(-1, n, 3).contiguous()
+    c = c6.detach().to(dt).reshape(-1, n, n).contiguous()
+    return dt, dev, n, z, x, c
+
+
+def dispersion2(numbers, positions, param, c6, r4r2, damping_function=None, cutoff=None, **kwargs):
+    from .damping import rational_damping
+
+    if damping_function is not None and damping_function is not rational_damping or kwargs:
+        raise NotImplementedError("only the default rational (Becke-Johnson) damping is implemented")
+    _no_grad(positions, c6, *param.values())
+    dt, dev, n, z, x, c = _prep(numbers, positions, c6)
+    q = r4r2.detach().to(dt).reshape(-1, n).contiguous()
+    par = _params(param, cutoff, dt)
+    out = torch.empty(z.shape, dtype=dt, device=dev)
+    fn = getattr(_lib.lib(), f"d3b200_stage_disp2_{_sfx(dt)}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(c), _p(q), C.byref(par), _p(out), _stream(dev)))
+    return out.reshape(numbers.shape)
+
+
+def dispersion_atm(numbers, positions, c6, rvdw, cutoff, s9=None, rs9=None, alp=None):
+    _no_grad(positions, c6)
+    dt, dev, n, z, x, c = _prep(numbers, positions, c6)
+    rv = rvdw.detach().to(dt).reshape(-1, n, n).contiguous()
+    par = _lib.Params()
+    par.s9 = _scalar(s9, defaults.S9)
+    par.alp = _scalar(alp, defaults.ALP)
+    # the reference's default rs9 tensor is float32(4/3) (damping/atm.py:50)
+    par.rs9 = float(torch.tensor(defaults.RS9)) if rs9 is None else float(rs9.detach().to(dt))
+    par.cutoff = _scalar(cutoff, defaults.D3_DISP_CUTOFF)
+    out = torch.empty(z.shape, dtype=dt, device=dev)
+    fn = getattr(_lib.lib(), f"d3b200_stage_atm_{_sfx(dt)}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(c), _p(rv), C.byref(par), _p(out), _stream(dev)))
+    return out.reshape(numbers.shape)
+
+
+def dispersion3(numbers, positions, param, c6, rvdw, cutoff, rs9=None):
+    return dispersion_atm(numbers, positions, c6, rvdw, cutoff,
+                          param.get("s9", defaults.S9), rs9, param.get("alp", defaults.ALP))
+
+
+def dispersion(numbers, positions, param, c6, rvdw=None, r4r2=None, damping_function=None, cutoff=None,
+               **kwargs):
+    """Two-body (+ ATM if `param["s9"] != 0`) energy from a caller-provided dense c6
+    (reference disp.py:168-242)."""
+    dt, dev = positions.dtype, positions.device
+    if r4r2 is None:
+        r4r2 = data.R4R2(dt, dev)[numbers]
+    if numbers.shape != positions.shape[:-1]:
+        raise ValueError("Shape of positions is not consistent with atomic numbers.")
+    if numbers.shape != r4r2.shape:
+        raise ValueError("Shape of expectation values is not consistent with atomic numbers.")
+    _check_z(numbers)
+    energy = dispersion2(numbers, positions, param, c6, r4r2, damping_function, cutoff, **kwargs)
+    if "s9" in param and bool(param["s9"] != 0.0):
+        if rvdw is None:
+            rvdw = data.VDW_PAIRWISE(dt, dev)[numbers.unsqueeze(-1), numbers.unsqueeze(-2)]
+        energy = energy + dispersion3(numbers, positions, param, c6, rvdw, cutoff)
+    return energy

@@ -298,3 +298,69 @@ def test_rvdw_table_equals_dense(runs):
     a = run_cuda(numbers, positions, param, cutoff, dtype, g=g)
     b = run_cuda(numbers, positions, param, cutoff, dtype, g=g, rvdw_table=True)
     assert np.array_equal(a["energy"], b["energy"]) and np.array_equal(a["grad"], b["grad"])
+
+
+# ---------------------------------------------------------------------------
+# stage-level drop-ins (README.rst:238-261 operator API)
+# ---------------------------------------------------------------------------
+def test_stage_functions_match_reference_stages(runs):
+    """cn_d3 -> weight_references -> atomic_c6 -> dispersion on the README batch,
+    against the unmodified reference's own intermediates."""
+    import tad_dftd3_b200 as d3
+
+    c, r = runs.case("stages_c2"), runs.case("c2_atm_f64")
+    dt = torch.double
+    numbers = torch.from_numpy(r["numbers"]).to(DEV)
+    positions = torch.from_numpy(r["positions"]).to(DEV)
+    refcn, refc6, rcov, r4r2, rvdw = tables(dt, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    cn = d3.ncoord.cn_d3(numbers, positions, counting_function=d3.ncoord.exp_count, rcov=rcov[numbers])
+    w = d3.model.weight_references(numbers, cn, ref)
+    c6 = d3.model.atomic_c6(numbers, w, ref)
+    param = {str(k): torch.tensor(float(v), dtype=dt) for k, v in zip(r["param_keys"], r["param_vals"])}
+    e = d3.disp.dispersion(numbers, positions, param, c6,
+                           rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)], r4r2[numbers])
+    assert_close(cn.cpu(), c["cn"], RTOL, ATOL, "cn")
+    assert_close(w.cpu(), c["weights"], RTOL, ATOL, "weights")
+    assert_close(c6.cpu(), c["c6"], RTOL, ATOL, "c6")
+    assert_close(e.cpu(), c["energy"], RTOL, ATOL, "dispersion")
+    # the staged route and the fused route agree
+    fused = d3.dftd3(numbers, positions, param, ref=ref,
+                     rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)])
+    assert_close(e.cpu(), fused.cpu(), RTOL, ATOL, "staged vs fused")
+
+
+@pytest.mark.parametrize("name", ["PbH4_BiH3", "C6H5I_CH3SH"])
+def test_stage_pins_from_reference_tests(pins, name):
+    """Values held by the reference's own tests: CN from the in-tree geometry
+    (test_model/samples.py), weights from the pinned CN, and disp2 from the pinned
+    dense c6 with TPSS0-D3BJ parameters (test_disp/test_disp.py:34-46)."""
+    import tad_dftd3_b200 as d3
+
+    c = pins.case(name)
+    dt = torch.double
+    numbers = torch.from_numpy(c["numbers"]).to(DEV)
+    positions = torch.from_numpy(c["positions"]).to(DEV)
+    n = numbers.shape[0]
+    cn = d3.ncoord.cn_d3(numbers, positions)
+    assert_close(cn.cpu(), c["cn"], 0, 5e-11, name + " cn")
+    ref = d3.Reference(cn=tables(dt, DEV)[0], c6=tables(dt, DEV)[1])
+    w = d3.model.weight_references(numbers, torch.from_numpy(c["cn"]).to(DEV), ref)
+    assert_close(w.cpu(), c["weights"].reshape(n, 7), 0, 1e-13, name + " weights")
+    param = {k: torch.tensor(v, dtype=dt) for k, v in
+             (("s6", 1.0), ("s8", 1.2576), ("a1", 0.3768), ("a2", 4.5865))}
+    e = d3.disp.dispersion(numbers, positions, param, torch.from_numpy(c["c6"]).reshape(n, n).to(DEV))
+    loose = name == "C6H5I_CH3SH"  # README geometry carries fewer digits than the pinned run
+    assert_close(e.cpu(), c["disp2"], 1e-9 if loose else 1e-13, 2e-11 if loose else 1e-16, name + " disp2")
+
+
+def test_stage_functions_are_forward_only():
+    import tad_dftd3_b200 as d3
+
+    numbers = torch.tensor([8, 1, 1], device=DEV)
+    pos = torch.tensor([[0.0, 0.0, -0.7], [1.4, 0.0, 0.4], [-1.4, 0.0, 0.4]], device=DEV, dtype=torch.double,
+                       requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        d3.ncoord.cn_d3(numbers, pos)
+    with torch.no_grad():
+        assert d3.ncoord.cn_d3(numbers, pos).shape == (3,)
