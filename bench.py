@@ -85,7 +85,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -284,7 +284,13 @@ def main():
     launches0 = _lib.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clocks:
-        # keep the GPU busy long enough for nvidia-smi to see loaded clocks
+        # untimed pre-heat (~1 s of the same step) so that nvidia-smi samples the
+        # clocks UNDER LOAD: the K timed steps alone last only a few milliseconds
+        t_heat = time.perf_counter()
+        while time.perf_counter() - t_heat < 1.0:
+            for _ in range(50):
+                step_resident()
+            torch.cuda.synchronize(dev)
         barrier()
         for a, b in ev:
             flush.zero_()
@@ -354,7 +360,8 @@ def main():
                 "pair_terms_per_gpu": pairs, "pairs_within_25_bohr": near,
                 "entry": "d3b200_batch_vjp_f64 (one fused launch: CN, weights, C6, BJ energy, analytic gradient)",
                 "l2": "256 MB buffer written between timed steps",
-                "timing": "CUDA events around each step on the launch stream, mean of steps, max over ranks",
+                "timing": "CUDA events around each step on the launch stream, mean of steps, max over ranks; "
+                          "1 s untimed pre-heat under the clock sampler",
                 "parallelism": f"structures sharded over {world} GPU(s), no data-path collective",
                 "tables": "synthetic C6 table (reference-c6.pt unavailable offline)",
             },
@@ -369,7 +376,7 @@ def main():
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / peak_tflops, "traffic": None,
-                "kernel": "d3::molecule_kernel<double, E|G>",
+                "kernel": "d3::molecule_kernel_v2<double, true>",
                 "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_model": "140/pair-term (r<=25 Bohr), 89 (25<r<=50), SURVEY.md 8(d)",
                 "hbm_gbs_measured_peak": _measured_hbm(),
