@@ -226,11 +226,17 @@ int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* p
  * cutoff rule kept).  Run after `_pair` and before `_cnbwd`: ADDS (fp64 atomics,
  * once per short edge) the three-body parts to energy[], grad[] and decn[] for
  * the triples whose owner edge (i, j), i < j, has i in row_begin..row_end-1
- * (any multiple of 1 here).  rvdw: `[104][104]` element-pair table. */
+ * (any row range).  rvdw: `[104][104]` element-pair table.
+ * Optional fast path for structures with nelem <= 8 distinct elements
+ * (nelem = 0 selects the general kernel): zlist[nelem] = the distinct atomic
+ * numbers, eidx[natoms] = index of each atom's element in zlist (-1 = padding),
+ * work = scratch of (natoms * nelem * 8 + 64) reals. */
 int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par,
-                          const double* rvdw, int want_grad, void* stream);
+                          const double* rvdw, int nelem, const int32_t* zlist,
+                          const int8_t* eidx, double* work, int want_grad, void* stream);
 int d3b200_system_atm_f32(const d3b200_system_f32* sys, const d3b200_params* par,
-                          const float* rvdw, int want_grad, void* stream);
+                          const float* rvdw, int nelem, const int32_t* zlist,
+                          const int8_t* eidx, float* work, int want_grad, void* stream);
 
 /* ------------------------------------------------------------------------
  * Stage-level entry points (forward only): the reference's operator API keeps

@@ -297,7 +297,8 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
 }
 
 template <typename B>
-int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int want_grad, void* stream) {
+int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int nelem,
+            const int32_t* zlist, const int8_t* eidx, B* work, int want_grad, void* stream) {
   d3::AtmArgs<B> p;
   int rc = sys_fill<B>(p.sys, s, par);
   if (rc) return rc;
@@ -307,8 +308,34 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
   p.s9 = (B)par->s9; p.rs9 = (B)par->rs9; p.pexp = (B)((par->alp + 2.0) / 3.0);
   const int rows = p.sys.row_end - p.sys.row_begin;
   if (rows == 0 || par->s9 == 0.0) return D3B200_OK;
-  if (want_grad) d3::system_atm_kernel<B, true><<<rows, 32 * d3::kAtmWarps, 0, (cudaStream_t)stream>>>(p);
-  else d3::system_atm_kernel<B, false><<<rows, 32 * d3::kAtmWarps, 0, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nelem > 0 && nelem <= d3::kAtmEmax && zlist && eidx && work) {
+    d3::AtmArgs2<B> q;
+    q.sys = p.sys;
+    q.nelem = nelem;
+    q.eidx = reinterpret_cast<const signed char*>(eidx);
+    B* tvec = work;
+    B* rve = work + (size_t)p.sys.natoms * nelem * 8;
+    q.tvec = tvec; q.rvdw_e = rve;
+    q.s9 = p.s9; q.rs9 = p.rs9; q.pexp = p.pexp;
+    q.cube_root_pow = par->alp == 14.0 ? 1 : 0;
+    const int nt = p.sys.natoms * nelem;
+    d3::system_tvec_kernel<B><<<(nt + 127) / 128, 128, 0, st>>>(p.sys.natoms, nelem, p.sys.z, zlist, p.sys.w, p.sys.refc6, tvec);
+    d3::system_rvdw_compact_kernel<B><<<1, 64, 0, st>>>(nelem, zlist, rvdw, rve);
+    const size_t smem = d3::atm2_smem_bytes<B>(nelem);
+    if (want_grad) {
+      auto kern = d3::system_atm2_kernel<B, true>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<rows, 32 * d3::kAtmWarps, smem, st>>>(q);
+    } else {
+      auto kern = d3::system_atm2_kernel<B, false>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<rows, 32 * d3::kAtmWarps, smem, st>>>(q);
+    }
+    return launched("system_atm2_kernel");
+  }
+  if (want_grad) d3::system_atm_kernel<B, true><<<rows, 32 * d3::kAtmWarps, 0, st>>>(p);
+  else d3::system_atm_kernel<B, false><<<rows, 32 * d3::kAtmWarps, 0, st>>>(p);
   return launched("system_atm_kernel");
 }
 
@@ -374,8 +401,14 @@ D3_STAGE_API(f64, double)
 D3_STAGE_API(f32, float)
 #undef D3_STAGE_API
 
-int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, const double* r, int g, void* st) { return sys_atm<double>(s, p, r, g, st); }
-int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int g, void* st) { return sys_atm<float>(s, p, r, g, st); }
+int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, const double* r, int ne,
+                          const int32_t* zl, const int8_t* ei, double* wk, int g, void* st) {
+  return sys_atm<double>(s, p, r, ne, zl, ei, wk, g, st);
+}
+int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int ne,
+                          const int32_t* zl, const int8_t* ei, float* wk, int g, void* st) {
+  return sys_atm<float>(s, p, r, ne, zl, ei, wk, g, st);
+}
 int d3b200_system_cn_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_cn<double>(s, p, st); }
 int d3b200_system_weights_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_weights<double>(s, p, st); }
 int d3b200_system_pair_f64(const d3b200_system_f64* s, const d3b200_params* p, int g, void* st) { return sys_pair<double>(s, p, g, st); }

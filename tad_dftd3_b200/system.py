@@ -15,6 +15,7 @@ make it the unit of work of the i-row sharded multi-GPU mode
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch import Tensor
@@ -89,6 +90,16 @@ class SystemPlan:
         hi = torch.where(empty, xyz[:, 0, :], hi)
         self.box = torch.cat([lo, hi], 1).contiguous()
         self.dtype, self.device = dt, dev
+        self._elements = None
+
+    def elements(self):
+        """(zlist int32 [E], eidx int8 [npad]) -- distinct elements and each atom's index (-1 = padding)."""
+        if self._elements is None:
+            zlist = torch.unique(self.z[self.z > 0])
+            lut = torch.full((128,), -1, dtype=torch.int8, device=self.device)
+            lut[zlist.long()] = torch.arange(zlist.numel(), dtype=torch.int8, device=self.device)
+            self._elements = (zlist.to(torch.int32).contiguous(), lut[self.z.long()].contiguous())
+        return self._elements
 
     def aux(self, g: Tensor | None) -> Tensor:
         """[npad, 2] = sqrt(r4r2), cotangent g (ones when None)."""
@@ -162,7 +173,14 @@ class SystemRunner:
             return
         if self.rvdw is None:
             raise ValueError("the ATM term needs the [104,104] rvdw table")
-        self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), int(want_grad))
+        zlist, eidx = self.plan.elements()
+        ne = int(zlist.numel())
+        if 0 < ne <= 8 and os.environ.get("TAD_DFTD3_B200_ATM_GENERAL") != "1":
+            self._atm_work = torch.empty(self.plan.npad * ne * 8 + 64, dtype=self.plan.dtype, device=self.plan.device)
+            self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), ne, C.c_void_p(zlist.data_ptr()),
+                       C.c_void_p(eidx.data_ptr()), C.c_void_p(self._atm_work.data_ptr()), int(want_grad))
+        else:
+            self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), 0, None, None, None, int(want_grad))
 
     # single-GPU drivers -----------------------------------------------------
     def run_energy(self) -> Tensor:
