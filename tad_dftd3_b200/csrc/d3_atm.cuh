@@ -314,7 +314,7 @@ __device__ __forceinline__ S pow16_3(S x) {
 }
 
 template <typename S, bool WANT_G>
-__global__ void __launch_bounds__(32 * kAtmWarps) system_atm2_kernel(AtmArgs2<S> P) {
+__global__ void __launch_bounds__(32 * kAtmWarps, 4) system_atm2_kernel(AtmArgs2<S> P) {
   const SysArgs<S>& A = P.sys;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int E = P.nelem;
