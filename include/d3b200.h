@@ -117,7 +117,7 @@ int d3b200_batch_energy_f32(int nbatch, int natoms, const int64_t* numbers,
                             const d3b200_params* par, float* energy, void* workspace,
                             size_t workspace_bytes, void* stream);
 
-/* Vector-Jacobian product of the above: with L = sum_i g[i] * E[i],
+/* Vector-Jacobian product of the above: with L = sum_i g[i] * E[i] (g == NULL: g = 1),
  *   grad  : dL/dpositions `[nbatch][natoms][3]`
  *   pgrad : dL/d(s6, s8, a1, a2, s9) per structure `[nbatch][5]`, or NULL.
  *   energy: optional `[nbatch][natoms]` (NULL to skip).

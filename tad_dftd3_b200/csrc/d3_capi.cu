@@ -158,7 +158,7 @@ int vjp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
   d3::MolArgs<B> a;
   int rc = fill_common<B, B>(a, nbatch, natoms, numbers, positions, model, par, nullptr);
   if (rc) return rc;
-  if (!g || !grad) return fail(D3B200_EINVAL, "null cotangent or gradient%s");
+  if (!grad) return fail(D3B200_EINVAL, "null gradient output%s");  // g == NULL: unit cotangent
   if (nbatch == 0 || natoms == 0) return D3B200_OK;
   a.g = g;
   a.energy = energy;

@@ -94,12 +94,21 @@ def _param_vector(param: dict, dtype) -> Tensor:
     vals = [param.get(k, d) for k, d in zip(keys, dflt)]
     live = [v for v in vals if isinstance(v, Tensor) and (v.requires_grad or _is_functorch(v))]
     if not live:
-        return torch.tensor([_scalar(v) for v in vals], dtype=dtype)
+        key = tuple(_scalar(v) for v in vals) + (dtype,)
+        t = _pvec_cache.get(key)
+        if t is None:
+            if len(_pvec_cache) > 64:
+                _pvec_cache.clear()
+            t = _pvec_cache[key] = torch.tensor(key[:5], dtype=dtype)
+        return t
     dev = live[0].device
     return torch.stack([
         (v.to(device=dev, dtype=dtype) if isinstance(v, Tensor) else torch.tensor(v, dtype=dtype, device=dev)).reshape(())
         for v in vals
     ])
+
+
+_pvec_cache: dict = {}
 
 
 def _atm_requested(param: dict) -> bool:
@@ -191,10 +200,7 @@ def dftd3(
         cn_cutoff=defaults.D3_CN_CUTOFF, kcn=defaults.D3_KCN,
         alp=_scalar(param.get("alp", defaults.ALP)),
     )
-    p = _param_vector(param, dtype)
-    if not atm:
-        # s9 present but zero (or absent): two-body only, and no gradient to s9
-        p = p * torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0], dtype=dtype, device=p.device)
+    p = _param_vector(param if atm else {k: v for k, v in param.items() if k != "s9"}, dtype)
     return d3_energy(numbers, positions, p, rcov_t, r4r2_t, rvdw_t, refcn, refc6, st)
 
 

@@ -76,10 +76,21 @@ def _pvals(p: Tensor):
     return p.detach().reshape(-1).tolist()
 
 
+def _as(t: Tensor, dtype, device) -> Tensor:
+    """detach + move + make contiguous, skipping every step that is a no-op
+    (each skipped torch call saves a few microseconds of host time per launch)."""
+    if t.requires_grad:
+        t = t.detach()
+    if t.dtype != dtype or t.device != device:
+        t = t.to(device=device, dtype=dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
 class _Call:
     """Flattened, contiguous device views of one call + the C structs."""
 
-    def __init__(self, numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st: Settings, order: int):
+    def __init__(self, numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st: Settings, order: int,
+                 pvals=None):
         if positions.device.type != "cuda":
             raise RuntimeError(
                 "tad_dftd3_b200 runs on CUDA devices only (there is no CPU path); "
@@ -87,25 +98,32 @@ class _Call:
             )
         self.lead = lead = positions.shape[:-2]
         self.n = n = positions.shape[-2]
-        self.dtype, self.device = positions.dtype, positions.device
-        self.x = positions.detach().reshape(-1, n, 3).contiguous()
-        z = numbers.detach().expand(*lead, n).reshape(-1, n)
-        self.z = (z if z.dtype == torch.int64 else z.to(torch.int64)).contiguous()
+        self.dtype, self.device = dt, dev = positions.dtype, positions.device
+        x = _as(positions, dt, dev)
+        self.x = x if x.dim() == 3 else x.reshape(-1, n, 3)
+        z = numbers
+        if z.shape != positions.shape[:-1]:
+            z = z.expand(*lead, n)
+        z = _as(z, torch.int64, dev)
+        self.z = z if z.dim() == 2 else z.reshape(-1, n)
         self.nflat = nflat = self.x.shape[0]
         self.st = st
-        dd = dict(device=self.device, dtype=self.dtype)
-        self.rcov = rcov.detach().to(**dd).contiguous() if st.rcov_per_element else \
-            rcov.detach().to(**dd).expand(*lead, n).reshape(nflat, n).contiguous()
-        self.r4r2 = r4r2.detach().to(**dd).contiguous() if st.r4r2_per_element else \
-            r4r2.detach().to(**dd).expand(*lead, n).reshape(nflat, n).contiguous()
+
+        def atomwise(t, trailing=()):
+            if t.shape != (*lead, n, *trailing):
+                t = t.expand(*lead, n, *trailing)
+            return _as(t, dt, dev).reshape(nflat, n, *trailing)
+
+        self.rcov = _as(rcov, dt, dev) if st.rcov_per_element else atomwise(rcov)
+        self.r4r2 = _as(r4r2, dt, dev) if st.r4r2_per_element else atomwise(r4r2)
         self.rvdw = None
         if st.rvdw_mode == 1:
-            self.rvdw = rvdw.detach().to(**dd).contiguous()
+            self.rvdw = _as(rvdw, dt, dev)
         elif st.rvdw_mode == 2:
-            self.rvdw = rvdw.detach().to(**dd).expand(*lead, n, n).reshape(nflat, n, n).contiguous()
-        self.refcn = refcn.detach().to(**dd).contiguous()
-        self.refc6 = refc6.detach().to(**dd).contiguous()
-        self.pvals = _pvals(p)
+            self.rvdw = atomwise(rvdw, (n,))
+        self.refcn = _as(refcn, dt, dev)
+        self.refc6 = _as(refc6, dt, dev)
+        self.pvals = _pvals(p) if pvals is None else pvals
         self.par = _params(self.pvals, st)
         m = _lib.Model()
         m.rcov, m.r4r2 = self.rcov.data_ptr(), self.r4r2.data_ptr()
@@ -114,14 +132,14 @@ class _Call:
         m.rvdw = self.rvdw.data_ptr() if self.rvdw is not None else None
         m.rvdw_mode = int(st.rvdw_mode)
         self.model = m
-        self.sfx = _sfx(self.dtype)
+        self.sfx = _sfx(dt)
         # ATM scratch (sqrt|C6| matrix per structure)
         self.work = None
         self.work_bytes = 0
         if self.par.s9 != 0.0 and nflat and n:
             fn = getattr(_lib.lib(), f"d3b200_batch_workspace_bytes_{self.sfx}")
             self.work_bytes = int(fn(nflat, n, order, 1))
-            self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=self.device)
+            self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=dev)
 
     def per_atom(self, t: Tensor, trailing=()):
         return t.detach().to(device=self.device, dtype=self.dtype).expand(*self.lead, self.n, *trailing) \
@@ -136,13 +154,19 @@ class _Call:
         return f(*shape, dtype=self.dtype, device=self.device)
 
 
+_limits: dict = {}
+
+
 def _tiled(c: "_Call", order: int) -> bool:
     """Structures beyond the one-CTA limit go to the tiled `d3b200_system_*` sweeps."""
     if not (c.nflat and c.n):
         return False
     if os.environ.get("TAD_DFTD3_B200_TILED") == "1":
         return True
-    limit = getattr(_lib.lib(), f"d3b200_batch_max_atoms_{c.sfx}")(order)
+    key = (c.sfx, order)
+    limit = _limits.get(key)
+    if limit is None:
+        limit = _limits[key] = getattr(_lib.lib(), f"d3b200_batch_max_atoms_{c.sfx}")(order)
     return c.n > limit
 
 
@@ -288,6 +312,9 @@ _V_NAMES = ("numbers", "positions", "p", "g", "rcov", "r4r2", "rvdw", "refcn", "
 _H_NAMES = ("numbers", "positions", "p", "g", "vx", "vp", "rcov", "r4r2", "rvdw", "refcn", "refc6", "st")
 
 
+_SPECULATE = os.environ.get("TAD_DFTD3_B200_SPECULATE", "1") == "1"
+
+
 def _is_functorch(x) -> bool:
     f = torch._C._functorch
     return isinstance(x, Tensor) and bool(f.is_batchedtensor(x) or f.is_gradtrackingtensor(x))
@@ -308,18 +335,18 @@ class D3Energy(torch.autograd.Function):
 
     @staticmethod
     def forward(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st):
-        speculate = (positions.requires_grad and not p.requires_grad and not _is_functorch(positions)
-                     and float(p.reshape(-1)[4]) == 0.0 and os.environ.get("TAD_DFTD3_B200_SPECULATE", "1") == "1")
-        if speculate:
-            c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0)
-            if c.nflat and c.n and not _tiled(c, 0):
-                energy, grad = c.new(c.nflat, c.n), c.new(c.nflat, c.n, 3)
-                ones = torch.ones(c.nflat, c.n, dtype=c.dtype, device=c.device)
-                fn = getattr(_lib.lib(), f"d3b200_batch_vjp_{c.sfx}")
-                with torch.cuda.device(c.device):
-                    _lib.check(fn(c.nflat, c.n, _ptr(c.z), _ptr(c.x), C.byref(c.model), C.byref(c.par),
-                                  _ptr(ones), _ptr(energy), _ptr(grad), None, None, C.c_size_t(0), c.stream()))
-                return energy.reshape(*c.lead, c.n), grad.reshape(*c.lead, c.n, 3)
+        if (positions.requires_grad and not p.requires_grad and _SPECULATE
+                and not _is_functorch(positions)):
+            pvals = _pvals(p)
+            if pvals[4] == 0.0:
+                c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0, pvals)
+                if c.nflat and c.n and not _tiled(c, 0):
+                    energy, grad = c.new(c.nflat, c.n), c.new(c.nflat, c.n, 3)
+                    fn = getattr(_lib.lib(), f"d3b200_batch_vjp_{c.sfx}")
+                    with torch.cuda.device(c.device):
+                        _lib.check(fn(c.nflat, c.n, _ptr(c.z), _ptr(c.x), C.byref(c.model), C.byref(c.par),
+                                      None, _ptr(energy), _ptr(grad), None, None, C.c_size_t(0), c.stream()))
+                    return energy.reshape(*c.lead, c.n), grad.reshape(*c.lead, c.n, 3)
         e = _run_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st)
         return e, e.new_empty(0)
 
