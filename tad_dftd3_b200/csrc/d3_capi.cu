@@ -3,6 +3,7 @@
 // arithmetic lives in the kernel headers.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/d3b200.h"

@@ -81,3 +81,68 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.D3LibraryError, match="no CPU"):
         _lib.lib()
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/d3b200.h must be consumable from C (the drop-in boundary is a C ABI)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "d3b200.h"\nint main(void) { d3b200_params p; (void)p; return D3B200_OK; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
+def test_stage_wrappers_validate_like_the_reference():
+    """Shape errors of the stage functions (reference disp.py:212-219, tad-mctc cn_d3) before any launch."""
+    import tad_dftd3_b200 as d3
+
+    numbers = torch.tensor([1, 1, 8])
+    positions = torch.zeros(3, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        d3.ncoord.cn_d3(numbers, positions)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        d3.disp.dispersion(numbers, positions, {}, torch.zeros(3, 3), r4r2=torch.ones(3))
+
+
+def test_reference_object_contract():
+    """Mirror of the reference's Reference holder checks (reference.py:231-245, test_reference.py)."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import REFCN
+
+    cn, c6 = REFCN(torch.double), syn.synthetic_c6_table(torch.double)
+    ref = d3.Reference(cn=cn, c6=c6)
+    assert ref.dtype == torch.double and ref.device == cn.device
+    assert "n_element=104" in str(ref) and "n_reference=7" in repr(ref)
+    assert ref.type(torch.double) is ref and ref.type(torch.float32).dtype == torch.float32
+    with pytest.raises(RuntimeError, match="dtype"):
+        d3.Reference(cn=cn.float(), c6=c6)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        d3.Reference(cn=cn[:50], c6=c6)
+    with pytest.raises(AttributeError):
+        ref.device = "cpu"
+
+
+def test_data_tables():
+    """R4R2 formula (data/r4r2.py:80-85), radii validated against the pinned CN elements, refcn layout."""
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN, VDW_PAIRWISE, set_vdw_pairwise
+
+    q = R4R2(torch.double)
+    assert q.shape == (119,) and q[0] == 0 and abs(float(q[1]) - (0.5 * 8.0589 * 1.0) ** 0.5) < 1e-12
+    rc = COV_D3(torch.double)
+    assert abs(float(rc[1]) - 4.0 / 3.0 * 0.32 / 0.529177210903) < 1e-12
+    refcn = REFCN(torch.double)
+    assert refcn.shape == (104, 7) and (refcn[0] == -1).all() and float(refcn[1, 0]) == 0.9118
+    with pytest.raises(FileNotFoundError):
+        VDW_PAIRWISE(torch.double)
+    set_vdw_pairwise(torch.ones(104, 104))
+    try:
+        assert VDW_PAIRWISE(torch.double).shape == (104, 104)
+    finally:
+        set_vdw_pairwise(None)
