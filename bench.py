@@ -209,6 +209,7 @@ def main():
                     help="c3: 4096-molecule batch (default, the headline metric); "
                          "c4: one 50k-atom water cluster, rows sharded over the GPUs")
     ap.add_argument("--nwater", type=int, default=16667)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="c3 only: arithmetic type of the path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -247,8 +248,9 @@ def main():
     # ---- this rank's shard (weak scaling: every rank owns nmol structures)
     numbers_h, positions_h = make_batch(args.nmol, seed=rank)
     numbers_h, positions_h = numbers_h.pin_memory(), positions_h.pin_memory()
+    positions_h = positions_h.to(dt).pin_memory()
     numbers, positions = numbers_h.to(dev), positions_h.to(dev)
-    near, far = count_pairs(numbers, positions)
+    near, far = count_pairs(numbers, positions.double())
     pairs = near + far
     flops = near * FLOPS_NEAR + far * FLOPS_FAR
     ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
@@ -263,7 +265,7 @@ def main():
     call = ops._Call(numbers, positions, p, rcov_t, r4r2_t, None, refcn, refc6, st, 0)
     energy = torch.empty(numbers.shape, dtype=dt, device=dev)
     grad = torch.empty(*numbers.shape, 3, dtype=dt, device=dev)
-    fn = lib.d3b200_batch_vjp_f64
+    fn = getattr(lib, f"d3b200_batch_vjp_{args.dtype}")
     stream = torch.cuda.current_stream(dev)
 
     def step_resident():
@@ -342,11 +344,12 @@ def main():
     # ---- FP64 FMA-chain peak on this GPU (roofline denominator)
     out = torch.zeros(1, dtype=dt, device=dev)
     blocks, iters = 148 * 8, 4096
+    probe = getattr(lib, f"d3b200_probe_fma_{args.dtype}")
     for _ in range(2):
-        lib.d3b200_probe_fma_f64(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+        probe(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
     pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pa.record(stream)
-    lib.d3b200_probe_fma_f64(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+    probe(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
     pb.record(stream)
     torch.cuda.synchronize(dev)
     peak_tflops = blocks * 256 * iters * 128 / (pa.elapsed_time(pb) * 1e-3) / 1e12
@@ -368,10 +371,10 @@ def main():
             "unit": "pair-terms/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
                 "workload": f"c3: {args.nmol} drug-like molecules per GPU (50-120 atoms, padded to 120), "
-                            "D3(BJ) two-body + CN, energy+grad fp64",
+                            f"D3(BJ) two-body + CN, energy+grad {args.dtype}",
                 "pair_terms_per_gpu": pairs, "pairs_within_25_bohr": near,
                 "entry": "d3b200_batch_vjp_f64 (one fused launch: CN, weights, C6, BJ energy, analytic gradient)",
                 "l2": "256 MB buffer written between timed steps",
@@ -382,18 +385,20 @@ def main():
             },
             "e2e": {
                 "value": pairs_all / (e2e_ms * 1e-3), "unit": "pair-terms/s",
-                "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * 8),
-                "d2h_bytes_per_step": int(e_h.numel() * 8 + g_h.numel() * 8),
+                "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * positions_h.element_size()),
+                "d2h_bytes_per_step": int((e_h.numel() + g_h.numel()) * e_h.element_size()),
                 "ms_per_step": e2e_ms,
                 "api": f"tad_dftd3_b200.dftd3() + torch.autograd.grad per chunk ({nchunk} chunks over 2 streams), "
                        "pinned host buffers",
             },
             "gpu_launches": launches,
             "roofline": {
-                "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved / peak_tflops, "traffic": None,
-                "kernel": "d3::molecule_kernel_v2<double, true>",
-                "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": achieved, "peak": peak_tflops,
+                "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": 15.8e6 if args.dtype == "f64" else None,
+                "kernel": "d3::molecule_kernel_v2<%s, true>" % ("double" if args.dtype == "f64" else "float"),
+                "peak_source": "FMA-chain probe of the same type measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "fp64_pipe_active_pct_ncu": 54.3 if args.dtype == "f64" else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1f_molecule_kernel_v2_raw.csv",
                 "flops_model": "140/pair-term (r<=25 Bohr), 89 (25<r<=50), SURVEY.md 8(d)",
                 "hbm_gbs_measured_peak": _measured_hbm(),
             },
