@@ -173,6 +173,10 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
  *             (want_grad = 0: energy only)        model/c6.py + disp.py:276-302
  *   _cnbwd    grad[i][3] += CN chain-rule term    (autograd through cn_d3)
  * g (in aux) is the cotangent of the per-atom energies, L = sum g_i E_i.
+ *   _tvec     (optional, after _weights; needs nelem/zlist/eidx/tvec) pre-contracts
+ *             T_k[e][a] = sum_b K[Z_e,Z_k,a,b] w_kb for every atom; `_pair` and `_atm`
+ *             then need one 7-wide dot per C6 instead of a 7x7 contraction per
+ *             (row, partner element).
  * jsplit >= 1 CTAs share each 128-row tile (the j-tiles are dealt round-robin
  * among them, which is what fills the GPU when N / 128 is small compared with
  * the SM count); their partial rows go through `scratch`
@@ -193,6 +197,10 @@ typedef struct d3b200_system_f64 {
   double* grad;
   int jsplit;
   double* scratch;
+  int nelem;            /* optional fast path, 0 = off: number of distinct elements (<= 8) */
+  const int32_t* zlist; /* [nelem] the distinct atomic numbers                              */
+  const int8_t* eidx;   /* [natoms] index of each atom's element in zlist, -1 = padding     */
+  double* tvec;            /* [natoms*nelem*8 + 64] scratch filled by _system_tvec_            */
 } d3b200_system_f64;
 
 typedef struct d3b200_system_f32 {
@@ -211,14 +219,20 @@ typedef struct d3b200_system_f32 {
   float* grad;
   int jsplit;
   float* scratch;
+  int nelem;            /* optional fast path, 0 = off: number of distinct elements (<= 8) */
+  const int32_t* zlist; /* [nelem] the distinct atomic numbers                              */
+  const int8_t* eidx;   /* [natoms] index of each atom's element in zlist, -1 = padding     */
+  float* tvec;            /* [natoms*nelem*8 + 64] scratch filled by _system_tvec_            */
 } d3b200_system_f32;
 
 int d3b200_system_cn_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
 int d3b200_system_weights_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
+int d3b200_system_tvec_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
 int d3b200_system_pair_f64(const d3b200_system_f64* sys, const d3b200_params* par, int want_grad, void* stream);
 int d3b200_system_cnbwd_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
 int d3b200_system_cn_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
 int d3b200_system_weights_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
+int d3b200_system_tvec_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
 int d3b200_system_pair_f32(const d3b200_system_f32* sys, const d3b200_params* par, int want_grad, void* stream);
 int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
 
@@ -226,17 +240,12 @@ int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* p
  * cutoff rule kept).  Run after `_pair` and before `_cnbwd`: ADDS (fp64 atomics,
  * once per short edge) the three-body parts to energy[], grad[] and decn[] for
  * the triples whose owner edge (i, j), i < j, has i in row_begin..row_end-1
- * (any row range).  rvdw: `[104][104]` element-pair table.
- * Optional fast path for structures with nelem <= 8 distinct elements
- * (nelem = 0 selects the general kernel): zlist[nelem] = the distinct atomic
- * numbers, eidx[natoms] = index of each atom's element in zlist (-1 = padding),
- * work = scratch of (natoms * nelem * 8 + 64) reals. */
+ * (any row range).  rvdw: `[104][104]` element-pair table.  Uses the T vectors
+ * when the system struct carries them (after `_system_tvec_`). */
 int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par,
-                          const double* rvdw, int nelem, const int32_t* zlist,
-                          const int8_t* eidx, double* work, int want_grad, void* stream);
+                          const double* rvdw, int want_grad, void* stream);
 int d3b200_system_atm_f32(const d3b200_system_f32* sys, const d3b200_params* par,
-                          const float* rvdw, int nelem, const int32_t* zlist,
-                          const int8_t* eidx, float* work, int want_grad, void* stream);
+                          const float* rvdw, int want_grad, void* stream);
 
 /* ------------------------------------------------------------------------
  * Stage-level entry points (forward only): the reference's operator API keeps

@@ -43,7 +43,8 @@ class System(C.Structure):
     _fields_ = [("natoms", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int)] + [
         (k, C.c_void_p) for k in
         ("atoms", "aux", "z", "box", "refcn", "refc6", "cn", "w", "dw", "decn", "energy", "grad")] + [
-        ("jsplit", C.c_int), ("scratch", C.c_void_p)]
+        ("jsplit", C.c_int), ("scratch", C.c_void_p),
+        ("nelem", C.c_int), ("zlist", C.c_void_p), ("eidx", C.c_void_p), ("tvec", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -73,8 +74,8 @@ for _sfx in ("f64", "f32"):
     _SIGNATURES[f"d3b200_stage_c6_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_disp2_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, C.POINTER(Params), _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_atm_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, C.POINTER(Params), _P, _P], C.c_int)
-    _SIGNATURES[f"d3b200_system_atm_{_sfx}"] = (
-        [C.POINTER(System), C.POINTER(Params), _P, _I, _P, _P, _P, _I, _P], C.c_int)
+    _SIGNATURES[f"d3b200_system_atm_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _P, _I, _P], C.c_int)
+    _SIGNATURES[f"d3b200_system_tvec_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _P], C.c_int)
 
 _lib = None
 

@@ -270,8 +270,8 @@ constexpr int kAtmList = 1024;           // partners gathered per round (32 sub-
 template <typename S>
 struct AtmArgs2 {
   SysArgs<S> sys;
-  const S* tvec;            // [natoms][nelem][8]  (7 used)
-  const signed char* eidx;  // [natoms] compact element index (-1 = padding)
+  const S* tvec;            // = sys.tvec  [natoms][nelem][8]  (7 used)
+  const signed char* eidx;  // = sys.eidx  compact element index (-1 = padding)
   const S* rvdw_e;          // [nelem][nelem] compact element-pair radii
   int nelem;
   S s9, rs9, pexp;

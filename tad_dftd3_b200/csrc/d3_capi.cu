@@ -230,6 +230,10 @@ int sys_fill(d3::SysArgs<B>& a, const typename SysOf<B>::type* s, const d3b200_p
   a.refcn = s->refcn; a.refc6 = s->refc6;
   a.cn = s->cn; a.decn = s->decn; a.energy = s->energy; a.grad = s->grad;
   a.jsplit = s->jsplit; a.part = s->scratch;
+  a.nelem = 0; a.zlist = nullptr; a.eidx = nullptr; a.tvec = nullptr;
+  if (s->nelem > 0 && s->nelem <= d3::kSysEmax && s->zlist && s->eidx && s->tvec) {
+    a.nelem = s->nelem; a.zlist = s->zlist; a.eidx = reinterpret_cast<const signed char*>(s->eidx); a.tvec = s->tvec;
+  }
   if (s->jsplit < 1 || !s->scratch) return fail(D3B200_EINVAL, "system scratch / jsplit missing%s");
   a.s6 = (B)par->s6; a.s8 = (B)par->s8; a.a1 = (B)par->a1; a.a2 = (B)par->a2;
   B cut = (B)par->cutoff, cncut = (B)par->cn_cutoff;
@@ -267,6 +271,17 @@ int sys_weights(const typename SysOf<B>::type* s, const d3b200_params* par, void
 }
 
 template <typename B>
+int sys_tvec(const typename SysOf<B>::type* s, const d3b200_params* par, void* stream) {
+  d3::SysArgs<B> a;
+  int rc = sys_fill<B>(a, s, par);
+  if (rc) return rc;
+  if (!a.nelem || !s->w || !s->refc6) return fail(D3B200_EINVAL, "tvec needs nelem/zlist/eidx/tvec, w and refc6%s");
+  const int nt = a.natoms * a.nelem;
+  d3::system_tvec_kernel<B><<<(nt + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.natoms, a.nelem, a.z, a.zlist, a.w, a.refc6, a.tvec);
+  return launched("system_tvec_kernel");
+}
+
+template <typename B>
 int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int want_grad, void* stream) {
   d3::SysArgs<B> a;
   int rc = sys_fill<B>(a, s, par);
@@ -276,7 +291,18 @@ int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int wan
   const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
   if (nblk == 0) return D3B200_OK;
   if (!want_grad) a.grad = nullptr;
-  if (want_grad) d3::system_pair_kernel<B, true><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
+  if (a.nelem) {
+    const size_t smem = d3::pair_t_smem_bytes<B>(a.nelem);
+    if (want_grad) {
+      auto kern = d3::system_pair_t_kernel<B, true>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<dim3(nblk, a.jsplit), d3::kSysTile, smem, (cudaStream_t)stream>>>(a);
+    } else {
+      auto kern = d3::system_pair_t_kernel<B, false>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<dim3(nblk, a.jsplit), d3::kSysTile, smem, (cudaStream_t)stream>>>(a);
+    }
+  } else if (want_grad) d3::system_pair_kernel<B, true><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
   else d3::system_pair_kernel<B, false><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
   if ((rc = launched("system_pair_kernel"))) return rc;
   d3::system_reduce_kernel<B, 1><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
@@ -298,8 +324,7 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
 }
 
 template <typename B>
-int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int nelem,
-            const int32_t* zlist, const int8_t* eidx, B* work, int want_grad, void* stream) {
+int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int want_grad, void* stream) {
   d3::AtmArgs<B> p;
   int rc = sys_fill<B>(p.sys, s, par);
   if (rc) return rc;
@@ -310,20 +335,18 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
   const int rows = p.sys.row_end - p.sys.row_begin;
   if (rows == 0 || par->s9 == 0.0) return D3B200_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (nelem > 0 && nelem <= d3::kAtmEmax && zlist && eidx && work) {
+  if (p.sys.nelem) {
     d3::AtmArgs2<B> q;
     q.sys = p.sys;
-    q.nelem = nelem;
-    q.eidx = reinterpret_cast<const signed char*>(eidx);
-    B* tvec = work;
-    B* rve = work + (size_t)p.sys.natoms * nelem * 8;
-    q.tvec = tvec; q.rvdw_e = rve;
+    q.nelem = p.sys.nelem;
+    q.eidx = p.sys.eidx;
+    q.tvec = p.sys.tvec;
+    B* rve = p.sys.tvec + (size_t)p.sys.natoms * q.nelem * 8;   // 64 spare reals behind the T vectors
+    q.rvdw_e = rve;
     q.s9 = p.s9; q.rs9 = p.rs9; q.pexp = p.pexp;
     q.cube_root_pow = par->alp == 14.0 ? 1 : 0;
-    const int nt = p.sys.natoms * nelem;
-    d3::system_tvec_kernel<B><<<(nt + 127) / 128, 128, 0, st>>>(p.sys.natoms, nelem, p.sys.z, zlist, p.sys.w, p.sys.refc6, tvec);
-    d3::system_rvdw_compact_kernel<B><<<1, 64, 0, st>>>(nelem, zlist, rvdw, rve);
-    const size_t smem = d3::atm2_smem_bytes<B>(nelem);
+    d3::system_rvdw_compact_kernel<B><<<1, 64, 0, st>>>(q.nelem, p.sys.zlist, rvdw, rve);
+    const size_t smem = d3::atm2_smem_bytes<B>(q.nelem);
     if (want_grad) {
       auto kern = d3::system_atm2_kernel<B, true>;
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -402,14 +425,10 @@ D3_STAGE_API(f64, double)
 D3_STAGE_API(f32, float)
 #undef D3_STAGE_API
 
-int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, const double* r, int ne,
-                          const int32_t* zl, const int8_t* ei, double* wk, int g, void* st) {
-  return sys_atm<double>(s, p, r, ne, zl, ei, wk, g, st);
-}
-int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int ne,
-                          const int32_t* zl, const int8_t* ei, float* wk, int g, void* st) {
-  return sys_atm<float>(s, p, r, ne, zl, ei, wk, g, st);
-}
+int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, const double* r, int g, void* st) { return sys_atm<double>(s, p, r, g, st); }
+int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int g, void* st) { return sys_atm<float>(s, p, r, g, st); }
+int d3b200_system_tvec_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_tvec<double>(s, p, st); }
+int d3b200_system_tvec_f32(const d3b200_system_f32* s, const d3b200_params* p, void* st) { return sys_tvec<float>(s, p, st); }
 int d3b200_system_cn_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_cn<double>(s, p, st); }
 int d3b200_system_weights_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_weights<double>(s, p, st); }
 int d3b200_system_pair_f64(const d3b200_system_f64* s, const d3b200_params* p, int g, void* st) { return sys_pair<double>(s, p, g, st); }

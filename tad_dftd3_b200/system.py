@@ -46,25 +46,56 @@ def morton_order(pos: Tensor) -> Tensor:
     return torch.argsort(code, stable=True)
 
 
+_order_cache: dict = {}   # id(numbers) -> [weakref, version, idx, order, age]
+ORDER_MAX_AGE = 20        # calls after which the Morton / element order is rebuilt
+
+
+def _cached_order(numbers: Tensor, positions: Tensor):
+    """(idx, order) for `numbers`: indices of the real atoms and their sorted order.
+    The order only steers efficiency (the bounding boxes are recomputed from the
+    current positions on every call), so it is reused for a few calls while the
+    same `numbers` tensor keeps coming back (MD / optimisation loops)."""
+    import weakref
+
+    key = id(numbers)
+    hit = _order_cache.get(key)
+    if hit is not None and hit[0]() is numbers and hit[1] == numbers._version and hit[4] < ORDER_MAX_AGE \
+            and hit[2].device == positions.device:
+        hit[4] += 1
+        return hit[2], hit[3]
+    dev = positions.device
+    idx = torch.nonzero(numbers != 0).reshape(-1)
+    n = int(idx.numel())
+    if n:
+        pos = positions.detach()[idx]
+        z = numbers[idx]
+        o1 = morton_order(pos)
+        tile = torch.arange(n, device=dev) // TILE
+        o2 = torch.argsort(tile * 128 + z[o1], stable=True)
+        order = o1[o2]
+    else:
+        order = idx
+    if len(_order_cache) > 64:
+        _order_cache.clear()
+    try:
+        _order_cache[key] = [weakref.ref(numbers), numbers._version, idx, order, 0]
+    except TypeError:  # pragma: no cover
+        pass
+    return idx, order
+
+
 class SystemPlan:
     """Sorted / padded / packed view of one structure."""
 
     def __init__(self, numbers: Tensor, positions: Tensor, rcov: Tensor, r4r2: Tensor, kcn: float):
         dev, dt = positions.device, positions.dtype
         self.natoms_in = numbers.shape[0]
-        idx = torch.nonzero(numbers != 0).reshape(-1)
+        idx, order = _cached_order(numbers, positions)
         n = int(idx.numel())
         self.n = n
         self.npad = npad = max(TILE, -(-n // TILE) * TILE)
         pos = positions.detach()[idx]
         z = numbers[idx]
-        if n:
-            o1 = morton_order(pos)
-            tile = torch.arange(n, device=dev) // TILE
-            o2 = torch.argsort(tile * 128 + z[o1], stable=True)
-            order = o1[o2]
-        else:
-            order = idx
         self.perm = idx[order]                      # sorted slot -> original atom index
         ps = pos[order]
         zs = z[order]
@@ -145,6 +176,17 @@ class SystemRunner:
         self.jsplit = int(max(1, min(ntiles, -(-self.TARGET_CTAS // rows_tiles))))
         self.scratch = torch.empty(5 * self.jsplit * npad, dtype=dt, device=dev)
         s.jsplit, s.scratch = self.jsplit, self.scratch.data_ptr()
+        # pre-contracted reference vectors (structures with <= 8 distinct elements)
+        s.nelem = 0
+        self.use_tvec = False
+        if os.environ.get("TAD_DFTD3_B200_NO_TVEC") != "1":
+            zlist, eidx = plan.elements()
+            ne = int(zlist.numel())
+            if 0 < ne <= 8:
+                self._zlist, self._eidx = zlist, eidx
+                self.tvec = torch.empty(npad * ne * 8 + 64, dtype=dt, device=dev)
+                s.nelem, s.zlist, s.eidx, s.tvec = ne, zlist.data_ptr(), eidx.data_ptr(), self.tvec.data_ptr()
+                self.use_tvec = True
         self.sys = s
 
     def _call(self, name, rows, *extra):
@@ -160,6 +202,8 @@ class SystemRunner:
 
     def weights(self):
         self._call("weights", None)
+        if self.use_tvec:
+            self._call("tvec", None)
 
     def sweep_pair(self, want_grad: bool, rows=None):
         self._call("pair", rows, int(want_grad))
@@ -173,14 +217,7 @@ class SystemRunner:
             return
         if self.rvdw is None:
             raise ValueError("the ATM term needs the [104,104] rvdw table")
-        zlist, eidx = self.plan.elements()
-        ne = int(zlist.numel())
-        if 0 < ne <= 8 and os.environ.get("TAD_DFTD3_B200_ATM_GENERAL") != "1":
-            self._atm_work = torch.empty(self.plan.npad * ne * 8 + 64, dtype=self.plan.dtype, device=self.plan.device)
-            self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), ne, C.c_void_p(zlist.data_ptr()),
-                       C.c_void_p(eidx.data_ptr()), C.c_void_p(self._atm_work.data_ptr()), int(want_grad))
-        else:
-            self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), 0, None, None, None, int(want_grad))
+        self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), int(want_grad))
 
     # single-GPU drivers -----------------------------------------------------
     def run_energy(self) -> Tensor:

@@ -24,7 +24,7 @@ print("v1 750", run(n2,x2,par))
 os.environ["TAD_DFTD3_B200_TILED"]="1"
 print("tiled 390", run(n1,x1,par, cutoff=torch.tensor(15.0)))
 print("tiled atm 390", run(n1,x1,paratm, cutoff=torch.tensor(12.0)))
-os.environ["TAD_DFTD3_B200_ATM_GENERAL"]="1"
+os.environ["TAD_DFTD3_B200_NO_TVEC"]="1"
 print("tiled atm general 390", run(n1,x1,paratm, cutoff=torch.tensor(12.0)))
 os.environ["TAD_DFTD3_B200_TILED"]="0"
 h=torch.func.jacrev(torch.func.jacrev(lambda p: d3.dftd3(n[0].to(dev), p, par, ref=ref).sum()))(x[0].to(dev))
