@@ -99,7 +99,9 @@ def _param_vector(param: dict, dtype) -> Tensor:
         if t is None:
             if len(_pvec_cache) > 64:
                 _pvec_cache.clear()
-            t = _pvec_cache[key] = torch.tensor(key[:5], dtype=dtype)
+            # (created inside jacrev/vmap the tensor is wrapped at the live levels;
+            # only the plain tensor may outlive the transform)
+            t = _pvec_cache[key] = _plain(torch.tensor(key[:5], dtype=dtype))
         return t
     dev = live[0].device
     return torch.stack([

@@ -364,3 +364,26 @@ def test_stage_functions_are_forward_only():
         d3.ncoord.cn_d3(numbers, pos)
     with torch.no_grad():
         assert d3.ncoord.cn_d3(numbers, pos).shape == (3,)
+
+
+def test_repeated_transforms_do_not_leak_wrappers(runs):
+    """Module-level caches must never keep functorch wrappers alive across calls
+    (same Hessian twice, then a plain call, then a Hessian with other parameters)."""
+    import tad_dftd3_b200 as d3
+
+    c = runs.case("pbh4_hess_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    refcn, refc6, *_ = tables(dtype, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    numbers, positions = numbers.to(DEV), positions.to(DEV)
+
+    def hess(par):
+        return torch.func.jacrev(torch.func.jacrev(lambda p: d3.dftd3(numbers, p, par, ref=ref).sum()))(positions)
+
+    par = {k: v.to(DEV) for k, v in param.items()}
+    h1 = hess(par)
+    h2 = hess(par)
+    e = d3.dftd3(numbers, positions, par, ref=ref)
+    h3 = hess(dict(par, s8=torch.tensor(1.1, dtype=dtype, device=DEV)))
+    assert torch.equal(h1, h2) and torch.isfinite(e).all() and not torch.equal(h1, h3)
+    assert_close(h1.cpu(), c["hessian"], 1e-9, 1e-12, "hessian")
