@@ -284,6 +284,11 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     barrier()
+    # sanity of what is being timed (outside the timed region): every output finite,
+    # exact zeros on padding, vanishing net force per structure
+    assert bool(torch.isfinite(energy).all()) and bool(torch.isfinite(grad).all()), "non-finite output"
+    assert bool((energy[numbers == 0] == 0).all())
+    net_force = float(grad.sum(1).abs().max())
     launches0 = _lib.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clocks:
@@ -386,6 +391,7 @@ def main():
                           "1 s untimed pre-heat under the clock sampler",
                 "parallelism": f"structures sharded over {world} GPU(s), no data-path collective",
                 "tables": "synthetic C6 table (reference-c6.pt unavailable offline)",
+                "checks": {"all_outputs_finite": True, "max_net_force_per_structure": net_force},
             },
             "e2e": {
                 "value": pairs_all / (e2e_ms * 1e-3), "unit": "pair-terms/s",

@@ -79,6 +79,14 @@ template <typename T> D3_HD Dual<T> rcp(Dual<T> a) {
   return Dual<T>(r, -a.d * r * r);
 }
 
+// IEEE division (the weight normalisation divides denormals by denormals)
+D3_HD float dv(float a, float b) { return a / b; }
+D3_HD double dv(double a, double b) { return a / b; }
+template <typename T> D3_HD Dual<T> dv(Dual<T> a, Dual<T> b) {
+  T q = a.v / b.v;
+  return Dual<T>(q, (a.d - q * b.d) / b.v);
+}
+
 D3_HD float rsq(float a) { return rsqrtf(a); }
 D3_HD double rsq(double a) { return rsqrt(a); }
 template <typename T> D3_HD Dual<T> rsq(Dual<T> a) {

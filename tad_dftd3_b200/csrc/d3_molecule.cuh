@@ -117,12 +117,13 @@ __device__ __forceinline__ void reference_weights(
     }
     return;
   }
-  W inv = rcp(norm);
+  // true division: when CN is far from every reference CN the Gaussians and
+  // their sum are denormal (1e-310); 1/norm would overflow where g/norm is exact
   W wa[kNRef];
   W mean = W(0.0);
 #pragma unroll
   for (int a = 0; a < kNRef; ++a) {
-    wa[a] = gw[a] * inv;
+    wa[a] = dv(gw[a], norm);
     mean += wa[a] * dc[a];
   }
 #pragma unroll

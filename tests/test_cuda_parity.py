@@ -387,3 +387,28 @@ def test_repeated_transforms_do_not_leak_wrappers(runs):
     h3 = hess(dict(par, s8=torch.tensor(1.1, dtype=dtype, device=DEV)))
     assert torch.equal(h1, h2) and torch.isfinite(e).all() and not torch.equal(h1, h3)
     assert_close(h1.cpu(), c["hessian"], 1e-9, 1e-12, "hessian")
+
+
+def test_denormal_weight_norm_regression():
+    """Structure 62 of the config-3 batch has a Cl with CN = 14.3: its Gaussian weights
+    and their sum are denormal (1e-310), not zero.  1/norm overflows; the reference
+    divides.  (Found by the full-size finiteness check.)"""
+    from tad_dftd3_b200 import synthetic as syn
+
+    numbers, positions = syn.drug_like_batch(4096, 50, 120, seed=0)
+    b = 62
+    n = int((numbers[b] != 0).sum())
+    numbers, positions = numbers[b, :n], positions[b, :n]
+    dtype = torch.double
+    param = {k: torch.tensor(v, dtype=dtype) for k, v in
+             (("s6", 1.0), ("s8", 0.78981345), ("a1", 0.49484001), ("a2", 5.73083694), ("s9", 1.0))}
+    g = torch.linspace(0.5, 1.5, n, dtype=dtype)
+    out = run_cuda(numbers, positions, param, 50.0, dtype, g=g, pgrad=True)
+    pos = positions.clone().requires_grad_(True)
+    par = {k: v.clone().requires_grad_(k in ("s6", "s8", "a1", "a2")) for k, v in param.items()}
+    e = oracle_energy(numbers, pos, par, 50.0, dtype)
+    grads = torch.autograd.grad((e * g).sum(), [pos] + [par[k] for k in ("s6", "s8", "a1", "a2")])
+    assert np.isfinite(out["energy"]).all() and np.isfinite(out["grad"]).all()
+    assert_close(out["energy"], e.detach(), RTOL, ATOL, "energy")
+    assert_close(out["grad"], grads[0], RTOL, ATOL, "grad")
+    assert_close(out["pgrad"], [float(x) for x in grads[1:]], RTOL, ATOL, "pgrad")
