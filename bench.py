@@ -158,7 +158,7 @@ def reference_step_fn(nmol_sample, seed=0):
         pos = positions.clone().requires_grad_(True)
         e = energy(pos)
         (g,) = torch.autograd.grad(e.sum(), pos)
-        return float(e.sum()), g
+        return float(e.detach().sum()), g
 
     desc = (f"{nmol_sample} molecules of the c3 batch (seed {seed}), energy + autograd gradient, "
             f"torch {torch.__version__} CPU fp64")
