@@ -68,21 +68,21 @@ def run_sharded(runner, want_grad: bool, group=None):
 
 class _ShardedD3(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, numbers, positions, rcov, r4r2, refcn, refc6, par, group):
-        plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn)
+    def forward(ctx, numbers, positions, rcov, r4r2, refcn, refc6, par, group, tables=(False, False)):
+        plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn, *tables)
         runner = SystemRunner(plan, refcn, refc6, par, None, _world(group)[1])
         run_sharded(runner, False, group)
         ctx.save_for_backward(numbers, positions, rcov, r4r2, refcn, refc6)
-        ctx.par, ctx.group = par, group
+        ctx.par, ctx.group, ctx.tables = par, group, tables
         return plan.scatter(runner.energy)
 
     @staticmethod
     def backward(ctx, gE):
         numbers, positions, rcov, r4r2, refcn, refc6 = ctx.saved_tensors
-        plan = SystemPlan(numbers, positions, rcov, r4r2, ctx.par.kcn)
+        plan = SystemPlan(numbers, positions, rcov, r4r2, ctx.par.kcn, *ctx.tables)
         runner = SystemRunner(plan, refcn, refc6, ctx.par, gE, _world(ctx.group)[1])
         run_sharded(runner, True, ctx.group)
-        return None, plan.scatter(runner.grad), None, None, None, None, None, None
+        return None, plan.scatter(runner.grad), None, None, None, None, None, None, None
 
 
 def dftd3_sharded(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, rcov=None,
@@ -104,10 +104,13 @@ def dftd3_sharded(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, 
     if ref is None:
         ref = _default_reference(dt, dev)
     refcn, refc6, _ = ref._prepared(dev, dt)
+    from .disp import _element_table
+
+    tables = (rcov is None, r4r2 is None)
     if rcov is None:
-        rcov = data.COV_D3(dt, dev)[numbers]
+        rcov = _element_table("COV_D3", dt, dev)
     if r4r2 is None:
-        r4r2 = data.R4R2(dt, dev)[numbers]
+        r4r2 = _element_table("R4R2", dt, dev)
     par = _lib.Params()
     par.s6 = _scalar(param.get("s6", defaults.S6))
     par.s8 = _scalar(param.get("s8", defaults.S8))
@@ -116,4 +119,4 @@ def dftd3_sharded(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, 
     par.s9, par.rs9, par.alp = 0.0, defaults.RS9, defaults.ALP
     par.cutoff = defaults.D3_DISP_CUTOFF if cutoff is None else _scalar(cutoff)
     par.cn_cutoff, par.kcn = defaults.D3_CN_CUTOFF, defaults.D3_KCN
-    return _ShardedD3.apply(numbers, positions, rcov, r4r2, refcn, refc6, par, group)
+    return _ShardedD3.apply(numbers, positions, rcov, r4r2, refcn, refc6, par, group, tables)

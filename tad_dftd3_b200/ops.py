@@ -170,7 +170,7 @@ def _tiled(c: "_Call", order: int) -> bool:
     return c.n > limit
 
 
-def _tiled_run(c: "_Call", g, want_grad: bool):
+def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None):
     from .system import SystemPlan, SystemRunner
 
     if c.par.s9 != 0.0 and c.st.rvdw_mode != 1:
@@ -181,10 +181,10 @@ def _tiled_run(c: "_Call", g, want_grad: bool):
         )
     es, gs = [], []
     for b in range(c.nflat):
-        z = c.z[b]
-        rcov = c.rcov[z] if c.st.rcov_per_element else c.rcov[b]
-        r4r2 = c.r4r2[z] if c.st.r4r2_per_element else c.r4r2[b]
-        plan = SystemPlan(z, c.x[b], rcov, r4r2, c.st.kcn)
+        z = numbers if (c.nflat == 1 and numbers.dim() == 1 and numbers.dtype == torch.int64) else c.z[b]
+        rcov = c.rcov if c.st.rcov_per_element else c.rcov[b]
+        r4r2 = c.r4r2 if c.st.r4r2_per_element else c.r4r2[b]
+        plan = SystemPlan(z, c.x[b], rcov, r4r2, c.st.kcn, c.st.rcov_per_element, c.st.r4r2_per_element)
         run = SystemRunner(plan, c.refcn, c.refc6, c.par, None if g is None else g[b], 1, c.rvdw)
         if want_grad:
             e, gr = run.run_vjp()
@@ -198,7 +198,7 @@ def _tiled_run(c: "_Call", g, want_grad: bool):
 def _run_energy(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st):
     c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0)
     if _tiled(c, 0):
-        return _tiled_run(c, None, False)[0].reshape(*c.lead, c.n)
+        return _tiled_run(c, None, False, numbers)[0].reshape(*c.lead, c.n)
     out = c.new(c.nflat, c.n)
     if c.nflat and c.n:
         fn = getattr(_lib.lib(), f"d3b200_batch_energy_{c.sfx}")
@@ -216,7 +216,7 @@ def _run_vjp(numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6, st, want_
                 "damping-parameter gradients for structures beyond the fused-kernel "
                 f"limit ({c.n} atoms) are not available yet"
             )
-        _, gr = _tiled_run(c, c.per_atom(g), True)
+        _, gr = _tiled_run(c, c.per_atom(g), True, numbers)
         return gr.reshape(*c.lead, c.n, 3), c.new(c.nflat, NPAR, zero=True).reshape(*c.lead, NPAR)
     grad = c.new(c.nflat, c.n, 3)
     pgrad = c.new(c.nflat, NPAR, zero=True)

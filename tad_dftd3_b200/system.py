@@ -46,98 +46,116 @@ def morton_order(pos: Tensor) -> Tensor:
     return torch.argsort(code, stable=True)
 
 
-_order_cache: dict = {}   # id(numbers) -> [weakref, version, idx, order, age]
-ORDER_MAX_AGE = 20        # calls after which the Morton / element order is rebuilt
+_static_cache: dict = {}   # key -> _Static
+ORDER_MAX_AGE = 20         # calls after which the Morton / element order is rebuilt
 
 
-def _cached_order(numbers: Tensor, positions: Tensor):
-    """(idx, order) for `numbers`: indices of the real atoms and their sorted order.
-    The order only steers efficiency (the bounding boxes are recomputed from the
-    current positions on every call), so it is reused for a few calls while the
-    same `numbers` tensor keeps coming back (MD / optimisation loops)."""
-    import weakref
+class _Static:
+    """Everything of a plan that does not depend on the positions: which atoms are
+    real, their sorted order, sorted Z / kcn*rcov / sqrt(r4r2), padding, element
+    list.  The ORDER depends on the positions only through efficiency (the boxes
+    are recomputed from the current positions on every call), so it is reused for
+    `ORDER_MAX_AGE` calls while the same `numbers` tensor keeps coming back
+    (MD / optimisation loops)."""
 
-    key = id(numbers)
-    hit = _order_cache.get(key)
-    if hit is not None and hit[0]() is numbers and hit[1] == numbers._version and hit[4] < ORDER_MAX_AGE \
-            and hit[2].device == positions.device:
-        hit[4] += 1
-        return hit[2], hit[3]
-    dev = positions.device
-    idx = torch.nonzero(numbers != 0).reshape(-1)
-    n = int(idx.numel())
-    if n:
-        pos = positions.detach()[idx]
-        z = numbers[idx]
-        o1 = morton_order(pos)
-        tile = torch.arange(n, device=dev) // TILE
-        o2 = torch.argsort(tile * 128 + z[o1], stable=True)
-        order = o1[o2]
-    else:
-        order = idx
-    if len(_order_cache) > 64:
-        _order_cache.clear()
-    try:
-        _order_cache[key] = [weakref.ref(numbers), numbers._version, idx, order, 0]
-    except TypeError:  # pragma: no cover
-        pass
-    return idx, order
-
-
-class SystemPlan:
-    """Sorted / padded / packed view of one structure."""
-
-    def __init__(self, numbers: Tensor, positions: Tensor, rcov: Tensor, r4r2: Tensor, kcn: float):
+    def __init__(self, numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table):
         dev, dt = positions.device, positions.dtype
-        self.natoms_in = numbers.shape[0]
-        idx, order = _cached_order(numbers, positions)
+        idx = torch.nonzero(numbers != 0).reshape(-1)
         n = int(idx.numel())
         self.n = n
         self.npad = npad = max(TILE, -(-n // TILE) * TILE)
-        pos = positions.detach()[idx]
         z = numbers[idx]
+        if n:
+            o1 = morton_order(positions.detach()[idx])
+            tile = torch.arange(n, device=dev) // TILE
+            o2 = torch.argsort(tile * 128 + z[o1], stable=True)
+            order = o1[o2]
+        else:
+            order = idx
         self.perm = idx[order]                      # sorted slot -> original atom index
-        ps = pos[order]
         zs = z[order]
-        atoms = torch.empty(npad, 4, dtype=dt, device=dev)
-        far = _FAR + torch.arange(npad - n, device=dev, dtype=dt) * 100.0
-        atoms[:n, :3] = ps
-        atoms[:n, 3] = kcn * rcov.detach().to(dt)[self.perm]
-        atoms[n:, :3] = far.unsqueeze(-1)
-        atoms[n:, 3] = 0.0
-        self.atoms = atoms
         self.z = torch.zeros(npad, dtype=torch.int32, device=dev)
         self.z[:n] = zs.to(torch.int32)
+        rc = rcov.detach().to(dt)
+        q = r4r2.detach().to(dt)
+        rc = rc[zs] if rcov_table else rc[self.perm]
+        q = q[zs] if r4r2_table else q[self.perm]
+        template = torch.zeros(npad, 4, dtype=dt, device=dev)
+        template[n:, :3] = (_FAR + torch.arange(npad - n, device=dev, dtype=dt) * 100.0).unsqueeze(-1)
+        template[:n, 3] = kcn * rc
+        self.template = template
         self.sqrtq = torch.ones(npad, dtype=dt, device=dev)
-        self.sqrtq[:n] = torch.sqrt(r4r2.detach().to(dt)[self.perm])
+        self.sqrtq[:n] = torch.sqrt(q)
+        self.aux1 = torch.stack([self.sqrtq, torch.ones_like(self.sqrtq)], 1).contiguous()
+        self.real = (self.z != 0).reshape(npad // SUB, SUB, 1)
+        self.empty = ~self.real.any(1)
+        zlist = torch.unique(self.z[self.z > 0])
+        lut = torch.full((128,), -1, dtype=torch.int8, device=dev)
+        lut[zlist.long()] = torch.arange(zlist.numel(), dtype=torch.int8, device=dev)
+        self.elements = (zlist.to(torch.int32).contiguous(), lut[self.z.long()].contiguous())
+        self.age = 0
+
+
+def _static_for(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table) -> _Static:
+    import weakref
+
+    def tkey(t, table):
+        return ("table" if table else "atom", id(t), t._version)
+
+    key = (id(numbers), numbers._version, positions.dtype, str(positions.device), float(kcn),
+           tkey(rcov, rcov_table), tkey(r4r2, r4r2_table))
+    hit = _static_cache.get(key)
+    if hit is not None and hit[0]() is numbers and hit[1]() is rcov and hit[2]() is r4r2 \
+            and hit[3].age < ORDER_MAX_AGE:
+        hit[3].age += 1
+        return hit[3]
+    st = _Static(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table)
+    if len(_static_cache) > 32:
+        _static_cache.clear()
+    try:
+        _static_cache[key] = (weakref.ref(numbers), weakref.ref(rcov), weakref.ref(r4r2), st)
+    except TypeError:  # pragma: no cover
+        pass
+    return st
+
+
+class SystemPlan:
+    """Sorted / padded / packed view of one structure.
+
+    `rcov` / `r4r2` are per-atom arrays `[N]` (the reference's keyword arrays) or,
+    with `*_table=True`, per-element tables indexed by Z."""
+
+    def __init__(self, numbers: Tensor, positions: Tensor, rcov: Tensor, r4r2: Tensor, kcn: float,
+                 rcov_table: bool = False, r4r2_table: bool = False):
+        dev, dt = positions.device, positions.dtype
+        self.natoms_in = numbers.shape[0]
+        st = _static_for(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table)
+        self.static = st
+        self.n, self.npad, self.perm, self.z, self.sqrtq = st.n, st.npad, st.perm, st.z, st.sqrtq
+        n, npad = st.n, st.npad
+        atoms = st.template.clone()
+        atoms[:n, :3] = positions.detach()[st.perm]
+        self.atoms = atoms
         # sub-tile boxes over the real atoms (all-padding sub-tiles sit far away)
         xyz = atoms[:, :3].reshape(npad // SUB, SUB, 3)
-        real = (self.z != 0).reshape(npad // SUB, SUB, 1)
         big = torch.finfo(dt).max
-        lo = torch.where(real, xyz, xyz.new_tensor(big)).amin(1)
-        hi = torch.where(real, xyz, xyz.new_tensor(-big)).amax(1)
-        empty = ~real.any(1)
-        lo = torch.where(empty, xyz[:, 0, :], lo)
-        hi = torch.where(empty, xyz[:, 0, :], hi)
+        lo = torch.where(st.real, xyz, xyz.new_tensor(big)).amin(1)
+        hi = torch.where(st.real, xyz, xyz.new_tensor(-big)).amax(1)
+        lo = torch.where(st.empty, xyz[:, 0, :], lo)
+        hi = torch.where(st.empty, xyz[:, 0, :], hi)
         self.box = torch.cat([lo, hi], 1).contiguous()
         self.dtype, self.device = dt, dev
-        self._elements = None
 
     def elements(self):
         """(zlist int32 [E], eidx int8 [npad]) -- distinct elements and each atom's index (-1 = padding)."""
-        if self._elements is None:
-            zlist = torch.unique(self.z[self.z > 0])
-            lut = torch.full((128,), -1, dtype=torch.int8, device=self.device)
-            lut[zlist.long()] = torch.arange(zlist.numel(), dtype=torch.int8, device=self.device)
-            self._elements = (zlist.to(torch.int32).contiguous(), lut[self.z.long()].contiguous())
-        return self._elements
+        return self.static.elements
 
     def aux(self, g: Tensor | None) -> Tensor:
         """[npad, 2] = sqrt(r4r2), cotangent g (ones when None)."""
-        a = torch.ones(self.npad, 2, dtype=self.dtype, device=self.device)
-        a[:, 0] = self.sqrtq
-        if g is not None:
-            a[: self.n, 1] = g.detach().to(self.dtype)[self.perm]
+        if g is None:
+            return self.static.aux1               # read-only use
+        a = self.static.aux1.clone()
+        a[: self.n, 1] = g.detach().to(self.dtype)[self.perm]
         return a
 
     def scatter(self, sorted_vals: Tensor) -> Tensor:
@@ -161,9 +179,10 @@ class SystemRunner:
         self.par = par
         self.sfx = "f64" if dt == torch.float64 else "f32"
         self.auxt = plan.aux(g)
-        new = lambda *s: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
-        self.cn, self.decn, self.energy = new(npad), new(npad), new(npad)
-        self.w, self.dw, self.grad = new(npad, 8), new(npad, 8), new(npad, 3)
+        buf = torch.zeros(22 * npad, dtype=dt, device=dev)      # one allocation, one fill
+        self.cn, self.decn, self.energy = buf[:npad], buf[npad:2 * npad], buf[2 * npad:3 * npad]
+        self.grad = buf[3 * npad:6 * npad].view(npad, 3)
+        self.w, self.dw = buf[6 * npad:14 * npad].view(npad, 8), buf[14 * npad:22 * npad].view(npad, 8)
         self.refcn, self.refc6 = refcn, refc6
         s = _lib.System()
         s.natoms = npad
