@@ -174,9 +174,15 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
  *   _cnbwd    grad[i][3] += CN chain-rule term    (autograd through cn_d3)
  * g (in aux) is the cotangent of the per-atom energies, L = sum g_i E_i.
  *   _tvec     (optional, after _weights; needs nelem/zlist/eidx/tvec) pre-contracts
- *             T_k[e][a] = sum_b K[Z_e,Z_k,a,b] w_kb for every atom; `_pair` and `_atm`
+ *             T_k[e][a] = sum_b K[Z_e,Z_k,a,b] w_kb (and Td_k with dw_k) for every atom; `_pair` and `_atm`
  *             then need one 7-wide dot per C6 instead of a 7x7 contraction per
  *             (row, partner element).
+ * symmetric = 1 (needs the T vectors for `_pair`): every unordered pair is evaluated
+ *             once; a launch owns the row tiles row_begin/128 + k*tile_stride below
+ *             row_end and walks the tiles J >= I; results are ADDED with fp64
+ *             atomics to cn / energy / grad / decn for BOTH atoms of a pair, so the
+ *             arrays must be zero before `_cn` (cn) and before `_pair` (the others), and
+ *             on several GPUs they are summed (all-reduce) instead of gathered.
  * jsplit >= 1 CTAs share each 128-row tile (the j-tiles are dealt round-robin
  * among them, which is what fills the GPU when N / 128 is small compared with
  * the SM count); their partial rows go through `scratch`
@@ -200,7 +206,9 @@ typedef struct d3b200_system_f64 {
   int nelem;            /* optional fast path, 0 = off: number of distinct elements (<= 8) */
   const int32_t* zlist; /* [nelem] the distinct atomic numbers                              */
   const int8_t* eidx;   /* [natoms] index of each atom's element in zlist, -1 = padding     */
-  double* tvec;            /* [natoms*nelem*8 + 64] scratch filled by _system_tvec_            */
+  double* tvec;            /* [natoms*nelem*16 + 64] scratch filled by _system_tvec_           */
+  int symmetric;        /* 1: pairs-once sweeps (see below); 0: full-row sweeps             */
+  int tile_stride;      /* symmetric only: own row tiles row_begin/128 + k*tile_stride      */
 } d3b200_system_f64;
 
 typedef struct d3b200_system_f32 {
@@ -222,7 +230,9 @@ typedef struct d3b200_system_f32 {
   int nelem;            /* optional fast path, 0 = off: number of distinct elements (<= 8) */
   const int32_t* zlist; /* [nelem] the distinct atomic numbers                              */
   const int8_t* eidx;   /* [natoms] index of each atom's element in zlist, -1 = padding     */
-  float* tvec;            /* [natoms*nelem*8 + 64] scratch filled by _system_tvec_            */
+  float* tvec;            /* [natoms*nelem*16 + 64] scratch filled by _system_tvec_           */
+  int symmetric;        /* 1: pairs-once sweeps (see below); 0: full-row sweeps             */
+  int tile_stride;      /* symmetric only: own row tiles row_begin/128 + k*tile_stride      */
 } d3b200_system_f32;
 
 int d3b200_system_cn_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);

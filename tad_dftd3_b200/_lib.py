@@ -44,7 +44,8 @@ class System(C.Structure):
         (k, C.c_void_p) for k in
         ("atoms", "aux", "z", "box", "refcn", "refc6", "cn", "w", "dw", "decn", "energy", "grad")] + [
         ("jsplit", C.c_int), ("scratch", C.c_void_p),
-        ("nelem", C.c_int), ("zlist", C.c_void_p), ("eidx", C.c_void_p), ("tvec", C.c_void_p)]
+        ("nelem", C.c_int), ("zlist", C.c_void_p), ("eidx", C.c_void_p), ("tvec", C.c_void_p),
+        ("symmetric", C.c_int), ("tile_stride", C.c_int)]
 
 
 _P = C.c_void_p

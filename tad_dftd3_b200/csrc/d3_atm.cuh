@@ -279,26 +279,36 @@ struct AtmArgs2 {
 };
 
 // T vectors of every atom (grid over atoms, one thread per (atom, element))
+// tvec  [natoms][nelem][8]: T_k[e][a]  = sum_b K[Z_e, Z_k, a, b] w_kb
+// tdvec [natoms][nelem][8]: Td_k[e][a] = sum_b K[Z_e, Z_k, a, b] dw_kb   (right behind tvec)
 template <typename S>
 __global__ void system_tvec_kernel(int natoms, int nelem, const int* z, const int* zlist, const S* w,
-                                   const S* refc6, S* tvec) {
+                                   const S* dw, const S* refc6, S* tvec) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= natoms * nelem) return;
   const int k = idx / nelem, e = idx % nelem;
   const int Zk = z[k], Ze = zlist[e];
-  S out[8];
+  S out[8], outd[8];
 #pragma unroll
-  for (int a = 0; a < 8; ++a) out[a] = S(0);
+  for (int a = 0; a < 8; ++a) { out[a] = S(0); outd[a] = S(0); }
   if (Zk > 0) {
     const S* K = refc6 + ((size_t)Ze * kMaxZ + Zk) * 49;
 #pragma unroll
     for (int a = 0; a < kNRef; ++a) {
 #pragma unroll
-      for (int b = 0; b < kNRef; ++b) out[a] += __ldg(K + a * kNRef + b) * w[8 * (size_t)k + b];
+      for (int b = 0; b < kNRef; ++b) {
+        const S kab = __ldg(K + a * kNRef + b);
+        out[a] += kab * w[8 * (size_t)k + b];
+        outd[a] += kab * dw[8 * (size_t)k + b];
+      }
     }
   }
+  S* tdvec = tvec + (size_t)natoms * nelem * 8;
 #pragma unroll
-  for (int a = 0; a < 8; ++a) tvec[((size_t)k * nelem + e) * 8 + a] = out[a];
+  for (int a = 0; a < 8; ++a) {
+    tvec[((size_t)k * nelem + e) * 8 + a] = out[a];
+    tdvec[((size_t)k * nelem + e) * 8 + a] = outd[a];
+  }
 }
 
 // x^(16/3) for x > 0: y = x^(-1/3) from a float seed and one cubic step, then (x y^2)^16

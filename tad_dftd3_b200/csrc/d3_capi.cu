@@ -12,6 +12,7 @@
 #include "d3_system.cuh"
 #include "d3_atm.cuh"
 #include "d3_stages.cuh"
+#include "d3_system_sym.cuh"
 
 namespace {
 
@@ -246,6 +247,14 @@ int launched(const char* what) {
   return e == cudaSuccess ? D3B200_OK : cuda_fail(e, what);
 }
 
+// row tiles owned by a symmetric launch
+template <typename T>
+int sym_tiles(const T* s) {
+  const int stride = s->tile_stride > 0 ? s->tile_stride : 1;
+  const int span = (s->row_end - s->row_begin) / d3::kSysTile;
+  return (span + stride - 1) / stride;
+}
+
 template <typename B>
 int sys_cn(const typename SysOf<B>::type* s, const d3b200_params* par, void* stream) {
   d3::SysArgs<B> a;
@@ -254,6 +263,11 @@ int sys_cn(const typename SysOf<B>::type* s, const d3b200_params* par, void* str
   if (!s->cn) return fail(D3B200_EINVAL, "null cn%s");
   const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
   if (nblk == 0) return D3B200_OK;
+  if (s->symmetric) {
+    d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
+    d3::sym_cn_kernel<B><<<dim3(sym_tiles(s), a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    return launched("sym_cn_kernel");
+  }
   d3::system_cn_kernel<B><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
   if ((rc = launched("system_cn_kernel"))) return rc;
   d3::system_reduce_kernel<B, 0><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
@@ -275,9 +289,9 @@ int sys_tvec(const typename SysOf<B>::type* s, const d3b200_params* par, void* s
   d3::SysArgs<B> a;
   int rc = sys_fill<B>(a, s, par);
   if (rc) return rc;
-  if (!a.nelem || !s->w || !s->refc6) return fail(D3B200_EINVAL, "tvec needs nelem/zlist/eidx/tvec, w and refc6%s");
+  if (!a.nelem || !s->w || !s->dw || !s->refc6) return fail(D3B200_EINVAL, "tvec needs nelem/zlist/eidx/tvec, w and refc6%s");
   const int nt = a.natoms * a.nelem;
-  d3::system_tvec_kernel<B><<<(nt + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.natoms, a.nelem, a.z, a.zlist, a.w, a.refc6, a.tvec);
+  d3::system_tvec_kernel<B><<<(nt + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.natoms, a.nelem, a.z, a.zlist, a.w, a.dw, a.refc6, a.tvec);
   return launched("system_tvec_kernel");
 }
 
@@ -291,6 +305,23 @@ int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int wan
   const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
   if (nblk == 0) return D3B200_OK;
   if (!want_grad) a.grad = nullptr;
+  if (s->symmetric) {
+    if (!a.nelem) return fail(D3B200_EINVAL, "symmetric pair sweep needs the T vectors (nelem <= 8)%s");
+    if (!s->energy) return fail(D3B200_EINVAL, "symmetric pair sweep needs the energy array%s");
+    d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
+    const size_t smem = d3::sym_pair_smem_bytes<B>(a.nelem);
+    const dim3 grid(sym_tiles(s), a.jsplit);
+    if (want_grad) {
+      auto kern = d3::sym_pair_t_kernel<B, true>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<grid, d3::kSysTile, smem, (cudaStream_t)stream>>>(p);
+    } else {
+      auto kern = d3::sym_pair_t_kernel<B, false>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<grid, d3::kSysTile, smem, (cudaStream_t)stream>>>(p);
+    }
+    return launched("sym_pair_t_kernel");
+  }
   if (a.nelem) {
     const size_t smem = d3::pair_t_smem_bytes<B>(a.nelem);
     if (want_grad) {
@@ -317,6 +348,11 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
   if (!s->decn || !s->grad) return fail(D3B200_EINVAL, "null cnbwd argument%s");
   const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
   if (nblk == 0) return D3B200_OK;
+  if (s->symmetric) {
+    d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
+    d3::sym_cnbwd_kernel<B><<<dim3(sym_tiles(s), a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    return launched("sym_cnbwd_kernel");
+  }
   d3::system_cnbwd_kernel<B><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
   if ((rc = launched("system_cnbwd_kernel"))) return rc;
   d3::system_reduce_kernel<B, 2><<<nblk, d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
@@ -341,7 +377,7 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
     q.nelem = p.sys.nelem;
     q.eidx = p.sys.eidx;
     q.tvec = p.sys.tvec;
-    B* rve = p.sys.tvec + (size_t)p.sys.natoms * q.nelem * 8;   // 64 spare reals behind the T vectors
+    B* rve = p.sys.tvec + (size_t)p.sys.natoms * q.nelem * 16;  // 64 spare reals behind T and Td
     q.rvdw_e = rve;
     q.s9 = p.s9; q.rs9 = p.rs9; q.pexp = p.pexp;
     q.cube_root_pow = par->alp == 14.0 ? 1 : 0;

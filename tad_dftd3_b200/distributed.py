@@ -51,7 +51,8 @@ def run_sharded(runner, want_grad: bool, group=None):
     per-atom arrays.  Returns the rank's row range; afterwards `runner.energy`
     (and `runner.grad`) are complete on every rank."""
     rank, world = _world(group)
-    rows = row_partition(runner.plan.npad, world)[rank]
+    part = getattr(runner, "partition", None)
+    rows = part(rank, world) if part is not None else row_partition(runner.plan.npad, world)[rank]
     for t in (runner.cn, runner.decn, runner.energy, runner.grad):
         t.zero_()
     runner.sweep_cn(rows)

@@ -203,10 +203,28 @@ class SystemRunner:
             ne = int(zlist.numel())
             if 0 < ne <= 8:
                 self._zlist, self._eidx = zlist, eidx
-                self.tvec = torch.empty(npad * ne * 8 + 64, dtype=dt, device=dev)
+                self.tvec = torch.empty(npad * ne * 16 + 64, dtype=dt, device=dev)
                 s.nelem, s.zlist, s.eidx, s.tvec = ne, zlist.data_ptr(), eidx.data_ptr(), self.tvec.data_ptr()
                 self.use_tvec = True
+        # Pairs-once sweeps need the T vectors and pay a fixed cost per CTA (staging
+        # tiles, atomics), so they win only while a CTA still walks many j-tiles:
+        # measured on the 50k-atom cluster, 5.75 vs 6.47 ms at jsplit 5 (one GPU) but
+        # 1.31 vs 1.14 ms per rank at jsplit 37 (eight GPUs).
+        # TAD_DFTD3_B200_FULLROW=1 / =0 forces one or the other.
+        force = os.environ.get("TAD_DFTD3_B200_FULLROW")
+        self.symmetric = self.use_tvec and (force == "0" or (force != "1" and self.jsplit <= 8))
+        s.symmetric, s.tile_stride = int(self.symmetric), 1
         self.sys = s
+
+    def partition(self, rank: int, world: int):
+        """Rows this rank sweeps.  Full-row kernels: a contiguous tile-aligned range.
+        Pairs-once kernels: every `world`-th row tile starting at tile `rank`
+        (the triangle J >= I is balanced that way)."""
+        if self.symmetric:
+            self.sys.tile_stride = max(1, world)
+            return (min(rank * TILE, self.plan.npad), self.plan.npad)
+        self.sys.tile_stride = 1
+        return row_partition(self.plan.npad, world)[rank]
 
     def _call(self, name, rows, *extra):
         self.sys.row_begin, self.sys.row_end = rows if rows is not None else (0, self.plan.npad)
