@@ -165,6 +165,53 @@ def reference_step_fn(nmol_sample, seed=0):
     return step, kind, near + far, desc
 
 
+def reference_single(numbers, positions, param, *, cutoff=None, rvdw_table=None, hessian=False, chunk_size=None):
+    """The reference's own CPU path (unmodified source over the stand-in when `baseline/_ref`
+    or /root/reference is present, else the oracle port) on ONE structure: returns
+    (seconds for energy + gradient [or the Hessian], kind)."""
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from refimport import reference_available
+
+    dt = torch.double
+    numbers, positions = numbers.cpu(), positions.cpu().to(dt)
+    c6 = syn.synthetic_c6_table(dt)
+    rcov, r4r2 = COV_D3(dt)[numbers], R4R2(dt)[numbers]
+    par = {k: torch.tensor(float(v), dtype=dt) for k, v in param.items()}
+    rvdw = None if rvdw_table is None else rvdw_table.cpu()[numbers.unsqueeze(-1), numbers.unsqueeze(-2)]
+    cut = None if cutoff is None else torch.tensor(cutoff, dtype=dt)
+    if reference_available() is not None:
+        from refimport import import_reference
+
+        d3ref = import_reference()
+        from tad_dftd3.reference import Reference
+
+        refobj = Reference(cn=REFCN(dt), c6=c6)
+        kind = "reference"
+
+        def energy(pos):
+            return d3ref.dftd3(numbers, pos, par, ref=refobj, rcov=rcov, r4r2=r4r2, rvdw=rvdw, cutoff=cut,
+                               chunk_size=chunk_size)
+    else:
+        import d3_oracle as orc
+
+        kind = "port"
+
+        def energy(pos):
+            return orc.dftd3(numbers, pos, par, refcn=REFCN(dt), refc6=c6, rcov=rcov, r4r2=r4r2, rvdw=rvdw,
+                             cutoff=50.0 if cutoff is None else cutoff)
+
+    t0 = time.perf_counter()
+    if hessian:
+        torch.func.jacrev(torch.func.jacrev(lambda p: energy(p).sum(-1)))(positions)
+    else:
+        pos = positions.clone().requires_grad_(True)
+        torch.autograd.grad(energy(pos).sum(), pos)
+    return time.perf_counter() - t0, kind
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -641,6 +688,19 @@ def run_c5a(args, rank, local, world, dev):
                      "flops_model": "140 per unordered triple (SURVEY.md 8d)"},
         "clocks": clocks.summary(),
     }
+    if not args.no_cpu_baseline:
+        # the reference's ATM is dense N^3 (216 MB per temporary at N = 300): time a 300-atom sub-cluster
+        torch.set_num_threads(os.cpu_count() or 1)
+        centre = positions.mean(0)
+        sub = torch.argsort((positions - centre).norm(dim=1))[:300]
+        t_sub, _, _ = count_triples(positions[sub], args.cutoff)
+        sec, kind = reference_single(numbers[sub], positions[sub], dict(PARAM, s9=1.0), cutoff=args.cutoff,
+                                     rvdw_table=rvdw)
+        sec0, _ = reference_single(numbers[sub], positions[sub], PARAM, cutoff=args.cutoff)
+        line["cpu_baseline"] = {"value": t_sub / max(sec - sec0, 1e-9), "unit": "triples/s",
+                                "cores": torch.get_num_threads(), "kind": kind, "seconds": sec - sec0,
+                                "sample": "central 300-atom sub-cluster, (two-body + ATM) minus (two-body) wall time, "
+                                          "energy + autograd gradient"}
     print(json.dumps(line))
 
 
@@ -677,6 +737,11 @@ def run_c5b(args, rank, local, world, dev):
             "config": {"workload": "c5b: examples/hessian.py construction on one 200-atom chain-grown molecule",
                        "hessian_shape": list(h.shape), "max_asymmetry": sym,
                        "reference_cpu_seconds_survey": 10.6}}
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sec, kind = reference_single(numbers, positions, PARAM, hessian=True)
+        line["cpu_baseline"] = {"value": sec, "unit": "s", "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": "the same 200-atom molecule, jacrev o jacrev through the reference"}
     print(json.dumps(line))
 
 
