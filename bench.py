@@ -250,7 +250,8 @@ def main():
     ap.add_argument("--nmol", type=int, default=4096)
     ap.add_argument("--ref-nmol", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=1, help="c3 end-to-end: pipeline the batch in this many chunks")
+    ap.add_argument("--e2e-chunk", type=int, default=0,
+                    help="c3 end-to-end: structures per pipeline chunk of dftd3_host (0 = library default, one wave of CTAs)")
     ap.add_argument("--cutoff", type=float, default=25.0, help="c5a: dispersion/triple cutoff in Bohr")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5a", "c5b"],
                     help="c3: 4096-molecule batch (default, the headline metric); "
@@ -280,7 +281,7 @@ def main():
     from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
 
     lib = _lib.lib()
-    dt = torch.double
+    dt = torch.double if args.dtype == "f64" else torch.float32
     if args.workload == "c5a":
         run_c5a(args, rank, local, world, dev)
         return
@@ -360,27 +361,16 @@ def main():
         e_h = torch.empty(numbers.shape, dtype=dt).pin_memory()
         g_h = torch.empty(*numbers.shape, 3, dtype=dt).pin_memory()
 
-        # The batch is independent per structure, so the end-to-end path streams it
-        # in chunks over two CUDA streams: H2D of chunk k+1 and D2H of chunk k-1
-        # overlap the kernel of chunk k.  Every chunk goes through the public API.
-        nchunk = max(1, args.e2e_chunks)
-        bounds = [args.nmol * k // nchunk for k in range(nchunk + 1)]
-        streams = [torch.cuda.Stream(dev) for _ in range(min(2, nchunk))]
+        # End to end through the public host-buffer API: `dftd3_host` cuts the batch
+        # into chunks of structures and pipelines H2D copy / fused kernel / D2H copy
+        # (d3b200_batch_vjp_host_f64); it returns after the results are in e_h / g_h.
+        host_chunk = max(0, args.e2e_chunk)
+        n_e2e_launch = d3.HostPipeline.chunks(args.nmol, host_chunk)
+        positions_e2e, ref_e2e = positions_h, ref
 
         def step_e2e():
-            for s_ in streams:
-                s_.wait_stream(stream)
-            for k in range(nchunk):
-                lo, hi = bounds[k], bounds[k + 1]
-                with torch.cuda.stream(streams[k % len(streams)]):
-                    z = numbers_h[lo:hi].to(dev, non_blocking=True)
-                    x = positions_h[lo:hi].to(dev, non_blocking=True).requires_grad_(True)
-                    e = d3.dftd3(z, x, par, ref=ref)
-                    (gx,) = torch.autograd.grad(e.sum(), x)
-                    e_h[lo:hi].copy_(e.detach(), non_blocking=True)
-                    g_h[lo:hi].copy_(gx, non_blocking=True)
-            for s_ in streams:
-                stream.wait_stream(s_)
+            d3.dftd3_host(numbers_h, positions_e2e, par, ref=ref_e2e, energy_out=e_h, grad_out=g_h,
+                          chunk=host_chunk, device=dev, sync=True)
 
         for _ in range(args.warmup):
             step_e2e()
@@ -445,8 +435,9 @@ def main():
                 "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * positions_h.element_size()),
                 "d2h_bytes_per_step": int((e_h.numel() + g_h.numel()) * e_h.element_size()),
                 "ms_per_step": e2e_ms,
-                "api": f"tad_dftd3_b200.dftd3() + torch.autograd.grad per chunk ({nchunk} chunks over 2 streams), "
-                       "pinned host buffers",
+                "api": f"tad_dftd3_b200.dftd3_host(): pinned host buffers in, pinned host energies + gradient out; "
+                       f"{n_e2e_launch} chunks pipelined H2D / kernel / D2H (d3b200_batch_vjp_host_{args.dtype}), "
+                       "synchronised every step",
             },
             "gpu_launches": launches,
             "roofline": {

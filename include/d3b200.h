@@ -155,6 +155,45 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Host-buffer entry (the end-to-end form of `_batch_vjp_`): inputs and outputs
+ * live in HOST memory (page-locked for the copies to be asynchronous), as a
+ * caller of the reference's CPU `dftd3()` + autograd holds them.
+ *
+ * The batch is independent per structure, so it is cut into chunks of
+ * `chunk` structures and pipelined over the streams of a `d3b200_pipe`:
+ * H2D of chunk k+1, the fused kernel of chunk k (two alternating compute
+ * streams, so that the tail of one launch overlaps the head of the next) and
+ * D2H of chunk k-1 run concurrently.  Work is ordered after everything already
+ * queued on `stream`, and `stream` waits for the last D2H: synchronise `stream`
+ * before reading h_energy / h_grad.  Nothing is synchronised inside.
+ *
+ * A pipe owns 4 CUDA streams and a set of events on the current device; it is
+ * the only object of this ABI that is created and destroyed, and one pipe must
+ * not be used by two host threads at the same time.
+ *
+ *   model     : tables in DEVICE memory; per-element rcov / r4r2 only
+ *               (rcov_per_element = r4r2_per_element = 1), rvdw_mode 0 or 1
+ *   h_g       : cotangent `[nbatch][natoms]` or NULL (unit cotangent)
+ *   h_energy  : `[nbatch][natoms]` or NULL;  h_grad: `[nbatch][natoms][3]`
+ *   workspace : DEVICE staging, `d3b200_batch_host_workspace_bytes_*` bytes
+ *   chunk     : structures per chunk; <= 0 picks one (about one wave of CTAs) */
+typedef struct d3b200_pipe d3b200_pipe;
+int d3b200_pipe_create(d3b200_pipe** pipe);
+int d3b200_pipe_destroy(d3b200_pipe* pipe);
+size_t d3b200_batch_host_workspace_bytes_f64(int nbatch, int natoms, int with_g, int atm);
+size_t d3b200_batch_host_workspace_bytes_f32(int nbatch, int natoms, int with_g, int atm);
+int d3b200_batch_vjp_host_f64(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_numbers,
+                              const double* h_positions, const d3b200_model_f64* model,
+                              const d3b200_params* par, const double* h_g, double* h_energy,
+                              double* h_grad, void* workspace, size_t workspace_bytes, int chunk,
+                              void* stream);
+int d3b200_batch_vjp_host_f32(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_numbers,
+                              const float* h_positions, const d3b200_model_f32* model,
+                              const d3b200_params* par, const float* h_g, float* h_energy,
+                              float* h_grad, void* workspace, size_t workspace_bytes, int chunk,
+                              void* stream);
+
+/* ------------------------------------------------------------------------
  * One large structure, tiled over the whole GPU and shardable by rows.
  *
  * Same path as above (reference disp.py:150-165) for structures too large for

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "d3b200_last_error": ([], C.c_char_p),
     "d3b200_batch_max_atoms_f64": ([_I], C.c_int),
     "d3b200_batch_max_atoms_f32": ([_I], C.c_int),
+    "d3b200_pipe_create": ([C.POINTER(C.c_void_p)], C.c_int),
+    "d3b200_pipe_destroy": ([_P], C.c_int),
 }
 for _sfx in ("f64", "f32"):
     _SIGNATURES[f"d3b200_batch_energy_{_sfx}"] = (
@@ -65,6 +67,9 @@ for _sfx in ("f64", "f32"):
         [_I, _I, _P, _P, _P, C.POINTER(Model), C.POINTER(Params), C.POINTER(Params),
          _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P], C.c_int)
     _SIGNATURES[f"d3b200_batch_workspace_bytes_{_sfx}"] = ([_I, _I, _I, _I], C.c_size_t)
+    _SIGNATURES[f"d3b200_batch_host_workspace_bytes_{_sfx}"] = ([_I, _I, _I, _I], C.c_size_t)
+    _SIGNATURES[f"d3b200_batch_vjp_host_{_sfx}"] = (
+        [_P, _I, _I, _P, _P, C.POINTER(Model), C.POINTER(Params), _P, _P, _P, _P, C.c_size_t, _I, _P], C.c_int)
 
     _SIGNATURES[f"d3b200_probe_fma_{_sfx}"] = ([_I, _I, _P, _P], C.c_int)
     for _k in ("cn", "weights", "cnbwd"):

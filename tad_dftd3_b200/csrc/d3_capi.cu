@@ -210,6 +210,104 @@ int hvp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
   return launch<S, kWantE | kWantG | kWantP>(a, s);
 }
 
+// ---------------------------------------------------------------- host-buffer pipeline
+}  // namespace
+
+constexpr int kPipeMaxChunks = 64;
+struct d3b200_pipe {
+  cudaStream_t in, out, comp[2];
+  cudaEvent_t start, done, ev_in[kPipeMaxChunks], ev_k[kPipeMaxChunks];
+  int device;
+};
+
+namespace {
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+template <typename B>
+size_t host_workspace_bytes(int nbatch, int natoms, int with_g, int atm) {
+  if (nbatch <= 0 || natoms <= 0) return 0;
+  const size_t na = (size_t)nbatch * natoms;
+  size_t b = align256(na * sizeof(int64_t)) + align256(na * 3 * sizeof(B));   // numbers, positions
+  if (with_g) b += align256(na * sizeof(B));
+  b += align256(na * sizeof(B)) + align256(na * 3 * sizeof(B));                 // energy, grad
+  b += align256(workspace_bytes<B>(nbatch, natoms, atm));
+  return b;
+}
+
+template <typename B>
+int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_numbers, const B* h_positions,
+                  const typename ModelOf<B>::type* model, const d3b200_params* par, const B* h_g,
+                  B* h_energy, B* h_grad, void* workspace, size_t wbytes, int chunk, void* stream) {
+  if (!pipe) return fail(D3B200_EINVAL, "null pipe%s");
+  if (nbatch < 0 || natoms < 0) return fail(D3B200_EINVAL, "negative size%s");
+  if (!h_numbers || !h_positions || !model || !par || !h_grad) return fail(D3B200_EINVAL, "null argument%s");
+  if (!model->rcov_per_element || !model->r4r2_per_element || model->rvdw_mode == 2)
+    return fail(D3B200_EINVAL, "host entry takes per-element rcov / r4r2 / rvdw tables only%s");
+  if (nbatch == 0 || natoms == 0) return D3B200_OK;
+  const int atm = par->s9 != 0.0;
+  const size_t need = host_workspace_bytes<B>(nbatch, natoms, h_g != nullptr, atm);
+  if (!workspace || wbytes < need)
+    return fail(D3B200_EINVAL, "host-entry workspace too small%s: %ld < %ld bytes", "", (long)wbytes, (long)need);
+  if (chunk <= 0) chunk = 592;  // 148 SMs x 4 resident CTAs of the fused kernel
+  if ((nbatch + chunk - 1) / chunk + 4 > kPipeMaxChunks) chunk = (nbatch + kPipeMaxChunks - 5) / (kPipeMaxChunks - 4);
+  // chunk boundaries: quarter- and half-size chunks at both ends, so that the
+  // un-overlapped first H2D copy and last D2H copy are short
+  int bounds[kPipeMaxChunks + 1];
+  int nchunk = 0;
+  {
+    const int q = chunk / 4, h = chunk / 2;
+    int lo = 0, hi = nbatch;
+    int head[2], tail[2], nh = 0, nt = 0;
+    if (q > 0 && nbatch >= 2 * chunk) { head[nh++] = q; head[nh++] = h; tail[nt++] = q; tail[nt++] = h; }
+    bounds[nchunk++] = 0;
+    for (int k = 0; k < nh; ++k) { lo += head[k]; bounds[nchunk++] = lo; }
+    for (int k = 0; k < nt; ++k) hi -= tail[k];
+    while (lo + chunk < hi) { lo += chunk; bounds[nchunk++] = lo; }
+    if (lo < hi) bounds[nchunk++] = hi;
+    for (int k = nt - 1; k >= 0; --k) { hi += tail[k]; bounds[nchunk++] = hi; }
+    --nchunk;  // bounds[0..nchunk]
+  }
+
+  const size_t na = (size_t)nbatch * natoms;
+  char* w = reinterpret_cast<char*>(workspace);
+  int64_t* d_z = reinterpret_cast<int64_t*>(w); w += align256(na * sizeof(int64_t));
+  B* d_x = reinterpret_cast<B*>(w); w += align256(na * 3 * sizeof(B));
+  B* d_g = nullptr;
+  if (h_g) { d_g = reinterpret_cast<B*>(w); w += align256(na * sizeof(B)); }
+  B* d_e = reinterpret_cast<B*>(w); w += align256(na * sizeof(B));
+  B* d_gr = reinterpret_cast<B*>(w); w += align256(na * 3 * sizeof(B));
+  char* d_atm = w;
+  const size_t atm_per = workspace_bytes<B>(1, natoms, atm);
+
+  cudaError_t e;
+#define D3_CK(call, what) if ((e = (call)) != cudaSuccess) return cuda_fail(e, what)
+  D3_CK(cudaEventRecord(pipe->start, (cudaStream_t)stream), "cudaEventRecord");
+  D3_CK(cudaStreamWaitEvent(pipe->in, pipe->start, 0), "cudaStreamWaitEvent");
+  for (int k = 0; k < nchunk; ++k) {
+    const int lo = bounds[k], nb = bounds[k + 1] - lo;
+    const size_t o = (size_t)lo * natoms, cnt = (size_t)nb * natoms;
+    D3_CK(cudaMemcpyAsync(d_z + o, h_numbers + o, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, pipe->in), "H2D numbers");
+    D3_CK(cudaMemcpyAsync(d_x + 3 * o, h_positions + 3 * o, cnt * 3 * sizeof(B), cudaMemcpyHostToDevice, pipe->in), "H2D positions");
+    if (h_g) D3_CK(cudaMemcpyAsync(d_g + o, h_g + o, cnt * sizeof(B), cudaMemcpyHostToDevice, pipe->in), "H2D cotangent");
+    D3_CK(cudaEventRecord(pipe->ev_in[k], pipe->in), "cudaEventRecord");
+    cudaStream_t cs = pipe->comp[k & 1];
+    D3_CK(cudaStreamWaitEvent(cs, pipe->ev_in[k], 0), "cudaStreamWaitEvent");
+    int rc = vjp_impl<B>(nb, natoms, d_z + o, d_x + 3 * o, model, par, h_g ? d_g + o : nullptr,
+                         h_energy ? d_e + o : nullptr, d_gr + 3 * o, nullptr,
+                         atm ? d_atm + (size_t)lo * atm_per : nullptr, (size_t)nb * atm_per, cs);
+    if (rc) return rc;
+    D3_CK(cudaEventRecord(pipe->ev_k[k], cs), "cudaEventRecord");
+    D3_CK(cudaStreamWaitEvent(pipe->out, pipe->ev_k[k], 0), "cudaStreamWaitEvent");
+    if (h_energy) D3_CK(cudaMemcpyAsync(h_energy + o, d_e + o, cnt * sizeof(B), cudaMemcpyDeviceToHost, pipe->out), "D2H energy");
+    D3_CK(cudaMemcpyAsync(h_grad + 3 * o, d_gr + 3 * o, cnt * 3 * sizeof(B), cudaMemcpyDeviceToHost, pipe->out), "D2H gradient");
+  }
+  D3_CK(cudaEventRecord(pipe->done, pipe->out), "cudaEventRecord");
+  D3_CK(cudaStreamWaitEvent((cudaStream_t)stream, pipe->done, 0), "cudaStreamWaitEvent");
+#undef D3_CK
+  return D3B200_OK;
+}
+
 // ---------------------------------------------------------------- tiled system
 template <typename B> struct SysOf;
 template <> struct SysOf<double> { using type = d3b200_system_f64; };
@@ -540,6 +638,59 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
                          void* workspace, size_t workspace_bytes, void* stream) {
   return hvp_impl<float>(nbatch, natoms, numbers, positions, dpositions, model, par, dpar, g,
                          grad, pgrad, denergy, dgrad, dpgrad, workspace, workspace_bytes, stream);
+}
+
+int d3b200_pipe_create(d3b200_pipe** out) {
+  if (!out) return fail(D3B200_EINVAL, "null argument%s");
+  d3b200_pipe* p = (d3b200_pipe*)calloc(1, sizeof(d3b200_pipe));
+  if (!p) return fail(D3B200_EINVAL, "out of host memory%s");
+  cudaError_t e = cudaGetDevice(&p->device);
+  cudaStream_t* ss[4] = {&p->in, &p->out, &p->comp[0], &p->comp[1]};
+  for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(ss[k], cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->start, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming);
+  for (int k = 0; k < kPipeMaxChunks && e == cudaSuccess; ++k) {
+    e = cudaEventCreateWithFlags(&p->ev_in[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_k[k], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { d3b200_pipe_destroy(p); return cuda_fail(e, "d3b200_pipe_create"); }
+  *out = p;
+  return D3B200_OK;
+}
+int d3b200_pipe_destroy(d3b200_pipe* p) {
+  if (!p) return D3B200_OK;
+  cudaStream_t ss[4] = {p->in, p->out, p->comp[0], p->comp[1]};
+  for (int k = 0; k < 4; ++k) if (ss[k]) cudaStreamDestroy(ss[k]);
+  if (p->start) cudaEventDestroy(p->start);
+  if (p->done) cudaEventDestroy(p->done);
+  for (int k = 0; k < kPipeMaxChunks; ++k) {
+    if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
+    if (p->ev_k[k]) cudaEventDestroy(p->ev_k[k]);
+  }
+  free(p);
+  return D3B200_OK;
+}
+size_t d3b200_batch_host_workspace_bytes_f64(int nbatch, int natoms, int with_g, int atm) {
+  return host_workspace_bytes<double>(nbatch, natoms, with_g, atm);
+}
+size_t d3b200_batch_host_workspace_bytes_f32(int nbatch, int natoms, int with_g, int atm) {
+  return host_workspace_bytes<float>(nbatch, natoms, with_g, atm);
+}
+int d3b200_batch_vjp_host_f64(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_numbers,
+                              const double* h_positions, const d3b200_model_f64* model,
+                              const d3b200_params* par, const double* h_g, double* h_energy,
+                              double* h_grad, void* workspace, size_t workspace_bytes, int chunk,
+                              void* stream) {
+  return vjp_host_impl<double>(pipe, nbatch, natoms, h_numbers, h_positions, model, par, h_g, h_energy,
+                               h_grad, workspace, workspace_bytes, chunk, stream);
+}
+int d3b200_batch_vjp_host_f32(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_numbers,
+                              const float* h_positions, const d3b200_model_f32* model,
+                              const d3b200_params* par, const float* h_g, float* h_energy,
+                              float* h_grad, void* workspace, size_t workspace_bytes, int chunk,
+                              void* stream) {
+  return vjp_host_impl<float>(pipe, nbatch, natoms, h_numbers, h_positions, model, par, h_g, h_energy,
+                              h_grad, workspace, workspace_bytes, chunk, stream);
 }
 
 }  // extern "C"

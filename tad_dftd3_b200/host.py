@@ -1,0 +1,180 @@
+"""
+Energies and forces for batches that live in HOST memory.
+
+The reference computes on whatever device its inputs are on; a user with the
+batch in host memory (the reference's CPU use: `dftd3(numbers, positions,
+param)` followed by `torch.autograd.grad`, README.rst:200-266) gets the same
+two results here from one call:
+
+    energy, grad = tad_dftd3_b200.dftd3_host(numbers, positions, param)
+
+`numbers` / `positions` are CPU tensors (pinned memory makes the copies
+asynchronous); `energy [B, N]` and `grad [B, N, 3] = d(sum_i g_i E_i)/dx` come
+back as pinned CPU tensors.  Underneath, `d3b200_batch_vjp_host_*`
+(include/d3b200.h) cuts the batch into chunks of structures and pipelines
+H2D copy, fused kernel and D2H copy over the streams of a `d3b200_pipe`, so the
+PCIe transfers overlap the arithmetic instead of bracketing it.
+
+There is no CPU arithmetic here either: the CUDA library is required.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib, defaults
+from .ops import Settings, _params, _sfx
+
+__all__ = ["dftd3_host", "HostPipeline"]
+
+
+class HostPipeline:
+    """Owner of one `d3b200_pipe` and the device staging buffer of one device."""
+
+    def __init__(self, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("HostPipeline needs a CUDA device (tad_dftd3_b200 has no CPU path)")
+        self._lib = _lib.lib()
+        self._pipe = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.d3b200_pipe_create(C.byref(self._pipe)))
+        self._work: Optional[Tensor] = None
+        self._tables: dict = {}
+
+    def close(self):
+        if self._pipe:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                self._lib.d3b200_pipe_destroy(self._pipe)
+            self._pipe = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def chunks(nbatch: int, chunk: int = 0) -> int:
+        """Number of chunks (= kernel launches) `d3b200_batch_vjp_host_*` cuts a batch into."""
+        c = chunk if chunk > 0 else 592
+        if -(-nbatch // c) + 4 > 64:
+            c = (nbatch + 59) // 60
+        if c // 4 > 0 and nbatch >= 2 * c:
+            inner = nbatch - 2 * (c // 4 + c // 2)
+            return 4 + -(-inner // c)
+        return -(-nbatch // c)
+
+    def _workspace(self, nbytes: int) -> Tensor:
+        if self._work is None or self._work.numel() < nbytes:
+            self._work = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        return self._work
+
+    def run(self, numbers: Tensor, positions: Tensor, param: dict, *, ref=None, cutoff=None,
+            g: Optional[Tensor] = None, energy_out: Optional[Tensor] = None,
+            grad_out: Optional[Tensor] = None, chunk: int = 0, sync: bool = True):
+        from . import disp
+
+        if numbers.device.type != "cpu" or positions.device.type != "cpu":
+            raise RuntimeError("dftd3_host takes CPU tensors; use dftd3() for tensors already on the GPU")
+        if numbers.shape != positions.shape[:-1]:
+            raise ValueError(
+                f"Shape of positions ({tuple(positions.shape[:-1])}) is not consistent "
+                f"with atomic numbers ({tuple(numbers.shape)})."
+            )
+        if positions.shape[-1] != 3:
+            raise ValueError("positions must have shape (..., nat, 3)")
+        disp._check_numbers(numbers)   # ValueError for Z >= 104, once per distinct tensor
+        dt, dev = positions.dtype, self.device
+        sfx = _sfx(dt)
+        lead, n = positions.shape[:-2], positions.shape[-2]
+        z = numbers.to(torch.int64).contiguous().reshape(-1, n)
+        x = positions.contiguous().reshape(-1, n, 3)
+        nb = x.shape[0]
+        if self._lib.d3b200_batch_max_atoms_f64(0) < n:
+            raise ValueError("dftd3_host handles structures that fit the fused kernel; use dftd3() for larger ones")
+
+        if ref is None:
+            ref = disp._default_reference(dt, dev)
+        refcn, refc6, symmetric = ref._prepared(dev, dt)
+        if not symmetric:
+            raise ValueError("reference C6 table must be symmetric: c6[z1,z2,a,b] == c6[z2,z1,b,a]")
+        atm = disp._atm_requested(param)
+        rcov_t = disp._element_table("COV_D3", dt, dev)
+        r4r2_t = disp._element_table("R4R2", dt, dev)
+        rvdw_t = disp._element_table("VDW_PAIRWISE", dt, dev) if atm else None
+        st = Settings(
+            rcov_per_element=True, r4r2_per_element=True, rvdw_mode=1 if atm else 0,
+            cutoff=defaults.D3_DISP_CUTOFF if cutoff is None else disp._scalar(cutoff),
+            cn_cutoff=defaults.D3_CN_CUTOFF, kcn=defaults.D3_KCN,
+            alp=disp._scalar(param.get("alp", defaults.ALP)),
+        )
+        keys = ("s6", "s8", "a1", "a2", "s9")
+        dflt = (defaults.S6, defaults.S8, defaults.A1, defaults.A2, 0.0)
+        pv = [disp._scalar(param.get(k, d)) for k, d in zip(keys, dflt)]
+        if not atm:
+            pv[4] = 0.0
+        par = _params(pv, st)
+        m = _lib.Model()
+        m.rcov, m.r4r2 = rcov_t.data_ptr(), r4r2_t.data_ptr()
+        m.rcov_per_element = m.r4r2_per_element = 1
+        m.refcn, m.refc6 = refcn.data_ptr(), refc6.data_ptr()
+        m.rvdw = rvdw_t.data_ptr() if atm else None
+        m.rvdw_mode = 1 if atm else 0
+
+        if g is not None:
+            g = g.to(dt).expand(*lead, n).contiguous().reshape(nb, n)
+        if energy_out is None:
+            energy_out = torch.empty(nb, n, dtype=dt, pin_memory=True)
+        if grad_out is None:
+            grad_out = torch.empty(nb, n, 3, dtype=dt, pin_memory=True)
+        for t, shape in ((energy_out, (nb, n)), (grad_out, (nb, n, 3))):
+            if t.device.type != "cpu" or t.dtype != dt or not t.is_contiguous() or t.numel() != nb * n * (3 if len(shape) == 3 else 1):
+                raise ValueError("output buffers must be contiguous CPU tensors of the positions' dtype and shape")
+
+        if nb and n:
+            wsfn = getattr(self._lib, f"d3b200_batch_host_workspace_bytes_{sfx}")
+            wbytes = int(wsfn(nb, n, int(g is not None), int(atm)))
+            work = self._workspace(wbytes)
+            fn = getattr(self._lib, f"d3b200_batch_vjp_host_{sfx}")
+            _lib.launch_count += self.chunks(nb, chunk)
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev)
+                _lib.check(fn(self._pipe, nb, n, C.c_void_p(z.data_ptr()), C.c_void_p(x.data_ptr()),
+                              C.byref(m), C.byref(par), None if g is None else C.c_void_p(g.data_ptr()),
+                              C.c_void_p(energy_out.data_ptr()), C.c_void_p(grad_out.data_ptr()),
+                              C.c_void_p(work.data_ptr()), C.c_size_t(work.numel()), int(chunk),
+                              C.c_void_p(stream.cuda_stream)))
+                # host inputs must outlive the asynchronous copies
+                self._keep = (z, x, g, refcn, refc6)
+                if sync:
+                    stream.synchronize()
+        return energy_out.reshape(*lead, n), grad_out.reshape(*lead, n, 3)
+
+
+_pipes: dict = {}
+
+
+def dftd3_host(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, cutoff=None,
+               g: Optional[Tensor] = None, device=None, energy_out: Optional[Tensor] = None,
+               grad_out: Optional[Tensor] = None, chunk: int = 0, sync: bool = True):
+    """
+    Atom-resolved D3 energies and the gradient of `sum(g * energy)` (g = 1 by
+    default, i.e. minus the forces) for a padded batch held in host memory.
+
+    Same model as `dftd3()` with the default element tables (reference
+    disp.py:79-165); returns `(energy [..., N], grad [..., N, 3])` as CPU
+    tensors.  With `sync=False` the call returns as soon as the work is queued;
+    synchronise the current stream of `device` before reading the outputs.
+    """
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    pipe = _pipes.get(key)
+    if pipe is None:
+        pipe = _pipes[key] = HostPipeline(torch.device("cuda", key))
+    return pipe.run(numbers, positions, param, ref=ref, cutoff=cutoff, g=g, energy_out=energy_out,
+                    grad_out=grad_out, chunk=chunk, sync=sync)
