@@ -248,6 +248,8 @@ typedef struct d3b200_system_f64 {
   double* tvec;            /* [natoms*nelem*16 + 64] scratch filled by _system_tvec_           */
   int symmetric;        /* 1: pairs-once sweeps (see below); 0: full-row sweeps             */
   int tile_stride;      /* symmetric only: own row tiles row_begin/128 + k*tile_stride      */
+  void* atm_work;       /* optional scratch of `_system_atm_` (d3b200_system_atm_workspace_bytes_*) */
+  size_t atm_work_bytes;
 } d3b200_system_f64;
 
 typedef struct d3b200_system_f32 {
@@ -272,6 +274,8 @@ typedef struct d3b200_system_f32 {
   float* tvec;            /* [natoms*nelem*16 + 64] scratch filled by _system_tvec_           */
   int symmetric;        /* 1: pairs-once sweeps (see below); 0: full-row sweeps             */
   int tile_stride;      /* symmetric only: own row tiles row_begin/128 + k*tile_stride      */
+  void* atm_work;       /* optional scratch of `_system_atm_` (d3b200_system_atm_workspace_bytes_*) */
+  size_t atm_work_bytes;
 } d3b200_system_f32;
 
 int d3b200_system_cn_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
@@ -290,7 +294,14 @@ int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* p
  * once per short edge) the three-body parts to energy[], grad[] and decn[] for
  * the triples whose owner edge (i, j), i < j, has i in row_begin..row_end-1
  * (any row range).  rvdw: `[104][104]` element-pair table.  Uses the T vectors
- * when the system struct carries them (after `_system_tvec_`). */
+ * when the system struct carries them (after `_system_tvec_`).
+ * With the T vectors AND `atm_work` (device scratch of at least
+ * `d3b200_system_atm_workspace_bytes_*(natoms)` bytes, no initialisation needed)
+ * every triple is evaluated once: persistent CTAs take centre atoms
+ * row_begin..row_end-1 from a counter, compact the centre's neighbour list into
+ * the scratch and walk the pairs of neighbours (see csrc/d3_atm3.cuh). */
+size_t d3b200_system_atm_workspace_bytes_f64(int natoms);
+size_t d3b200_system_atm_workspace_bytes_f32(int natoms);
 int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par,
                           const double* rvdw, int want_grad, void* stream);
 int d3b200_system_atm_f32(const d3b200_system_f32* sys, const d3b200_params* par,

@@ -45,7 +45,8 @@ class System(C.Structure):
         ("atoms", "aux", "z", "box", "refcn", "refc6", "cn", "w", "dw", "decn", "energy", "grad")] + [
         ("jsplit", C.c_int), ("scratch", C.c_void_p),
         ("nelem", C.c_int), ("zlist", C.c_void_p), ("eidx", C.c_void_p), ("tvec", C.c_void_p),
-        ("symmetric", C.c_int), ("tile_stride", C.c_int)]
+        ("symmetric", C.c_int), ("tile_stride", C.c_int),
+        ("atm_work", C.c_void_p), ("atm_work_bytes", C.c_size_t)]
 
 
 _P = C.c_void_p
@@ -81,6 +82,7 @@ for _sfx in ("f64", "f32"):
     _SIGNATURES[f"d3b200_stage_disp2_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, C.POINTER(Params), _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_atm_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, C.POINTER(Params), _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_system_atm_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _P, _I, _P], C.c_int)
+    _SIGNATURES[f"d3b200_system_atm_workspace_bytes_{_sfx}"] = ([_I], C.c_size_t)
     _SIGNATURES[f"d3b200_system_tvec_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _P], C.c_int)
 
 _lib = None

@@ -11,6 +11,7 @@
 #include "d3_molecule_v2.cuh"
 #include "d3_system.cuh"
 #include "d3_atm.cuh"
+#include "d3_atm3.cuh"
 #include "d3_stages.cuh"
 #include "d3_system_sym.cuh"
 
@@ -457,6 +458,17 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
   return launched("system_reduce_kernel");
 }
 
+// CTAs of the persistent ATM kernel: resident CTAs per SM x SMs of the current device
+int atm3_grid() {
+  int dev = 0, nsm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) {
+    cudaGetLastError();
+    nsm = 148;
+  }
+  return nsm * d3::kAtm3Ctas;
+}
+
 template <typename B>
 int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int want_grad, void* stream) {
   d3::AtmArgs<B> p;
@@ -480,6 +492,21 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
     q.s9 = p.s9; q.rs9 = p.rs9; q.pexp = p.pexp;
     q.cube_root_pow = par->alp == 14.0 ? 1 : 0;
     d3::system_rvdw_compact_kernel<B><<<1, 64, 0, st>>>(q.nelem, p.sys.zlist, rvdw, rve);
+    if (s->atm_work && s->atm_work_bytes >= d3::atm3_workspace_bytes<B>(p.sys.natoms, atm3_grid())) {
+      // every triple once: persistent CTAs, centre atoms from a counter
+      d3::AtmArgs3<B> r;
+      r.a = q;
+      const int grid = atm3_grid();
+      char* wsp = reinterpret_cast<char*>(s->atm_work);
+      r.counter = reinterpret_cast<int*>(wsp);
+      r.rec = reinterpret_cast<B*>(wsp + 256);
+      r.list = reinterpret_cast<int*>(wsp + 256 + (size_t)grid * p.sys.natoms * d3::kAtm3Rec * sizeof(B));
+      cudaError_t e = cudaMemsetAsync(r.counter, 0, sizeof(int), st);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+      if (want_grad) d3::system_atm3_kernel<B, true><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
+      else d3::system_atm3_kernel<B, false><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
+      return launched("system_atm3_kernel");
+    }
     const size_t smem = d3::atm2_smem_bytes<B>(q.nelem);
     if (want_grad) {
       auto kern = d3::system_atm2_kernel<B, true>;
@@ -559,6 +586,8 @@ D3_STAGE_API(f64, double)
 D3_STAGE_API(f32, float)
 #undef D3_STAGE_API
 
+size_t d3b200_system_atm_workspace_bytes_f64(int natoms) { return natoms > 0 ? d3::atm3_workspace_bytes<double>(natoms, atm3_grid()) : 0; }
+size_t d3b200_system_atm_workspace_bytes_f32(int natoms) { return natoms > 0 ? d3::atm3_workspace_bytes<float>(natoms, atm3_grid()) : 0; }
 int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, const double* r, int g, void* st) { return sys_atm<double>(s, p, r, g, st); }
 int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int g, void* st) { return sys_atm<float>(s, p, r, g, st); }
 int d3b200_system_tvec_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_tvec<double>(s, p, st); }

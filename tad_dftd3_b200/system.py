@@ -254,6 +254,11 @@ class SystemRunner:
             return
         if self.rvdw is None:
             raise ValueError("the ATM term needs the [104,104] rvdw table")
+        if self.use_tvec and self.sys.atm_work is None and os.environ.get("TAD_DFTD3_B200_ATM2") != "1":
+            # scratch of the triples-once kernel (per-CTA neighbour lists and records)
+            nbytes = int(getattr(_lib.lib(), f"d3b200_system_atm_workspace_bytes_{self.sfx}")(self.plan.npad))
+            self._atm_work = torch.empty(nbytes, dtype=torch.uint8, device=self.plan.device)
+            self.sys.atm_work, self.sys.atm_work_bytes = self._atm_work.data_ptr(), nbytes
         self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), int(want_grad))
 
     # single-GPU drivers -----------------------------------------------------

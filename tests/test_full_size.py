@@ -211,5 +211,13 @@ def test_c5a_atm_10k_atoms_properties(ref):
         e4, g4 = run(numbers[:1500], positions[:1500], ref, par, **kw)
         assert_close(e3.cpu(), e4.cpu(), 1e-11, 1e-15, "general vs T-vector ATM energies")
         assert_close(g3.cpu(), g4.cpu(), 1e-9, 1e-14, "general vs T-vector ATM gradients")
+        # triples-once kernel (default) against the edge-owner T-vector kernel on the full cluster
+        os.environ["TAD_DFTD3_B200_ATM2"] = "1"
+        try:
+            e5, g5 = run(numbers, positions, ref, par, **kw)
+        finally:
+            del os.environ["TAD_DFTD3_B200_ATM2"]
+        assert_close(e5.cpu(), e.cpu(), 1e-10, 1e-14, "edge-owner vs triples-once ATM energies")
+        assert_close(g5.cpu(), g.cpu(), 1e-8, 1e-13, "edge-owner vs triples-once ATM gradients")
     finally:
         d3.data.set_vdw_pairwise(None)
