@@ -687,7 +687,7 @@ def run_c5a(args, rank, local, world, dev):
                    "whole_step_ms": ms_all, "total_energy": float(energy.sum())},
         "gpu_launches": 5 * (args.steps + args.warmup),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "d3::system_atm_kernel<double, true>",
+                     "traffic": None, "kernel": "d3::system_atm3_kernel<double, true> (every triple once)",
                      "flops_model": "140 per unordered triple (SURVEY.md 8d)"},
         "clocks": clocks.summary(),
     }

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libd3b200.so")
+# TAD_DFTD3_B200_LIB points at another build of the same library (kernel experiments)
+LIB_PATH = os.environ.get("TAD_DFTD3_B200_LIB") or os.path.join(HERE, "libd3b200.so")
 
 ABI_VERSION = 1
 

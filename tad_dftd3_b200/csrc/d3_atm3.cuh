@@ -15,8 +15,9 @@
 //  * persistent CTAs take centres i from a global counter (a launch owns the
 //    centres row_begin..row_end-1, which is also how ranks shard the term);
 //  * the CTA compacts the neighbours of i (r <= c), in index order, into its own
-//    list in global scratch, with one record per neighbour n:
-//    {sqrt|C6_in|, r_in^2, 1/r_in^2, (dC6_in/dCN_i)/C6_in, (dC6_in/dCN_n)/C6_in};
+//    list in global scratch, with one self-contained record per neighbour n:
+//    {x, y, z, (index, element)}, {sqrt|C6_in|, r_in^2, 1/r_in^2, (dC6_in/dCN_i)/C6_in,
+//    (dC6_in/dCN_n)/C6_in, R_in, g_n}, so the sweeps read one contiguous stream;
 //  * warps take 32-entry tiles of the list (largest first): lane <-> k, and walk
 //    all list positions j before k (j is warp-uniform).  Everything that belongs
 //    to k or to edge ik accumulates in registers over the j loop; the j-side sums
@@ -30,9 +31,13 @@
 
 namespace d3 {
 
-constexpr int kAtm3Warps = 8;
-constexpr int kAtm3Ctas = 2;         // resident CTAs per SM the kernel is built for
-constexpr int kAtm3Rec = 6;          // reals per neighbour record (5 used)
+#ifndef D3_ATM3_WARPS
+#define D3_ATM3_WARPS 8
+#define D3_ATM3_CTAS 2
+#endif
+constexpr int kAtm3Warps = D3_ATM3_WARPS;
+constexpr int kAtm3Ctas = D3_ATM3_CTAS;         // resident CTAs per SM the kernel is built for
+constexpr int kAtm3Rec = 12;         // reals per neighbour record (11 used), 16-byte aligned pairs
 constexpr int kAtm3RedStride = 40;   // row stride of the reduction tile (rows 16 banks apart)
 
 template <typename S>
@@ -74,6 +79,30 @@ __device__ __forceinline__ S warp_rows_reduce(const S (&vals)[V], S* tile, int l
 __device__ __forceinline__ float bcast(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// bit casts for the (index, element) slots of a record (moved, never computed with)
+__device__ __forceinline__ float int_as(int v, float) { return __int_as_float(v); }
+__device__ __forceinline__ double int_as(int v, double) { return __hiloint2double(0, v); }
+__device__ __forceinline__ int as_int(float v) { return __float_as_int(v); }
+__device__ __forceinline__ int as_int(double v) { return __double2loint(v); }
+
+// x^(16/3), x > 0: x^(-1/3) from two MUFU approximations, one cubic step, then (x y^2)^16
+template <typename S>
+__device__ __forceinline__ S pow16_3_fast(S x) {
+  float l, yf;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"((float)x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(-0.33333334f * l));
+  S y = S(yf);
+  const S y3 = y * y * y;
+  const S e = S(1) - x * y3;
+  y = y + (y * e) * (S(1.0 / 3.0) + S(2.0 / 9.0) * e);
+  const S c = x * (y * y);          // x^(1/3)
+  const S c2 = c * c, c4 = c2 * c2, c8 = c4 * c4;
+  return c8 * c8;
+}
+
+// record slots
+enum { kRx = 0, kRy, kRz, kRidx, kRh, kRr2, kRinv, kRci, kRcn, kRvdw, kRg, kRe };
+
 template <typename S, bool WANT_G>
 __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel(AtmArgs3<S> Q) {
   const AtmArgs2<S>& P = Q.a;
@@ -83,6 +112,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
   __shared__ S rv[kAtmEmax * kAtmEmax];
   __shared__ __align__(16) S wiS[16];
   __shared__ __align__(16) S red[nw * 7 * kAtm3RedStride];
+  __shared__ S wsh[nw][2 * kNRef][32];              // w_k, dw_k of each warp's tile, [a][lane]
   __shared__ S isum[nw][5];
   __shared__ int cnt[nw];
   __shared__ int s_center, s_tile;
@@ -95,7 +125,8 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
   int* list = Q.list + (size_t)blockIdx.x * natoms;
   S* rec = Q.rec + (size_t)blockIdx.x * natoms * kAtm3Rec;
   S* redw = red + wid * 7 * kAtm3RedStride;
-  const S* tdvec = P.tvec + (size_t)natoms * E * 8;
+  const S* __restrict__ tvec = P.tvec;
+  const unsigned tdoff = (unsigned)natoms * E * 8;  // Td vectors sit right behind the T vectors
   const S sixth = S(1) / S(6), two6 = S(2) * sixth, half6 = S(0.5) * sixth;
   const S rs93 = P.rs9 * P.rs9 * P.rs9;
   const S tiny = tiny_of<S>();
@@ -138,26 +169,27 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       n += tot;
       __syncthreads();
     }
-    // ---- one record per neighbour (edge i-n constants)
+    // ---- one record per neighbour: its own data and the constants of edge i-n
     for (int p = tid; p < n; p += blockDim.x) {
       const int nn = list[p];
       const Atom4<S> an = A.atoms[nn];
       const S dx = ai.x - an.x, dy = ai.y - an.y, dz = ai.z - an.z;
       const S r2 = dx * dx + dy * dy + dz * dz + tiny;
       const int en = P.eidx[nn];
-      const S* Tn = P.tvec + ((size_t)nn * E + ei) * 8;     // sum_b K[Zi,Zn,a,b] w_nb
-      const S* Tdn = tdvec + ((size_t)nn * E + ei) * 8;     // ... with dw_n
+      const S* Tn = tvec + ((size_t)nn * E + ei) * 8;      // sum_b K[Zi,Zn,a,b] w_nb
+      const S* Tdn = Tn + tdoff;                           // ... with dw_n
       S c6 = S(0), d_i = S(0), d_n = S(0);
 #pragma unroll
       for (int a = 0; a < kNRef; ++a) { c6 += wiS[a] * Tn[a]; d_i += wiS[8 + a] * Tn[a]; d_n += wiS[a] * Tdn[a]; }
       const S ic6 = frcp(c6);
-      S* r = rec + (size_t)p * kAtm3Rec;
-      r[0] = sqr(ab(c6) + tiny);
-      r[1] = r2;
-      r[2] = frcp(r2);
-      r[3] = d_i * ic6;
-      r[4] = d_n * ic6;
-      r[5] = rv[ei * E + en];
+      Pair2<S>* r = reinterpret_cast<Pair2<S>*>(rec + (size_t)p * kAtm3Rec);
+      Pair2<S> q;
+      q.a = an.x; q.b = an.y; r[0] = q;
+      q.a = an.z; q.b = int_as(nn, S(0)); r[1] = q;
+      q.a = sqr(ab(c6) + tiny); q.b = r2; r[2] = q;
+      q.a = frcp(r2); q.b = d_i * ic6; r[3] = q;
+      q.a = d_n * ic6; q.b = rv[ei * E + en]; r[4] = q;
+      q.a = A.aux[nn].b; q.b = int_as(en, S(0)); r[5] = q;
     }
     if (tid == 0) s_tile = (n + 31) / 32 - 1;
     __syncthreads();
@@ -172,48 +204,58 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       if (t < 0) break;
       const int kpos = 32 * t + lane;
       const bool kvalid = kpos < n;
-      const int kp = kvalid ? kpos : 32 * t;
-      const int kidx = list[kp];
-      const Atom4<S> ak = A.atoms[kidx];
-      const int ek = P.eidx[kidx];
-      const S gk = A.aux[kidx].b;
-      S wk[kNRef], dwk[kNRef];
+      const Pair2<S>* rk = reinterpret_cast<const Pair2<S>*>(rec + (size_t)(kvalid ? kpos : 32 * t) * kAtm3Rec);
+      const Pair2<S> k0_ = rk[0], k2_ = rk[2];
+      const S akx = k0_.a, aky = k0_.b, akz = rk[1].a;
+      const S hik = k2_.a, b2 = k2_.b, inv_b = rk[3].a, Rik = rk[4].b, gk = rk[5].a;
+      unsigned ekoff;
+      const S* rvk;
+      {
+        const int kidx = as_int(rk[1].b), ek = as_int(rk[5].b);
+        __syncwarp();
 #pragma unroll
-      for (int a = 0; a < kNRef; ++a) { wk[a] = A.w[8 * (size_t)kidx + a]; dwk[a] = WANT_G ? A.dw[8 * (size_t)kidx + a] : S(0); }
-      const S* rk = rec + (size_t)kp * kAtm3Rec;
-      const S hik = rk[0], b2 = rk[1], inv_b = rk[2], Rik = rk[5];
+        for (int a = 0; a < kNRef; ++a) {
+          wsh[wid][a][lane] = A.w[8 * (size_t)kidx + a];
+          if (WANT_G) wsh[wid][kNRef + a][lane] = A.dw[8 * (size_t)kidx + a];
+        }
+        __syncwarp();
+        ekoff = (unsigned)ek * 8;
+        rvk = rv + ek;
+      }
       S Sfb = S(0), Swe = S(0), Ek = S(0), Vx = S(0), Vy = S(0), Vz = S(0), Dk = S(0);
       const int jend = min(32 * t + 31, n - 1);        // positions j < k only
-      for (int jpos = 0; jpos < jend; ++jpos) {
-        const int jidx = list[jpos];                   // warp-uniform
-        const Atom4<S> aj = A.atoms[jidx];
-        const S dxjk = aj.x - ak.x, dyjk = aj.y - ak.y, dzjk = aj.z - ak.z;
+      const Pair2<S>* rj = reinterpret_cast<const Pair2<S>*>(rec);
+      for (int jpos = 0; jpos < jend; ++jpos, rj += kAtm3Rec / 2) {
+        const Pair2<S> j0_ = rj[0], j1_ = rj[1];         // warp-uniform loads
+        const S dxjk = j0_.a - akx, dyjk = j0_.b - aky, dzjk = j1_.a - akz;
         const S c2e = dxjk * dxjk + dyjk * dyjk + dzjk * dzjk;
         const bool mjk = c2e <= cutoff2;
+        const int jidx = as_int(j1_.b);
         // a triangle belongs to its smallest index: i < j (< k, the list is sorted)
         const bool act = kvalid && kpos > jpos && (!mjk || jidx > i);
         if (!__any_sync(0xffffffffu, act)) continue;
-        const S* rj = rec + (size_t)jpos * kAtm3Rec;
-        const S hij = rj[0], a2 = rj[1], inv_a = rj[2];
-        const int ej = P.eidx[jidx];
-        const S gj = A.aux[jidx].b;
+        const Pair2<S> j2_ = rj[2], j3_ = rj[3], j4_ = rj[4], j5_ = rj[5];
+        const S hij = j2_.a, a2 = j2_.b, inv_a = j3_.a;
+        const int ej = as_int(j5_.b);
         S vals[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) vals[v] = S(0);
         if (act) {
-          const Pair2<S>* Tj2 = reinterpret_cast<const Pair2<S>*>(P.tvec + ((size_t)jidx * E + ek) * 8);
+          const S* Tjp = tvec + ((unsigned)jidx * (unsigned)E * 8u + ekoff);
+          const Pair2<S>* Tj2 = reinterpret_cast<const Pair2<S>*>(Tjp);
           S Tj[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) { const Pair2<S> pp = Tj2[q]; Tj[2 * q] = pp.a; Tj[2 * q + 1] = pp.b; }
-          S c6jk = wk[0] * Tj[0];
+          S c6jk = wsh[wid][0][lane] * Tj[0];
 #pragma unroll
-          for (int a = 1; a < kNRef; ++a) c6jk += wk[a] * Tj[a];
+          for (int a = 1; a < kNRef; ++a) c6jk += wsh[wid][a][lane] * Tj[a];
           const S xjk = ab(c6jk) + tiny;
           const S hjk = xjk * frsq(xjk);
           const S c9 = P.s9 * (hij * (hik * hjk));
-          const S r0 = (rs93 * rj[5]) * (Rik * rv[ej * E + ek]);
+          const S r0 = (rs93 * j4_.b) * (Rik * rvk[ej * E]);
           const S c2 = c2e + tiny;
-          const S r2 = a2 * b2 * c2;
+          const S ab2 = a2 * b2;
+          const S r2 = ab2 * c2;
           const S r1inv = frsq(r2);
           const S r1inv2 = r1inv * r1inv;
           const S r3inv = r1inv2 * r1inv;
@@ -223,7 +265,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
           const S sr5 = s * r5inv;
           const S ang = S(0.375) * sr5 + r3inv;
           const S base = r0 * r1inv;
-          const S u = P.cube_root_pow ? pow16_3<S>(base) : fex(fmx(P.pexp * lg(base), S(-700)));
+          const S u = P.cube_root_pow ? pow16_3_fast<S>(base) : fex(fmx(P.pexp * lg(base), S(-700)));
           const S fd = frcp(S(1) + S(6) * u);
           const S e = c9 * (ang * fd);
           const S share = mjk ? S(2) : S(1);           // 1 + m_jk
@@ -237,8 +279,8 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
             const S k0 = c9 * fd, k1 = c9 * (ang * dfd0);
             const S common = k1 - k0 * (S(0.9375) * sr5 + S(1.5) * r3inv);
             const S k0r5 = S(0.375) * (k0 * r5inv);
-            const S inv_c = r1inv2 * (a2 * b2);
-            const S w6 = (mjk ? gi + gi : S(0)) + (gj + gk) * share;
+            const S inv_c = r1inv2 * ab2;
+            const S w6 = (mjk ? gi + gi : S(0)) + (j5_.a + gk) * share;
             const S we = w6 * e;
             const S fa = w6 * (k0r5 * (qt + pt - pq) + common * inv_a);
             const S fb = w6 * (k0r5 * (pt + pq - qt) + common * inv_b);
@@ -247,13 +289,13 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
             Swe += we;
             const S vx = fc * dxjk, vy = fc * dyjk, vz = fc * dzjk;
             Vx += vx; Vy += vy; Vz += vz;
-            const Pair2<S>* Td2 = reinterpret_cast<const Pair2<S>*>(tdvec + ((size_t)jidx * E + ek) * 8);
+            const Pair2<S>* Td2 = reinterpret_cast<const Pair2<S>*>(Tjp + tdoff);
             S Td[8];
 #pragma unroll
             for (int q2 = 0; q2 < 4; ++q2) { const Pair2<S> pp = Td2[q2]; Td[2 * q2] = pp.a; Td[2 * q2 + 1] = pp.b; }
-            S dk = dwk[0] * Tj[0], dj = wk[0] * Td[0];
+            S dk = wsh[wid][kNRef][lane] * Tj[0], dj = wsh[wid][0][lane] * Td[0];
 #pragma unroll
-            for (int a = 1; a < kNRef; ++a) { dk += dwk[a] * Tj[a]; dj += wk[a] * Td[a]; }
+            for (int a = 1; a < kNRef; ++a) { dk += wsh[wid][kNRef + a][lane] * Tj[a]; dj += wsh[wid][a][lane] * Td[a]; }
             const S qc = we * frcp(c6jk);
             Dk += qc * dk;
             vals[1 % NV] = fa; vals[2 % NV] = we; vals[3 % NV] = vx; vals[4 % NV] = vy; vals[5 % NV] = vz;
@@ -263,31 +305,35 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
         // ---- j side of this step: sums over the 32 lanes, five atomics
         const S tot = warp_rows_reduce<NV, S>(vals, redw, lane);
         const S EJ = bcast(tot, 0);
-        S out = sixth * EJ;
-        S* addr = A.energy + jidx;
         if (WANT_G) {
-          const S FA = bcast(tot, 4), WE = bcast(tot, 8), VX = bcast(tot, 12), VY = bcast(tot, 16),
-                  VZ = bcast(tot, 20), DJ = bcast(tot, 24);
-          const S dxij = ai.x - aj.x, dyij = ai.y - aj.y, dzij = ai.z - aj.z;
-          if (lane == 0) { Gix += FA * dxij; Giy += FA * dyij; Giz += FA * dzij; Di += WE * rj[3]; }
-          if (lane == 1) { out = two6 * (VX - FA * dxij); addr = A.grad + 3 * (size_t)jidx; }
-          if (lane == 2) { out = two6 * (VY - FA * dyij); addr = A.grad + 3 * (size_t)jidx + 1; }
-          if (lane == 3) { out = two6 * (VZ - FA * dzij); addr = A.grad + 3 * (size_t)jidx + 2; }
-          if (lane == 4) { out = half6 * (WE * rj[4] + DJ); addr = A.decn + jidx; }
+          const S FA = bcast(tot, 4), WE = bcast(tot, 8), DJ = bcast(tot, 24);
+          // lanes 1..3 fetch V_x, V_y, V_z (rows 3..5); branch-free selects
+          const S VC = bcast(tot, 4 * (2 + (lane & 3)));
+          const S dxij = ai.x - j0_.a, dyij = ai.y - j0_.b, dzij = ai.z - j1_.a;
+          const S dc = lane == 1 ? dxij : (lane == 2 ? dyij : dzij);
+          const S gv = two6 * (VC - FA * dc);
+          const S dv_ = half6 * (WE * j4_.a + DJ);
+          const S out = lane == 0 ? sixth * EJ : (lane == 4 ? dv_ : gv);
+          S* addr = lane == 0 ? A.energy + jidx : (lane == 4 ? A.decn + jidx : A.grad + 3 * (size_t)jidx + (lane - 1));
+          if (lane == 0) { Gix += FA * dxij; Giy += FA * dyij; Giz += FA * dzij; Di += WE * j3_.b; }
+          if (lane < 5) red_add(addr, out);
+        } else {
+          if (lane == 0) red_add(A.energy + jidx, sixth * EJ);
         }
-        if (lane < (WANT_G ? 5 : 1)) red_add(addr, out);
       }
       // ---- k side of the tile
       if (kvalid) {
+        const int kidx = as_int(rk[1].b);
         red_add(A.energy + kidx, sixth * Ek);
         if (WANT_G) {
-          const S dxik = ai.x - ak.x, dyik = ai.y - ak.y, dzik = ai.z - ak.z;
+          const S cki = rk[3].b, ckk = rk[4].a;
+          const S dxik = ai.x - akx, dyik = ai.y - aky, dzik = ai.z - akz;
           red_add(A.grad + 3 * (size_t)kidx, -two6 * (Sfb * dxik + Vx));
           red_add(A.grad + 3 * (size_t)kidx + 1, -two6 * (Sfb * dyik + Vy));
           red_add(A.grad + 3 * (size_t)kidx + 2, -two6 * (Sfb * dzik + Vz));
-          red_add(A.decn + kidx, half6 * (Swe * rk[4] + Dk));
+          red_add(A.decn + kidx, half6 * (Swe * ckk + Dk));
           Gix += Sfb * dxik; Giy += Sfb * dyik; Giz += Sfb * dzik;
-          Di += Swe * rk[3];
+          Di += Swe * cki;
         }
       }
     }
