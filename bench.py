@@ -273,6 +273,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import tad_dftd3_b200 as d3
@@ -284,6 +285,8 @@ def main():
     dt = torch.double if args.dtype == "f64" else torch.float32
     if args.workload == "c5a":
         run_c5a(args, rank, local, world, dev)
+        if world > 1:
+            dist.destroy_process_group()
         return
     if args.workload == "c5b":
         run_c5b(args, rank, local, world, dev)
@@ -632,15 +635,17 @@ def count_triples(positions, cutoff):
 
 
 def run_c5a(args, rank, local, world, dev):
-    """BASELINE config 5a: ATM three-body term on a 10k-atom water cluster with a triple cutoff."""
+    """BASELINE config 5a: ATM three-body term on a 10k-atom water cluster with a triple cutoff.
+    One step = the whole dftd3() evaluation with s9 = 1 (CN, weights, two-body sweep, three-body
+    sweep, CN-backward), centres of the three-body term sharded over the GPUs."""
+    import torch.distributed as dist
+
     import tad_dftd3_b200 as d3
-    from tad_dftd3_b200 import _lib
-    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200 import _lib, synthetic as syn
     from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+    from tad_dftd3_b200.distributed import run_sharded
     from tad_dftd3_b200.system import SystemPlan, SystemRunner
 
-    if rank != 0:
-        return
     dt = torch.double
     lib = _lib.lib()
     stream = torch.cuda.current_stream(dev)
@@ -657,41 +662,66 @@ def run_c5a(args, rank, local, world, dev):
     par.s9, par.rs9, par.alp = 1.0, 1.3333333730697632, 14.0
     par.cutoff, par.cn_cutoff, par.kcn = args.cutoff, 25.0, 16.0
     g = torch.ones(numbers.shape[0], dtype=dt, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
     t_atm, t_all = [], []
+    launches = 0
     with ClockSampler(local) as clocks:
         for it in range(args.warmup + args.steps):
+            barrier()
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            l0 = _lib.launch_count
             e0.record(stream)
             plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn)
-            run = SystemRunner(plan, refcn, refc6, par, g, 1, rvdw)
-            run.sweep_cn(); run.weights(); run.sweep_pair(True)
-            e1.record(stream)
-            run.sweep_atm(True)
-            e2.record(stream)
-            run.sweep_cnbwd()
+            run = SystemRunner(plan, refcn, refc6, par, g, world, rvdw)
+            atm = run.sweep_atm
+
+            def timed_atm(*a, _atm=atm):
+                e1.record(stream)
+                _atm(*a)
+                e2.record(stream)
+
+            run.sweep_atm = timed_atm
+            run_sharded(run, True)
             energy, grad = plan.scatter(run.energy), plan.scatter(run.grad)
             e3.record(stream)
-            torch.cuda.synchronize(dev)
+            barrier()
             if it >= args.warmup:
                 t_atm.append(e1.elapsed_time(e2)); t_all.append(e0.elapsed_time(e3))
-    ms_atm, ms_all = float(np.mean(t_atm)), float(np.mean(t_all))
+                launches += _lib.launch_count - l0
+    t = torch.tensor([float(np.mean(t_atm)), float(np.mean(t_all))], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_atm, ms_all = float(t[0]), float(t[1])
+    if rank != 0:
+        return
     peak = fp64_peak(lib, dev, stream)
     achieved = triples * 140.0 / (ms_atm * 1e-3) / 1e12
     line = {
-        "metric": "ATM energy+grad triples/s fp64", "value": triples / (ms_atm * 1e-3), "unit": "triples/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_atm,
+        "metric": "ATM energy+grad triples/s fp64", "value": triples / (ms_all * 1e-3), "unit": "triples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"c5a: ATM (s9=1) on a {numbers.shape[0]}-atom water cluster, triple cutoff {args.cutoff} Bohr, energy+grad fp64",
+        "config": {"workload": f"c5a: dftd3() with the ATM term (s9=1) on a {numbers.shape[0]}-atom water cluster, "
+                               f"cutoff {args.cutoff} Bohr, energy+grad fp64, centres sharded over the GPUs",
                    "triples": triples, "all_short_triangles": triangles, "short_edges": edges,
-                   "entry": "d3b200_system_atm_f64 (timed alone with CUDA events); whole dftd3 step in whole_step_ms",
-                   "whole_step_ms": ms_all, "total_energy": float(energy.sum())},
-        "gpu_launches": 5 * (args.steps + args.warmup),
-        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "d3::system_atm3_kernel<double, true> (every triple once)",
+                   "entry": "SystemPlan + d3b200_system_{cn,weights,tvec,pair,atm,cnbwd}_f64; value = triples / whole step "
+                            "(max over ranks, CUDA events); the three-body sweep alone in atm_ms",
+                   "atm_ms": ms_atm, "triples_per_s_atm_kernel": triples / (ms_atm * 1e-3),
+                   "total_energy": float(energy.sum()),
+                   "parallelism": f"centres of the three-body term and rows of the two-body sweeps over {world} GPU(s); "
+                                  "all-reduce of CN, dL/dCN, E, grad"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s",
+                     "frac": achieved / (peak * world), "traffic": None,
+                     "kernel": "d3::system_atm3_kernel<double, true> (every triple once), all ranks",
                      "flops_model": "140 per unordered triple (SURVEY.md 8d)"},
         "clocks": clocks.summary(),
     }
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:
         # the reference's ATM is dense N^3 (216 MB per temporary at N = 300): time a 300-atom sub-cluster
         torch.set_num_threads(os.cpu_count() or 1)
         centre = positions.mean(0)

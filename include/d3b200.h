@@ -297,9 +297,11 @@ int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* p
  * when the system struct carries them (after `_system_tvec_`).
  * With the T vectors AND `atm_work` (device scratch of at least
  * `d3b200_system_atm_workspace_bytes_*(natoms)` bytes, no initialisation needed)
- * every triple is evaluated once: persistent CTAs take centre atoms
- * row_begin..row_end-1 from a counter, compact the centre's neighbour list into
- * the scratch and walk the pairs of neighbours (see csrc/d3_atm3.cuh). */
+ * every triple is evaluated once: persistent CTAs take centre atoms from a
+ * counter, compact the centre's neighbour list into the scratch and walk the
+ * pairs of neighbours (see csrc/d3_atm3.cuh).  The launch owns the centres of
+ * the row tiles row_begin/128 + k*tile_stride below row_end (tile_stride <= 1:
+ * all tiles of the range), which is how ranks shard the term. */
 size_t d3b200_system_atm_workspace_bytes_f64(int natoms);
 size_t d3b200_system_atm_workspace_bytes_f32(int natoms);
 int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par,

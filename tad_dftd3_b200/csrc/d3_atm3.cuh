@@ -13,7 +13,8 @@
 //
 // Work decomposition
 //  * persistent CTAs take centres i from a global counter (a launch owns the
-//    centres row_begin..row_end-1, which is also how ranks shard the term);
+//    centres of the row tiles row_begin/128 + k * tile_stride below row_end, which
+//    is also how ranks shard the term: results are ADDED, so an all-reduce follows);
 //  * the CTA compacts the neighbours of i (r <= c), in index order, into its own
 //    list in global scratch, with one self-contained record per neighbour n:
 //    {x, y, z, (index, element)}, {sqrt|C6_in|, r_in^2, 1/r_in^2, (dC6_in/dCN_i)/C6_in,
@@ -46,6 +47,7 @@ struct AtmArgs3 {
   int* list;       // [gridDim.x][natoms]          neighbour indices of the CTA's current centre
   S* rec;          // [gridDim.x][natoms][kAtm3Rec] neighbour records
   int* counter;    // zero before the launch
+  int tile_stride; // the launch owns the row tiles row_begin/128 + k * tile_stride below row_end
 };
 
 template <typename S>
@@ -121,7 +123,9 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
   const int E = P.nelem;
   const int natoms = A.natoms;
   const int nsub = natoms / kSysSub;
-  const int nrows = A.row_end - A.row_begin;
+  const int tstride = Q.tile_stride > 0 ? Q.tile_stride : 1;
+  const int ntile_own = ((A.row_end - A.row_begin) / kSysTile + tstride - 1) / tstride;
+  const int nrows = ntile_own * kSysTile;
   int* list = Q.list + (size_t)blockIdx.x * natoms;
   S* rec = Q.rec + (size_t)blockIdx.x * natoms * kAtm3Rec;
   S* redw = red + wid * 7 * kAtm3RedStride;
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
     __syncthreads();
     const int c = s_center;
     if (c >= nrows) break;
-    const int i = A.row_begin + c;
+    const int i = A.row_begin + (c / kSysTile) * tstride * kSysTile + (c % kSysTile);
     const int ei = P.eidx[i];
     if (ei < 0) continue;                  // padding row (CTA-uniform)
     const Atom4<S> ai = A.atoms[i];

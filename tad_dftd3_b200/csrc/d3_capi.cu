@@ -496,6 +496,7 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       // every triple once: persistent CTAs, centre atoms from a counter
       d3::AtmArgs3<B> r;
       r.a = q;
+      r.tile_stride = s->tile_stride > 0 ? s->tile_stride : 1;
       const int grid = atm3_grid();
       char* wsp = reinterpret_cast<char*>(s->atm_work);
       r.counter = reinterpret_cast<int*>(wsp);
@@ -507,6 +508,7 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       else d3::system_atm3_kernel<B, false><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
       return launched("system_atm3_kernel");
     }
+    if (s->tile_stride > 1) return fail(D3B200_EINVAL, "strided ATM ownership needs atm_work (the triples-once kernel)%s");
     const size_t smem = d3::atm2_smem_bytes<B>(q.nelem);
     if (want_grad) {
       auto kern = d3::system_atm2_kernel<B, true>;
@@ -519,6 +521,7 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
     }
     return launched("system_atm2_kernel");
   }
+  if (s->tile_stride > 1) return fail(D3B200_EINVAL, "strided ATM ownership needs the T vectors and atm_work%s");
   if (want_grad) d3::system_atm_kernel<B, true><<<rows, 32 * d3::kAtmWarps, 0, st>>>(p);
   else d3::system_atm_kernel<B, false><<<rows, 32 * d3::kAtmWarps, 0, st>>>(p);
   return launched("system_atm_kernel");

@@ -12,6 +12,8 @@ exchange steps are the ones the data dependencies force:
     sweep_cn(rows)      -> all-gather CN            (N reals)
     weights()              per-atom, redundantly on every rank (cheaper than gathering w)
     sweep_pair(rows)    -> all-gather dL/dCN        (N reals)
+    sweep_atm(rows)        (s9 != 0) three-body term of the centres this rank owns, ADDED to
+                           E, dL/dx, dL/dCN of all three atoms -- summed by the same exchanges
     sweep_cnbwd(rows)   -> all-gather E, dL/dx      (4 N reals)
 
 The gathers are written as all-reduce(SUM) over arrays that are zero outside
@@ -59,6 +61,11 @@ def run_sharded(runner, want_grad: bool, group=None):
     _gather_rows(runner.cn, group)
     runner.weights()
     runner.sweep_pair(want_grad, rows)
+    atm = getattr(runner, "sweep_atm", None)
+    if atm is not None:
+        apart = getattr(runner, "atm_partition", None)
+        # adds to energy / grad / dL/dCN of every atom of a triple (no-op when s9 == 0)
+        atm(want_grad, apart(rank, world) if apart is not None else rows)
     if want_grad:
         _gather_rows(runner.decn, group)
         runner.sweep_cnbwd(rows)
@@ -69,37 +76,37 @@ def run_sharded(runner, want_grad: bool, group=None):
 
 class _ShardedD3(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, numbers, positions, rcov, r4r2, refcn, refc6, par, group, tables=(False, False)):
+    def forward(ctx, numbers, positions, rcov, r4r2, refcn, refc6, par, group, tables=(False, False), rvdw=None):
         plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn, *tables)
-        runner = SystemRunner(plan, refcn, refc6, par, None, _world(group)[1])
+        runner = SystemRunner(plan, refcn, refc6, par, None, _world(group)[1], rvdw)
         run_sharded(runner, False, group)
         ctx.save_for_backward(numbers, positions, rcov, r4r2, refcn, refc6)
-        ctx.par, ctx.group, ctx.tables = par, group, tables
+        ctx.par, ctx.group, ctx.tables, ctx.rvdw = par, group, tables, rvdw
         return plan.scatter(runner.energy)
 
     @staticmethod
     def backward(ctx, gE):
         numbers, positions, rcov, r4r2, refcn, refc6 = ctx.saved_tensors
         plan = SystemPlan(numbers, positions, rcov, r4r2, ctx.par.kcn, *ctx.tables)
-        runner = SystemRunner(plan, refcn, refc6, ctx.par, gE, _world(ctx.group)[1])
+        runner = SystemRunner(plan, refcn, refc6, ctx.par, gE, _world(ctx.group)[1], ctx.rvdw)
         run_sharded(runner, True, ctx.group)
-        return None, plan.scatter(runner.grad), None, None, None, None, None, None, None
+        return None, plan.scatter(runner.grad), None, None, None, None, None, None, None, None
 
 
 def dftd3_sharded(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, rcov=None,
                   r4r2=None, cutoff=None, group=None) -> Tensor:
     """
     `dftd3()` for one structure `(N,)`, rows sharded over the ranks of `group`
-    (two-body + CN; every rank passes the same inputs and receives the full
-    atom-resolved energy; `.backward()` gives the full gradient on every rank).
+    (two-body + CN, plus the ATM term when `param["s9"] != 0`; every rank passes
+    the same inputs and receives the full atom-resolved energy; `.backward()`
+    gives the full gradient on every rank).
     """
     from . import _lib, data
     from .disp import _check_numbers, _default_reference, _scalar
 
     if numbers.dim() != 1 or positions.shape != (numbers.shape[0], 3):
         raise ValueError("dftd3_sharded expects one structure: numbers (N,), positions (N, 3)")
-    if "s9" in param and bool(param["s9"] != 0.0):
-        raise NotImplementedError("the sharded path covers the two-body + CN terms")
+    atm = "s9" in param and bool(param["s9"] != 0.0)   # reference disp.py:234
     _check_numbers(numbers)
     dt, dev = positions.dtype, positions.device
     if ref is None:
@@ -117,7 +124,10 @@ def dftd3_sharded(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, 
     par.s8 = _scalar(param.get("s8", defaults.S8))
     par.a1 = _scalar(param.get("a1", defaults.A1))
     par.a2 = _scalar(param.get("a2", defaults.A2))
-    par.s9, par.rs9, par.alp = 0.0, defaults.RS9, defaults.ALP
+    par.s9 = _scalar(param["s9"]) if atm else 0.0
+    par.rs9 = float(torch.tensor(defaults.RS9))       # float32(4/3), reference disp.py:312
+    par.alp = _scalar(param.get("alp", defaults.ALP))
+    rvdw = _element_table("VDW_PAIRWISE", dt, dev) if atm else None
     par.cutoff = defaults.D3_DISP_CUTOFF if cutoff is None else _scalar(cutoff)
     par.cn_cutoff, par.kcn = defaults.D3_CN_CUTOFF, defaults.D3_KCN
-    return _ShardedD3.apply(numbers, positions, rcov, r4r2, refcn, refc6, par, group, tables)
+    return _ShardedD3.apply(numbers, positions, rcov, r4r2, refcn, refc6, par, group, tables, rvdw)

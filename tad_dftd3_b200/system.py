@@ -248,6 +248,16 @@ class SystemRunner:
     def sweep_cnbwd(self, rows=None):
         self._call("cnbwd", rows)
 
+    def atm_partition(self, rank: int, world: int):
+        """Centres of the three-body term this rank owns: every `world`-th row tile
+        starting at tile `rank` (interleaved, so surface and core tiles are spread
+        evenly); needs the triples-once kernel."""
+        if world <= 1 or not self.use_tvec or os.environ.get("TAD_DFTD3_B200_ATM2") == "1":
+            self._atm_stride = 1
+            return row_partition(self.plan.npad, world)[rank]
+        self._atm_stride = world
+        return (min(rank * TILE, self.plan.npad), self.plan.npad)
+
     def sweep_atm(self, want_grad: bool, rows=None):
         """Three-body term (adds to energy / grad / decn); no-op when s9 == 0."""
         if self.par.s9 == 0.0:
@@ -259,7 +269,12 @@ class SystemRunner:
             nbytes = int(getattr(_lib.lib(), f"d3b200_system_atm_workspace_bytes_{self.sfx}")(self.plan.npad))
             self._atm_work = torch.empty(nbytes, dtype=torch.uint8, device=self.plan.device)
             self.sys.atm_work, self.sys.atm_work_bytes = self._atm_work.data_ptr(), nbytes
-        self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), int(want_grad))
+        keep = self.sys.tile_stride
+        self.sys.tile_stride = getattr(self, "_atm_stride", 1)
+        try:
+            self._call("atm", rows, C.c_void_p(self.rvdw.data_ptr()), int(want_grad))
+        finally:
+            self.sys.tile_stride = keep
 
     # single-GPU drivers -----------------------------------------------------
     def run_energy(self) -> Tensor:

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class OracleRunner:
     """`SystemRunner` interface on CPU (rows of the full-row quantities)."""
 
-    def __init__(self, plan, refcn, refc6, par, g=None):
+    def __init__(self, plan, refcn, refc6, par, g=None, rvdw=None):
         import d3_oracle as orc
 
         self.orc, self.plan, self.par = orc, plan, par
@@ -33,7 +33,7 @@ class OracleRunner:
         self.rcov = plan.atoms[:, 3] / par.kcn
         self.q = plan.sqrtq ** 2
         self.g = plan.aux(g)[:, 1]
-        self.refcn, self.refc6 = refcn, refc6
+        self.refcn, self.refc6, self.rvdw = refcn, refc6, rvdw
         z = lambda *s: torch.zeros(*s, dtype=torch.double)  # noqa: E731
         self.cn, self.decn, self.energy, self.grad = z(n), z(n), z(n), z(n, 3)
         self.w = None
@@ -62,6 +62,28 @@ class OracleRunner:
             self.grad[sl] = gx[sl]
             self.decn[sl] = gcn[sl]
 
+    def sweep_atm(self, want_grad, rows):
+        """Three-body term of the atoms this rank owns.  Like the CUDA kernel it ADDS
+        to arrays that other ranks own as well (gradient and dL/dCN of every atom of
+        a triple), which is what the all-reduces of `run_sharded` have to get right."""
+        p = self.par
+        if p.s9 == 0.0:
+            return
+        real = torch.nonzero(self.z).reshape(-1)
+        z = self.z[real]
+        x = self.x[real].clone().requires_grad_(True)
+        cn = self.cn[real].clone().requires_grad_(True)
+        w = self.orc.weight_references(z, cn, self.refcn)
+        c6 = self.orc.atomic_c6(z, w, self.refc6)
+        rv = self.rvdw[z.unsqueeze(-1), z.unsqueeze(-2)]
+        e = self.orc.dispersion_atm(z, x, c6, rv, p.cutoff, p.s9, p.rs9, p.alp)
+        own = (real >= rows[0]) & (real < rows[1])
+        self.energy[real[own]] += e.detach()[own]
+        if want_grad and bool(own.any()):
+            gx, gcn = torch.autograd.grad((e * self.g[real])[own].sum(), (x, cn))
+            self.grad[real] += gx
+            self.decn[real] += gcn
+
     def sweep_cnbwd(self, rows):
         x = self.x.clone().requires_grad_(True)
         cn = self.orc.cn_d3(self.z, x, self.rcov)
@@ -75,7 +97,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, atm=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -87,15 +109,17 @@ def _worker(rank, world, port, out):
         from tad_dftd3_b200.system import SystemPlan, row_partition
 
         dt = torch.double
-        numbers, positions = syn.water_cluster(100, seed=4)       # 300 atoms -> 3 tiles of 128
+        # 300 atoms -> 3 tiles of 128; with the (dense N^3) three-body term 150 atoms -> 2 tiles
+        numbers, positions = syn.water_cluster(50 if atm else 100, seed=4)
         numbers = numbers.clone()
         numbers[[5, 17]] = 0                                       # ghost atoms
         par = _lib.Params()
         par.s6, par.s8, par.a1, par.a2 = 1.0, 0.78981345, 0.49484001, 5.73083694
-        par.cutoff, par.cn_cutoff, par.kcn = 30.0, 25.0, 16.0
+        par.cutoff, par.cn_cutoff, par.kcn = (12.0 if atm else 30.0), 25.0, 16.0
+        par.s9, par.rs9, par.alp = (1.0 if atm else 0.0), 1.3333333730697632, 14.0
         g = torch.linspace(0.5, 1.5, numbers.shape[0], dtype=dt)
         plan = SystemPlan(numbers, positions, COV_D3(dt)[numbers], R4R2(dt)[numbers], par.kcn)
-        runner = OracleRunner(plan, REFCN(dt), syn.synthetic_c6_table(dt), par, g)
+        runner = OracleRunner(plan, REFCN(dt), syn.synthetic_c6_table(dt), par, g, syn.synthetic_rvdw_table(dt))
         rows = run_sharded(runner, True)
         assert rows == row_partition(plan.npad, world)[rank]
         e, gr = plan.scatter(runner.energy), plan.scatter(runner.grad)
@@ -129,6 +153,40 @@ def test_sharded_two_ranks_matches_oracle(tmp_path):
     param = {"s6": 1.0, "s8": 0.78981345, "a1": 0.49484001, "a2": 5.73083694}
     e = orc.dftd3(numbers, pos, param, refcn=REFCN(dt), refc6=syn.synthetic_c6_table(dt),
                   rcov=COV_D3(dt)[numbers], r4r2=R4R2(dt)[numbers], cutoff=30.0)
+    (gr,) = torch.autograd.grad((e * g).sum(), pos)
+    np.testing.assert_allclose(res["energy"], e.detach().numpy(), rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(res["grad"], gr.numpy(), rtol=1e-10, atol=1e-13)
+    assert (res["energy"][[5, 17]] == 0).all()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_two_ranks_with_three_body_term(tmp_path):
+    """s9 != 0: each rank adds the three-body term of its own atoms into arrays the
+    other rank owns too; the exchanges of `run_sharded` must sum them (cutoff 12 Bohr
+    cuts triples partly, so the reference's ordered cutoff rule is exercised)."""
+    import d3_oracle as orc
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+
+    out = str(tmp_path / "res_atm.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out, True), nprocs=2, join=True)
+    res = np.load(out)
+    assert res["npad"] == 256 and tuple(res["rows"]) == (0, 128)
+
+    dt = torch.double
+    numbers, positions = syn.water_cluster(50, seed=4)
+    numbers = numbers.clone()
+    numbers[[5, 17]] = 0
+    g = torch.linspace(0.5, 1.5, numbers.shape[0], dtype=dt)
+    pos = positions.clone().requires_grad_(True)
+    param = {"s6": 1.0, "s8": 0.78981345, "a1": 0.49484001, "a2": 5.73083694, "s9": 1.0}
+    rvdw = syn.synthetic_rvdw_table(dt)
+    e = orc.dftd3(numbers, pos, param, refcn=REFCN(dt), refc6=syn.synthetic_c6_table(dt),
+                  rcov=COV_D3(dt)[numbers], r4r2=R4R2(dt)[numbers],
+                  rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)], cutoff=12.0)
+    e2 = orc.dftd3(numbers, pos, {k: v for k, v in param.items() if k != "s9"}, refcn=REFCN(dt),
+                   refc6=syn.synthetic_c6_table(dt), rcov=COV_D3(dt)[numbers], r4r2=R4R2(dt)[numbers], cutoff=12.0)
+    assert float((e - e2).abs().max()) > 1e-9          # the three-body term is really there
     (gr,) = torch.autograd.grad((e * g).sum(), pos)
     np.testing.assert_allclose(res["energy"], e.detach().numpy(), rtol=1e-11, atol=1e-14)
     np.testing.assert_allclose(res["grad"], gr.numpy(), rtol=1e-10, atol=1e-13)
