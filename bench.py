@@ -273,7 +273,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+        # NCCL prints its version banner (and warnings) to stdout: send them to a file so
+        # that stdout carries exactly the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/d3b200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     import tad_dftd3_b200 as d3
