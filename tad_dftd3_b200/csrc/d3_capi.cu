@@ -66,7 +66,7 @@ int launch_v2(const d3::MolArgs<B>& args, cudaStream_t stream) {
   const int N = args.natoms;
   const int threads = 32 * d3::v2_warps(N);
   const size_t smem = d3::molecule_v2_smem_bytes<B>(N);
-  auto kern = d3::molecule_kernel_v2<B, WANT_G>;
+  auto kern = args.r4r2_per_element ? d3::molecule_kernel_v2<B, WANT_G, true> : d3::molecule_kernel_v2<B, WANT_G, false>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");

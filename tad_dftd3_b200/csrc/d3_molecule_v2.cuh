@@ -91,7 +91,10 @@ template <int V> __device__ __forceinline__ int red_row(int lane) {
   return lane / Q;
 }
 
-template <typename S, bool WANT_G>
+// QE: r4r2 comes from the per-element table (the default `r4r2=None` of dftd3()), so
+// R0 = a1 sqrt(3 q_i q_j) + a2, R0^6, R0^8 and s8 * 3 q_i q_j depend on (row, partner
+// ELEMENT) only and are hoisted out of the partner loop next to the U contraction.
+template <typename S, bool WANT_G, bool QE>
 __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = A.natoms;
@@ -222,7 +225,12 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
 
   // ---------------------------------------------------------------- phase 1
   // CN_i = sum_j [r_ij <= 25] / (1 + exp(-kcn (rc_ij / r_ij - 1))), pairs once
-  constexpr int CNB = 4;
+#ifndef D3_V2_CNB
+#define D3_V2_CNB 4
+#define D3_V2_PB 2
+#define D3_V2_GB 3
+#endif
+  constexpr int CNB = D3_V2_CNB;
   D3_PIECES_BEGIN(4)
   {
     const Atom4<S> ai = sA[ic];
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
   __syncthreads();
 
   // ---------------------------------------------------------------- phase 3
-  constexpr int PB = 2;                     // partners per iteration and half-warp
+  constexpr int PB = D3_V2_PB;              // partners per iteration and half-warp
   constexpr int PV = WANT_G ? 5 : 1;        // j-side values per partner
   D3_PIECES_BEGIN(18)
   {
@@ -310,6 +318,16 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
           }
         }
       }
+      S r06g = S(0), r08g = S(0), s8qg = S(0);
+      if (QE) {
+        const S tq = s3qi * sB[gstart[grp]].a;     // sqrt(3 q_i q_g)
+        const S qq = tq * tq;
+        const S r0 = A.a1 * tq + A.a2;
+        const S r02 = r0 * r0;
+        r06g = r02 * r02 * r02;
+        r08g = r06g * r02;
+        s8qg = A.s8 * qq;
+      }
       for (int jb0 = jlo; jb0 < jhi; jb0 += 2 * PB) {
         S vals[PV * PB];
 #pragma unroll
@@ -329,19 +347,24 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
           S c6 = U[0] * wv[0];
 #pragma unroll
           for (int a = 1; a < kNRef; ++a) c6 += U[a] * wv[a];
-          S tq = s3qi * bj.a;               // sqrt(3 q_i q_j)
-          S qq = tq * tq;
-          S r0 = A.a1 * tq + A.a2;          // R0 = a1 sqrt(3 q_i q_j) + a2
-          S r02 = r0 * r0;
-          S r06 = r02 * r02 * r02;
-          S r08 = r06 * r02;
+          S r06, r08, s8q;
+          if (QE) {
+            r06 = r06g; r08 = r08g; s8q = s8qg;
+          } else {
+            S tq = s3qi * bj.a;             // sqrt(3 q_i q_j)
+            S qq = tq * tq;
+            S r0 = A.a1 * tq + A.a2;        // R0 = a1 sqrt(3 q_i q_j) + a2
+            S r02 = r0 * r0;
+            r06 = r02 * r02 * r02;
+            r08 = r06 * r02;
+            s8q = A.s8 * qq;
+          }
           S r4 = r2 * r2;
           S r6 = r4 * r2;
           S r8 = r4 * r4;
           S d6 = r6 + r06, d8 = r8 + r08;
           S inv = frcp(d6 * d8);
           S t6 = inv * d8, t8 = inv * d6;
-          S s8q = A.s8 * qq;
           S P = A.s6 * t6 + s8q * t8;
           S ep = ok ? c6 * P : S(0);
           vals[PV * s] = ep;
@@ -398,7 +421,7 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
 
   // ---------------------------------------------------------------- phase 4
   // CN chain: (dL/dCN_i + dL/dCN_j) df_ij/dx, df/dx_i = -kcn rc r^-3 f(1-f) (x_i - x_j)
-  constexpr int GB = 2;
+  constexpr int GB = D3_V2_GB;
   D3_PIECES_BEGIN(4)
   {
     const Atom4<S> ai = sA[ic];
