@@ -310,7 +310,7 @@ int d3b200_system_atm_f32(const d3b200_system_f32* sys, const d3b200_params* par
                           const float* rvdw, int want_grad, void* stream);
 
 /* ------------------------------------------------------------------------
- * Stage-level entry points (forward only): the reference's operator API keeps
+ * Stage-level entry points: the reference's operator API keeps
  * the intermediates as dense tensors (README.rst:238-261, test/test_disp/
  * test_disp.py feeds an external c6).  Padded-batch layout as above.
  *   _stage_cn      cn[B][N]          tad-mctc cn_d3 / exp_count (rcov per atom [B][N])
@@ -324,6 +324,19 @@ int d3b200_stage_weights_f64(size_t n, const int64_t* numbers, const double* cn,
                              double* weights, void* stream);
 int d3b200_stage_c6_f64(int nbatch, int natoms, const int64_t* numbers, const double* weights,
                         const double* refc6, double* c6, void* stream);
+/* Derivatives of `_stage_c6_` (the reference's hand-written AtomicC6 backward,
+ * model/c6.py:294-374).  C6 is bilinear in the weights, so two primitives close the
+ * chain to any order (tad_dftd3_b200/stages.py wires them into torch.autograd):
+ *   _stage_c6_bilinear  out[B][N][N]: out_ij = sum_ab u_ia K[Zi,Zj,a,b] w_jb
+ *   _stage_c6_contract  out[B][N][7]: out_ia = sum_j G_ij sum_b K[Zi,Zj,a,b] w_jb */
+int d3b200_stage_c6_bilinear_f64(int nbatch, int natoms, const int64_t* numbers, const double* u,
+                                 const double* w, const double* refc6, double* out, void* stream);
+int d3b200_stage_c6_contract_f64(int nbatch, int natoms, const int64_t* numbers, const double* G,
+                                 const double* w, const double* refc6, double* out, void* stream);
+int d3b200_stage_c6_bilinear_f32(int nbatch, int natoms, const int64_t* numbers, const float* u,
+                                 const float* w, const float* refc6, float* out, void* stream);
+int d3b200_stage_c6_contract_f32(int nbatch, int natoms, const int64_t* numbers, const float* G,
+                                 const float* w, const float* refc6, float* out, void* stream);
 int d3b200_stage_disp2_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
                            const double* c6, const double* r4r2, const d3b200_params* par,
                            double* energy, void* stream);

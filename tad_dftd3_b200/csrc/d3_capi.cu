@@ -552,6 +552,22 @@ int stage_c6(int nb, int n, const int64_t* z, const B* w, const B* refc6, B* c6,
   return launched("stage_c6_kernel");
 }
 template <typename B>
+int stage_c6_bilinear(int nb, int n, const int64_t* z, const B* u, const B* w, const B* refc6, B* out, void* st) {
+  if (nb < 0 || n < 0 || !z || !u || !w || !refc6 || !out) return fail(D3B200_EINVAL, "bad stage_c6_bilinear argument%s");
+  if (!nb || !n) return D3B200_OK;
+  if (nb > 65535 || n > 65535) return fail(D3B200_ESIZE, "stage_c6_bilinear: batch or structure too large%s");
+  d3::stage_c6_bilinear_kernel<B><<<dim3((n + 127) / 128, n, nb), 128, 0, (cudaStream_t)st>>>(n, z, u, w, refc6, out);
+  return launched("stage_c6_bilinear_kernel");
+}
+template <typename B>
+int stage_c6_contract(int nb, int n, const int64_t* z, const B* G, const B* w, const B* refc6, B* out, void* st) {
+  if (nb < 0 || n < 0 || !z || !G || !w || !refc6 || !out) return fail(D3B200_EINVAL, "bad stage_c6_contract argument%s");
+  if (!nb || !n) return D3B200_OK;
+  if (nb > 65535) return fail(D3B200_ESIZE, "stage_c6_contract: batch too large%s");
+  d3::stage_c6_contract_kernel<B><<<dim3((n + 63) / 64, nb), 64, 0, (cudaStream_t)st>>>(n, z, G, w, refc6, out);
+  return launched("stage_c6_contract_kernel");
+}
+template <typename B>
 int stage_disp2(int nb, int n, const int64_t* z, const B* x, const B* c6, const B* q, const d3b200_params* p, B* e, void* st) {
   if (nb < 0 || n < 0 || !z || !x || !c6 || !q || !p || !e) return fail(D3B200_EINVAL, "bad stage_disp2 argument%s");
   if (!nb || !n) return D3B200_OK;
@@ -581,6 +597,10 @@ extern "C" {
     return stage_weights<T>(n, z, cn, refcn, w, st); }                                                        \
   int d3b200_stage_c6_##SFX(int nb, int n, const int64_t* z, const T* w, const T* refc6, T* c6, void* st) {  \
     return stage_c6<T>(nb, n, z, w, refc6, c6, st); }                                                         \
+  int d3b200_stage_c6_bilinear_##SFX(int nb, int n, const int64_t* z, const T* u, const T* w, const T* refc6,   \
+                                     T* out, void* st) { return stage_c6_bilinear<T>(nb, n, z, u, w, refc6, out, st); } \
+  int d3b200_stage_c6_contract_##SFX(int nb, int n, const int64_t* z, const T* G, const T* w, const T* refc6,   \
+                                     T* out, void* st) { return stage_c6_contract<T>(nb, n, z, G, w, refc6, out, st); } \
   int d3b200_stage_disp2_##SFX(int nb, int n, const int64_t* z, const T* x, const T* c6, const T* q,         \
                                const d3b200_params* p, T* e, void* st) { return stage_disp2<T>(nb, n, z, x, c6, q, p, e, st); } \
   int d3b200_stage_atm_##SFX(int nb, int n, const int64_t* z, const T* x, const T* c6, const T* rvdw,        \

@@ -70,6 +70,66 @@ __global__ void stage_c6_kernel(int natoms, const int64_t* numbers, const S* w, 
   c6[(o + i) * natoms + j] = acc;
 }
 
+// Bilinear form behind atomic_c6 and its derivatives: out_ij = sum_ab u_ia K[Zi,Zj,a,b] w_jb
+// (atomic_c6 is u = w; the cotangent of `stage_c6_contract_kernel` is u = v).
+template <typename S>
+__global__ void stage_c6_bilinear_kernel(int natoms, const int64_t* numbers, const S* u, const S* w,
+                                         const S* refc6, S* out) {
+  const int b = blockIdx.z, i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= natoms) return;
+  const size_t o = (size_t)b * natoms;
+  int Zi = (int)numbers[o + i], Zj = (int)numbers[o + j];
+  if (Zi < 0 || Zi >= kMaxZ) Zi = 0;
+  if (Zj < 0 || Zj >= kMaxZ) Zj = 0;
+  const S* K = refc6 + ((size_t)Zi * kMaxZ + Zj) * (kNRef * kNRef);
+  const S* ui = u + (o + i) * kNRef;
+  const S* wj = w + (o + j) * kNRef;
+  S acc = S(0);
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) {
+    S t = S(0);
+#pragma unroll
+    for (int bb = 0; bb < kNRef; ++bb) t += K[a * kNRef + bb] * wj[bb];
+    acc += ui[a] * t;
+  }
+  out[(o + i) * natoms + j] = acc;
+}
+
+// Contraction behind the backward of atomic_c6 (reference model/c6.py:317-335, the
+// einsums "...ijab,...jb->...ija" and "...ij,...ija->...ia" in one pass):
+//   out_ia = sum_j G_ij sum_b K[Zi,Zj,a,b] w_jb          one thread per (structure, i)
+template <typename S>
+__global__ void stage_c6_contract_kernel(int natoms, const int64_t* numbers, const S* G, const S* w,
+                                         const S* refc6, S* out) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= natoms) return;
+  const size_t o = (size_t)b * natoms;
+  int Zi = (int)numbers[o + i];
+  if (Zi < 0 || Zi >= kMaxZ) Zi = 0;
+  S acc[kNRef];
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) acc[a] = S(0);
+  for (int j = 0; j < natoms; ++j) {
+    int Zj = (int)numbers[o + j];
+    if (Zj <= 0 || Zj >= kMaxZ) continue;
+    const S g = G[(o + i) * natoms + j];
+    const S* K = refc6 + ((size_t)Zi * kMaxZ + Zj) * (kNRef * kNRef);
+    const S* wj = w + (o + j) * kNRef;
+    S wv[kNRef];
+#pragma unroll
+    for (int bb = 0; bb < kNRef; ++bb) wv[bb] = wj[bb];
+#pragma unroll
+    for (int a = 0; a < kNRef; ++a) {
+      S t = S(0);
+#pragma unroll
+      for (int bb = 0; bb < kNRef; ++bb) t += K[a * kNRef + bb] * wv[bb];
+      acc[a] += g * t;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) out[(o + i) * kNRef + a] = Zi > 0 ? acc[a] : S(0);
+}
+
 template <typename S>
 __global__ void stage_disp2_kernel(int natoms, const int64_t* numbers, const S* pos, const S* c6,
                                    const S* r4r2, S s6, S s8, S a1, S a2, S cutoff2, S* energy) {

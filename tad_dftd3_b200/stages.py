@@ -6,9 +6,11 @@ its own CUDA kernel (`d3b200_stage_*`), with the reference's shapes, defaults
 and `ValueError`s (README.rst:238-261, disp.py:168-347, damping/atm.py:43-155).
 
 These keep the dense intermediates (`c6 [..., N, N]`) that the fused `dftd3()`
-path never materialises, and they are FORWARD ONLY: differentiable use goes
-through `dftd3()`, whose analytic derivatives cover the whole chain.  Inputs
-that require grad are rejected instead of being silently detached.
+path never materialises.  `atomic_c6` is differentiable with respect to the
+weights (the reference's custom AtomicC6 op, model/c6.py:294-480); the other
+stages are FORWARD ONLY: differentiable use goes through `dftd3()`, whose
+analytic derivatives cover the whole chain.  Inputs that require grad are
+rejected there instead of being silently detached.
 """
 from __future__ import annotations
 
@@ -116,21 +118,108 @@ def weight_references(numbers, cn, reference, weighting_function=None, **kwargs)
     return out.reshape(*numbers.shape, 7)
 
 
-def atomic_c6(numbers, weights, reference, chunk_size=None):
-    """Dense `[..., N, N]` C6 matrix.  `chunk_size` is accepted and ignored: the
-    kernel never builds the reference's `N x N x 7 x 7` gather."""
-    _cuda(weights, "weights")
-    _no_grad(weights)
-    dt, dev = weights.dtype, weights.device
-    _, refc6, _ = reference._prepared(dev, dt)
+def _c6_launch(name, numbers, a, b, refc6, out_shape):
+    """Common launcher of the two C6 primitives (any leading batch dimensions)."""
+    dt, dev = b.dtype, b.device
     n = numbers.shape[-1]
-    z = _z(numbers).reshape(-1, n)
-    w = weights.detach().reshape(-1, n, 7).contiguous()
-    out = torch.empty(z.shape[0], n, n, dtype=dt, device=dev)
-    fn = getattr(_lib.lib(), f"d3b200_stage_c6_{_sfx(dt)}")
+    z = _z(numbers).expand(*b.shape[:-2], n).reshape(-1, n).contiguous()
+    a2 = a.detach().to(dt).reshape(z.shape[0], n, -1).contiguous()
+    b2 = b.detach().reshape(z.shape[0], n, 7).contiguous()
+    out = torch.empty(z.shape[0], *out_shape(n), dtype=dt, device=dev)
+    fn = getattr(_lib.lib(), f"d3b200_stage_c6_{name}_{_sfx(dt)}")
     with torch.cuda.device(dev):
-        _lib.check(fn(z.shape[0], n, _p(z), _p(w), _p(refc6), _p(out), _stream(dev)))
-    return out.reshape(*numbers.shape, n)
+        _lib.check(fn(z.shape[0], n, _p(z), _p(a2), _p(b2), _p(refc6), _p(out), _stream(dev)))
+    return out.reshape(*b.shape[:-2], *out_shape(n))
+
+
+def _move_batch(info, in_dims, args, per_structure):
+    """vmap helper: batch dimension to the front (or expand) for the per-structure
+    tensors; like the reference's AtomicC6_V2.vmap (model/c6.py:436-480) the rule only
+    moves dimensions and re-dispatches through `apply`."""
+    out = []
+    for k, (a, d) in enumerate(zip(args, in_dims)):
+        if k in per_structure:
+            out.append(a.unsqueeze(0).expand(info.batch_size, *a.shape) if d is None else a.movedim(d, 0))
+        else:
+            if d is not None:
+                raise ValueError("Batch size mismatch: the reference C6 table must not be batched under vmap.")
+            out.append(a)
+    return out
+
+
+class _C6Bilinear(torch.autograd.Function):
+    """out_ij = sum_ab u_ia K[Zi,Zj,a,b] w_jb (K symmetric: K[zi,zj,a,b] = K[zj,zi,b,a])."""
+
+    generate_vmap_rule = False
+
+    @staticmethod
+    def forward(numbers, u, w, refc6):
+        return _c6_launch("bilinear", numbers, u, w, refc6, lambda n: (n, n))
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.save_for_backward(*inputs)
+
+    @staticmethod
+    def backward(ctx, g):
+        numbers, u, w, refc6 = ctx.saved_tensors
+        gu = _C6Contract.apply(numbers, g, w, refc6) if ctx.needs_input_grad[1] else None
+        gw = _C6Contract.apply(numbers, g.transpose(-1, -2), u, refc6) if ctx.needs_input_grad[2] else None
+        return None, gu, gw, None
+
+    @staticmethod
+    def vmap(info, in_dims, *args):
+        return _C6Bilinear.apply(*_move_batch(info, in_dims, args, (0, 1, 2))), 0
+
+
+class _C6Contract(torch.autograd.Function):
+    """out_ia = sum_j G_ij sum_b K[Zi,Zj,a,b] w_jb -- the reference's AtomicC6 backward
+    (model/c6.py:317-335) as one kernel."""
+
+    generate_vmap_rule = False
+
+    @staticmethod
+    def forward(numbers, G, w, refc6):
+        return _c6_launch("contract", numbers, G, w, refc6, lambda n: (n, 7))
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.save_for_backward(*inputs)
+
+    @staticmethod
+    def backward(ctx, v):
+        numbers, G, w, refc6 = ctx.saved_tensors
+        gG = _C6Bilinear.apply(numbers, v, w, refc6) if ctx.needs_input_grad[1] else None
+        gw = _C6Contract.apply(numbers, G.transpose(-1, -2), v, refc6) if ctx.needs_input_grad[2] else None
+        return None, gG, gw, None
+
+    @staticmethod
+    def vmap(info, in_dims, *args):
+        return _C6Contract.apply(*_move_batch(info, in_dims, args, (0, 1, 2))), 0
+
+
+def atomic_c6(numbers, weights, reference, chunk_size=None):
+    """Dense `[..., N, N]` C6 matrix (reference model/c6.py:42-96), differentiable with
+    respect to `weights` to any order on the CUDA kernels (the reference's
+    hand-written backward, model/c6.py:294-374).  `chunk_size` is accepted and
+    ignored: the kernels never build the reference's `N x N x 7 x 7` gather."""
+    _cuda(weights, "weights")
+    dt, dev = weights.dtype, weights.device
+    _, refc6, symmetric = reference._prepared(dev, dt)
+    needs_grad = weights.requires_grad and torch.is_grad_enabled()
+    f = torch._C._functorch
+    if not needs_grad and not (f.is_batchedtensor(weights) or f.is_gradtrackingtensor(weights)):
+        n = numbers.shape[-1]
+        z = _z(numbers).reshape(-1, n)
+        w = weights.detach().reshape(-1, n, 7).contiguous()
+        out = torch.empty(z.shape[0], n, n, dtype=dt, device=dev)
+        fn = getattr(_lib.lib(), f"d3b200_stage_c6_{_sfx(dt)}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(z.shape[0], n, _p(z), _p(w), _p(refc6), _p(out), _stream(dev)))
+        return out.reshape(*numbers.shape, n)
+    if not symmetric:
+        raise ValueError("reference C6 table must be symmetric: c6[z1,z2,a,b] == c6[z2,z1,b,a]")
+    return _C6Bilinear.apply(numbers, weights, weights, refc6)
 
 
 def _params(param: dict, cutoff, dt) -> _lib.Params:

@@ -366,6 +366,47 @@ def test_stage_functions_are_forward_only():
         assert d3.ncoord.cn_d3(numbers, pos).shape == (3,)
 
 
+def test_atomic_c6_is_differentiable_like_the_reference_op(runs):
+    """atomic_c6 w.r.t. the weights: VJP against autograd through the oracle's dense
+    einsum, gradcheck / gradgradcheck (reference test_c6.py:223-262) and vmap."""
+    import d3_oracle as orc
+    import tad_dftd3_b200 as d3
+
+    c = runs.case("c2_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    refcn, refc6, rcov, r4r2, _ = tables(dtype)
+    cn = orc.cn_d3(numbers, positions, rcov[numbers])
+    w0 = orc.weight_references(numbers, cn, refcn)
+    gen = torch.Generator().manual_seed(11)
+    gbar = torch.rand(*numbers.shape, numbers.shape[-1], generator=gen, dtype=dtype)
+
+    w_cpu = w0.clone().requires_grad_(True)
+    c6_cpu = orc.atomic_c6(numbers, w_cpu, refc6)
+    (wbar_cpu,) = torch.autograd.grad((c6_cpu * gbar).sum(), w_cpu)
+
+    ref = d3.Reference(cn=refcn.to(DEV), c6=refc6.to(DEV))
+    z = numbers.to(DEV)
+    w = w0.to(DEV).requires_grad_(True)
+    c6 = d3.model.atomic_c6(z, w, ref)
+    assert_close(c6.detach().cpu(), c6_cpu.detach(), 1e-12, 1e-14, "c6")
+    (wbar,) = torch.autograd.grad((c6 * gbar.to(DEV)).sum(), w)
+    assert_close(wbar.cpu(), wbar_cpu, 1e-11, 1e-13, "atomic_c6 VJP")
+
+    f = lambda ww: d3.model.atomic_c6(z, ww, ref)  # noqa: E731
+    w1 = w0.to(DEV).requires_grad_(True)
+    assert torch.autograd.gradcheck(f, (w1,), atol=1e-7, rtol=1e-6)
+    assert torch.autograd.gradgradcheck(f, (w1,), atol=1e-7, rtol=1e-6)
+
+    # vmap over the batch dimension gives the batched result
+    v = torch.func.vmap(lambda zz, ww: d3.model.atomic_c6(zz, ww, ref))(z, w0.to(DEV))
+    assert torch.equal(v, c6.detach())
+    # jacrev through the custom op (first row block only, to keep it small)
+    jac = torch.func.jacrev(lambda ww: d3.model.atomic_c6(z[0], ww, ref).sum(-1))(w0[0].to(DEV))
+    w2 = w0[0].clone().requires_grad_(True)
+    jac_cpu = torch.autograd.functional.jacobian(lambda ww: orc.atomic_c6(numbers[0], ww, refc6).sum(-1), w2)
+    assert_close(jac.cpu(), jac_cpu, 1e-11, 1e-13, "atomic_c6 jacobian")
+
+
 def test_repeated_transforms_do_not_leak_wrappers(runs):
     """Module-level caches must never keep functorch wrappers alive across calls
     (same Hessian twice, then a plain call, then a Hessian with other parameters)."""
