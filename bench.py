@@ -695,10 +695,37 @@ def run_c5a(args, rank, local, world, dev):
             if it >= args.warmup:
                 t_atm.append(e1.elapsed_time(e2)); t_all.append(e0.elapsed_time(e3))
                 launches += _lib.launch_count - l0
-    t = torch.tensor([float(np.mean(t_atm)), float(np.mean(t_all))], dtype=torch.double, device=dev)
+    # ---- end to end through the public API (dftd3_sharded == dftd3 at one GPU): pinned host
+    # numbers / positions in, pinned host energies + gradient out, every step
+    from tad_dftd3_b200.distributed import dftd3_sharded
+
+    d3.data.set_vdw_pairwise(rvdw)
+    num_h, pos_h = numbers.cpu().pin_memory(), positions.cpu().pin_memory()
+    e_h = torch.empty(numbers.shape[0], dtype=dt).pin_memory()
+    g_h = torch.empty(numbers.shape[0], 3, dtype=dt).pin_memory()
+    param = {k: torch.tensor(v, dtype=dt) for k, v in dict(PARAM, s9=1.0).items()}
+
+    def step_e2e():
+        z = num_h.to(dev, non_blocking=True)
+        x = pos_h.to(dev, non_blocking=True).requires_grad_(True)
+        e = dftd3_sharded(z, x, param, ref=ref, cutoff=torch.tensor(args.cutoff, dtype=dt))
+        (gx,) = torch.autograd.grad(e.sum(), x)
+        e_h.copy_(e.detach(), non_blocking=True)
+        g_h.copy_(gx, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_err = float((g_h.to(dev) - grad).abs().max())
+    t = torch.tensor([float(np.mean(t_atm)), float(np.mean(t_all)), e2e_ms], dtype=torch.double, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_atm, ms_all = float(t[0]), float(t[1])
+    ms_atm, ms_all, e2e_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         return
     peak = fp64_peak(lib, dev, stream)
@@ -717,6 +744,12 @@ def run_c5a(args, rank, local, world, dev):
                    "parallelism": f"centres of the three-body term and rows of the two-body sweeps over {world} GPU(s); "
                                   "all-reduce of CN, dL/dCN, E, grad"},
         "gpu_launches": launches,
+        "e2e": {"value": triples / (e2e_ms * 1e-3), "unit": "triples/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(num_h.numel() * 8 + pos_h.numel() * 8),
+                "d2h_bytes_per_step": int((e_h.numel() + g_h.numel()) * 8),
+                "api": "tad_dftd3_b200.distributed.dftd3_sharded() (= dftd3() at one GPU) + autograd.grad, pinned host "
+                       "buffers, plan (Morton / element sort) rebuilt every step",
+                "max_abs_grad_diff_vs_resident": e2e_err},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s",
                      "frac": achieved / (peak * world), "traffic": None,
                      "kernel": "d3::system_atm3_kernel<double, true> (every triple once), all ranks",
@@ -766,12 +799,35 @@ def run_c5b(args, rank, local, world, dev):
         if it >= args.warmup:
             times.append(time.perf_counter() - t0)
     sym = float((h.reshape(600, 600) - h.reshape(600, 600).T).abs().max())
+    # end to end: positions from pinned host memory, Hessian back into pinned host memory
+    from tad_dftd3_b200 import _lib
+
+    pos_h = positions.cpu().pin_memory()
+    h_h = torch.empty(200, 3, 200, 3, dtype=dt).pin_memory()
+    e2e, l0 = [], 0
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize(dev)
+        if it == args.warmup:
+            l0 = _lib.launch_count
+        t0 = time.perf_counter()
+        h_h.copy_(hess(pos_h.to(dev, non_blocking=True)), non_blocking=True)
+        torch.cuda.synchronize(dev)
+        if it >= args.warmup:
+            e2e.append(time.perf_counter() - t0)
+    launches = _lib.launch_count - l0
     line = {"metric": "Hessian (jacrev o jacrev) wall time, 200 atoms, two-body + CN, fp64", "value": float(np.mean(times)),
             "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "c5b: examples/hessian.py construction on one 200-atom chain-grown molecule",
                        "hessian_shape": list(h.shape), "max_asymmetry": sym,
-                       "reference_cpu_seconds_survey": 10.6}}
+                       "entry": "one d3b200_batch_energy_f64, one d3b200_batch_vjp_f64 and one d3b200_batch_hvp_f64 "
+                                "launch (cotangent batch of 600) per Hessian",
+                       "reference_cpu_seconds_survey": 10.6},
+            "e2e": {"value": float(np.mean(e2e)), "unit": "s", "h2d_bytes_per_step": int(pos_h.numel() * 8),
+                    "d2h_bytes_per_step": int(h_h.numel() * 8), "ms_per_step": float(np.mean(e2e)) * 1e3,
+                    "api": "torch.func.jacrev(jacrev(dftd3(...).sum)) on positions copied from pinned host memory, "
+                           "Hessian copied back to pinned host memory"},
+            "gpu_launches": launches}
     if not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         sec, kind = reference_single(numbers, positions, PARAM, hessian=True)

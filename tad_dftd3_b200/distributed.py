@@ -79,14 +79,21 @@ class _ShardedD3(torch.autograd.Function):
     def forward(ctx, numbers, positions, rcov, r4r2, refcn, refc6, par, group, tables=(False, False), rvdw=None):
         plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn, *tables)
         runner = SystemRunner(plan, refcn, refc6, par, None, _world(group)[1], rvdw)
-        run_sharded(runner, False, group)
+        # When the positions require grad the sweeps run with the gradient right away
+        # (unit cotangent): `energy.sum().backward()` is then one multiply, as in
+        # ops.D3Energy; any other cotangent repeats the sweeps in backward.
+        spec = bool(positions.requires_grad)
+        run_sharded(runner, spec, group)
         ctx.save_for_backward(numbers, positions, rcov, r4r2, refcn, refc6)
         ctx.par, ctx.group, ctx.tables, ctx.rvdw = par, group, tables, rvdw
+        ctx.grad1 = plan.scatter(runner.grad) if spec else None
         return plan.scatter(runner.energy)
 
     @staticmethod
     def backward(ctx, gE):
         numbers, positions, rcov, r4r2, refcn, refc6 = ctx.saved_tensors
+        if ctx.grad1 is not None and gE.numel() > 1 and all(s == 0 for s in gE.stride()):
+            return (None, ctx.grad1 * gE.reshape(-1)[0]) + (None,) * 8
         plan = SystemPlan(numbers, positions, rcov, r4r2, ctx.par.kcn, *ctx.tables)
         runner = SystemRunner(plan, refcn, refc6, ctx.par, gE, _world(ctx.group)[1], ctx.rvdw)
         run_sharded(runner, True, ctx.group)

@@ -136,7 +136,7 @@ class _Call:
         # ATM scratch (sqrt|C6| matrix per structure)
         self.work = None
         self.work_bytes = 0
-        if self.par.s9 != 0.0 and nflat and n:
+        if self.par.s9 != 0.0 and nflat and n and n <= _fused_limit(self.sfx, order):
             fn = getattr(_lib.lib(), f"d3b200_batch_workspace_bytes_{self.sfx}")
             self.work_bytes = int(fn(nflat, n, order, 1))
             self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=dev)
@@ -157,17 +157,22 @@ class _Call:
 _limits: dict = {}
 
 
+def _fused_limit(sfx: str, order: int) -> int:
+    """Largest structure the one-CTA-per-structure kernels take."""
+    key = (sfx, order)
+    limit = _limits.get(key)
+    if limit is None:
+        limit = _limits[key] = getattr(_lib.lib(), f"d3b200_batch_max_atoms_{sfx}")(order)
+    return limit
+
+
 def _tiled(c: "_Call", order: int) -> bool:
     """Structures beyond the one-CTA limit go to the tiled `d3b200_system_*` sweeps."""
     if not (c.nflat and c.n):
         return False
     if os.environ.get("TAD_DFTD3_B200_TILED") == "1":
         return True
-    key = (c.sfx, order)
-    limit = _limits.get(key)
-    if limit is None:
-        limit = _limits[key] = getattr(_lib.lib(), f"d3b200_batch_max_atoms_{c.sfx}")(order)
-    return c.n > limit
+    return c.n > _fused_limit(c.sfx, order)
 
 
 def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None):
@@ -338,9 +343,13 @@ class D3Energy(torch.autograd.Function):
         if (positions.requires_grad and not p.requires_grad and _SPECULATE
                 and not _is_functorch(positions)):
             pvals = _pvals(p)
+            c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0, pvals)
+            if c.nflat and c.n and _tiled(c, 0):
+                # large structures: the sweeps with gradient give the energies as well
+                e, gr = _tiled_run(c, None, True, numbers)
+                return e.reshape(*c.lead, c.n), gr.reshape(*c.lead, c.n, 3)
             if pvals[4] == 0.0:
-                c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0, pvals)
-                if c.nflat and c.n and not _tiled(c, 0):
+                if c.nflat and c.n:
                     energy, grad = c.new(c.nflat, c.n), c.new(c.nflat, c.n, 3)
                     fn = getattr(_lib.lib(), f"d3b200_batch_vjp_{c.sfx}")
                     with torch.cuda.device(c.device):

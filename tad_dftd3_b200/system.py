@@ -67,9 +67,17 @@ class _Static:
         z = numbers[idx]
         if n:
             o1 = morton_order(positions.detach()[idx])
-            tile = torch.arange(n, device=dev) // TILE
-            o2 = torch.argsort(tile * 128 + z[o1], stable=True)
-            order = o1[o2]
+            # With <= 8 distinct elements the sweeps read pre-contracted T vectors and do not
+            # care about the element order, so the tiles stay purely spatial (tighter 32-atom
+            # boxes, better culling).  Otherwise sort by element inside each 128-atom tile: the
+            # general pair kernel re-contracts the 7x7 block only when the partner element changes.
+            few = int(torch.unique(z).numel()) <= 8 and os.environ.get("TAD_DFTD3_B200_NO_TVEC") != "1"
+            if few and os.environ.get("TAD_DFTD3_B200_ELEMENT_SORT") != "1":
+                order = o1
+            else:
+                tile = torch.arange(n, device=dev) // TILE
+                o2 = torch.argsort(tile * 128 + z[o1], stable=True)
+                order = o1[o2]
         else:
             order = idx
         self.perm = idx[order]                      # sorted slot -> original atom index

@@ -205,7 +205,7 @@ def test_row_partition_is_tile_aligned_and_complete():
             assert all(a % 128 == 0 and b % 128 == 0 for a, b in parts)
 
 
-def test_plan_sorting_and_padding():
+def test_plan_sorting_and_padding(monkeypatch):
     from tad_dftd3_b200 import synthetic as syn
     from tad_dftd3_b200.data import COV_D3, R4R2
     from tad_dftd3_b200.system import SystemPlan
@@ -218,9 +218,14 @@ def test_plan_sorting_and_padding():
     assert plan.n == 179 and plan.npad == 256
     # permutation covers exactly the real atoms
     assert sorted(plan.perm.tolist()) == [i for i in range(180) if i != 3]
-    # elements are sorted inside each 128-atom tile
-    z = plan.z[: plan.n].reshape(-1).tolist()
+    # few elements (T-vector sweeps): purely spatial order; with the general pair kernel
+    # the elements are sorted inside each 128-atom tile
+    monkeypatch.setenv("TAD_DFTD3_B200_ELEMENT_SORT", "1")
+    numbers2 = numbers.clone()
+    plan2 = SystemPlan(numbers2, positions, COV_D3(dt)[numbers2], R4R2(dt)[numbers2], 16.0)
+    z = plan2.z[: plan2.n].reshape(-1).tolist()
     assert z[:128] == sorted(z[:128]) and z[128:] == sorted(z[128:])
+    assert sorted(plan2.perm.tolist()) == sorted(plan.perm.tolist())
     # boxes bound their real atoms; padding sits far away
     xyz = plan.atoms[:, :3].reshape(-1, 32, 3)
     for s in range(plan.npad // 32):
