@@ -15,7 +15,10 @@
 
 namespace d3 {
 
-constexpr int kSymChunk = 8;             // partners per transposed chunk
+#ifndef D3_SYM_CHUNK
+#define D3_SYM_CHUNK 8
+#endif
+constexpr int kSymChunk = D3_SYM_CHUNK;  // partners per transposed chunk
 constexpr int kSymParts = 32 / kSymChunk; // lanes sharing one partner column
 constexpr int kSymPitch = 33;            // 32 rows + 1: conflict-free column reads
 
