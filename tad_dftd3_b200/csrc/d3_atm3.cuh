@@ -19,8 +19,9 @@
 //    list in global scratch, with one self-contained record per neighbour n:
 //    {x, y, z, (index, element)}, {sqrt|C6_in|, r_in^2, 1/r_in^2, (dC6_in/dCN_i)/C6_in,
 //    (dC6_in/dCN_n)/C6_in, R_in, g_n}, so the sweeps read one contiguous stream;
-//  * warps take 32-entry tiles of the list (largest first): lane <-> k, and walk
-//    all list positions j before k (j is warp-uniform).  Everything that belongs
+//  * warps take tiles of 64 list entries (largest first): each lane owns two of them
+//    (two independent evaluation chains per step) and walks all list positions j
+//    before its k (j is warp-uniform).  Everything that belongs
 //    to k or to edge ik accumulates in registers over the j loop; the j-side sums
 //    of a step (7 values) go through a transposed shared-memory reduction and are
 //    added to the global arrays with five fp64 atomics per 32 triples; the i-side
@@ -33,9 +34,13 @@
 namespace d3 {
 
 #ifndef D3_ATM3_WARPS
-#define D3_ATM3_WARPS 8
-#define D3_ATM3_CTAS 2
+#define D3_ATM3_WARPS 4
+#define D3_ATM3_CTAS 3
 #endif
+#ifndef D3_ATM3_KPL
+#define D3_ATM3_KPL 2
+#endif
+constexpr int kAtm3Kpl = D3_ATM3_KPL;
 constexpr int kAtm3Warps = D3_ATM3_WARPS;
 constexpr int kAtm3Ctas = D3_ATM3_CTAS;         // resident CTAs per SM the kernel is built for
 constexpr int kAtm3Rec = 12;         // reals per neighbour record (11 used), 16-byte aligned pairs
@@ -111,10 +116,12 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
   const SysArgs<S>& A = P.sys;
   constexpr int nw = kAtm3Warps;
   constexpr int NV = WANT_G ? 7 : 1;
+  constexpr int KPL = kAtm3Kpl;                      // list entries per lane
+  constexpr int TK = 32 * KPL;
   __shared__ S rv[kAtmEmax * kAtmEmax];
   __shared__ __align__(16) S wiS[16];
   __shared__ __align__(16) S red[nw * 7 * kAtm3RedStride];
-  __shared__ S wsh[nw][2 * kNRef][32];              // w_k, dw_k of each warp's tile, [a][lane]
+  __shared__ S wsh[nw][KPL][2 * kNRef][32];         // w_k, dw_k of each warp's tile, [k of the lane][a][lane]
   __shared__ S isum[nw][5];
   __shared__ int cnt[nw];
   __shared__ int s_center, s_tile;
@@ -195,10 +202,10 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       q.a = d_n * ic6; q.b = rv[ei * E + en]; r[4] = q;
       q.a = A.aux[nn].b; q.b = int_as(en, S(0)); r[5] = q;
     }
-    if (tid == 0) s_tile = (n + 31) / 32 - 1;
+    if (tid == 0) s_tile = (n + TK - 1) / TK - 1;
     __syncthreads();
 
-    // ---- tiles of 32 list entries (lane <-> k), largest tile first
+    // ---- tiles of 32 * KPL list entries (each lane owns KPL of them), largest tile first
     S Eia = S(0);                                      // per lane: sum e * 2 m_jk
     S Gix = S(0), Giy = S(0), Giz = S(0), Di = S(0);   // per lane (k side) + lane 0 (j side)
     for (;;) {
@@ -206,77 +213,95 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       if (lane == 0) t = atomicSub(&s_tile, 1);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t < 0) break;
-      const int kpos = 32 * t + lane;
-      const bool kvalid = kpos < n;
-      const Pair2<S>* rk = reinterpret_cast<const Pair2<S>*>(rec + (size_t)(kvalid ? kpos : 32 * t) * kAtm3Rec);
-      const Pair2<S> k0_ = rk[0], k2_ = rk[2];
-      const S akx = k0_.a, aky = k0_.b, akz = rk[1].a;
-      const S hik = k2_.a, b2 = k2_.b, inv_b = rk[3].a, Rik = rk[4].b, gk = rk[5].a;
-      unsigned ekoff;
-      const S* rvk;
-      {
-        const int kidx = as_int(rk[1].b), ek = as_int(rk[5].b);
-        __syncwarp();
+      int kpos[KPL];
+      bool kvalid[KPL];
+      const Pair2<S>* rk[KPL];
+      S akx[KPL], aky[KPL], akz[KPL], hik[KPL], b2[KPL], inv_b[KPL], Rik[KPL], gk[KPL];
+      unsigned ekoff[KPL];
+      const S* rvk[KPL];
+      S Sfb[KPL], Swe[KPL], Ek[KPL], Vx[KPL], Vy[KPL], Vz[KPL], Dk[KPL];
+      __syncwarp();
+#pragma unroll
+      for (int kk = 0; kk < KPL; ++kk) {
+        kpos[kk] = TK * t + 32 * kk + lane;
+        kvalid[kk] = kpos[kk] < n;
+        rk[kk] = reinterpret_cast<const Pair2<S>*>(rec + (size_t)(kvalid[kk] ? kpos[kk] : TK * t) * kAtm3Rec);
+        const Pair2<S> k0_ = rk[kk][0], k2_ = rk[kk][2];
+        akx[kk] = k0_.a; aky[kk] = k0_.b; akz[kk] = rk[kk][1].a;
+        hik[kk] = k2_.a; b2[kk] = k2_.b; inv_b[kk] = rk[kk][3].a; Rik[kk] = rk[kk][4].b; gk[kk] = rk[kk][5].a;
+        const int kidx = as_int(rk[kk][1].b), ek = as_int(rk[kk][5].b);
 #pragma unroll
         for (int a = 0; a < kNRef; ++a) {
-          wsh[wid][a][lane] = A.w[8 * (size_t)kidx + a];
-          if (WANT_G) wsh[wid][kNRef + a][lane] = A.dw[8 * (size_t)kidx + a];
+          wsh[wid][kk][a][lane] = A.w[8 * (size_t)kidx + a];
+          if (WANT_G) wsh[wid][kk][kNRef + a][lane] = A.dw[8 * (size_t)kidx + a];
         }
-        __syncwarp();
-        ekoff = (unsigned)ek * 8;
-        rvk = rv + ek;
+        ekoff[kk] = (unsigned)ek * 8;
+        rvk[kk] = rv + ek;
+        Sfb[kk] = Swe[kk] = Ek[kk] = Vx[kk] = Vy[kk] = Vz[kk] = Dk[kk] = S(0);
       }
-      S Sfb = S(0), Swe = S(0), Ek = S(0), Vx = S(0), Vy = S(0), Vz = S(0), Dk = S(0);
-      const int jend = min(32 * t + 31, n - 1);        // positions j < k only
+      __syncwarp();
+      const int jend = min(TK * t + TK - 1, n - 1);    // positions j < k only
       const Pair2<S>* rj = reinterpret_cast<const Pair2<S>*>(rec);
       for (int jpos = 0; jpos < jend; ++jpos, rj += kAtm3Rec / 2) {
         const Pair2<S> j0_ = rj[0], j1_ = rj[1];         // warp-uniform loads
-        const S dxjk = j0_.a - akx, dyjk = j0_.b - aky, dzjk = j1_.a - akz;
-        const S c2e = dxjk * dxjk + dyjk * dyjk + dzjk * dzjk;
-        const bool mjk = c2e <= cutoff2;
         const int jidx = as_int(j1_.b);
-        // a triangle belongs to its smallest index: i < j (< k, the list is sorted)
-        const bool act = kvalid && kpos > jpos && (!mjk || jidx > i);
-        if (!__any_sync(0xffffffffu, act)) continue;
+        S dxjk[KPL], dyjk[KPL], dzjk[KPL], c2e[KPL];
+        bool mjk[KPL], act[KPL];
+        bool any_act = false;
+#pragma unroll
+        for (int kk = 0; kk < KPL; ++kk) {
+          dxjk[kk] = j0_.a - akx[kk]; dyjk[kk] = j0_.b - aky[kk]; dzjk[kk] = j1_.a - akz[kk];
+          c2e[kk] = dxjk[kk] * dxjk[kk] + dyjk[kk] * dyjk[kk] + dzjk[kk] * dzjk[kk];
+          mjk[kk] = c2e[kk] <= cutoff2;
+          // a triangle belongs to its smallest index: i < j (< k, the list is sorted)
+          act[kk] = kvalid[kk] && kpos[kk] > jpos && (!mjk[kk] || jidx > i);
+          any_act = any_act || act[kk];
+        }
+        if (!__any_sync(0xffffffffu, any_act)) continue;
         const Pair2<S> j2_ = rj[2], j3_ = rj[3], j4_ = rj[4], j5_ = rj[5];
         const S hij = j2_.a, a2 = j2_.b, inv_a = j3_.a;
         const int ej = as_int(j5_.b);
+        const unsigned jbase = (unsigned)jidx * (unsigned)E * 8u;
+        const S r0j = rs93 * j4_.b;
         S vals[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) vals[v] = S(0);
-        if (act) {
-          const S* Tjp = tvec + ((unsigned)jidx * (unsigned)E * 8u + ekoff);
+        // the KPL triples of a lane are evaluated unconditionally (independent chains for the
+        // scheduler); inactive ones are discarded by selects at the end
+#pragma unroll
+        for (int kk = 0; kk < KPL; ++kk) {
+          const S* Tjp = tvec + (jbase + ekoff[kk]);
           const Pair2<S>* Tj2 = reinterpret_cast<const Pair2<S>*>(Tjp);
           S Tj[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) { const Pair2<S> pp = Tj2[q]; Tj[2 * q] = pp.a; Tj[2 * q + 1] = pp.b; }
-          S c6jk = wsh[wid][0][lane] * Tj[0];
+          S c6jk = wsh[wid][kk][0][lane] * Tj[0];
 #pragma unroll
-          for (int a = 1; a < kNRef; ++a) c6jk += wsh[wid][a][lane] * Tj[a];
+          for (int a = 1; a < kNRef; ++a) c6jk += wsh[wid][kk][a][lane] * Tj[a];
           const S xjk = ab(c6jk) + tiny;
           const S hjk = xjk * frsq(xjk);
-          const S c9 = P.s9 * (hij * (hik * hjk));
-          const S r0 = (rs93 * j4_.b) * (Rik * rvk[ej * E]);
-          const S c2 = c2e + tiny;
-          const S ab2 = a2 * b2;
+          const S c9 = P.s9 * (hij * (hik[kk] * hjk));
+          const S r0 = r0j * (Rik[kk] * rvk[kk][ej * E]);
+          const S c2 = c2e[kk] + tiny;
+          const S ab2 = a2 * b2[kk];
           const S r2 = ab2 * c2;
           const S r1inv = frsq(r2);
           const S r1inv2 = r1inv * r1inv;
           const S r3inv = r1inv2 * r1inv;
           const S r5inv = r3inv * r1inv2;
-          const S p = a2 + c2 - b2, q = a2 - c2 + b2, tt = (c2 + b2) - a2;
+          const S p = a2 + c2 - b2[kk], q = a2 - c2 + b2[kk], tt = (c2 + b2[kk]) - a2;
           const S s = p * q * tt;
           const S sr5 = s * r5inv;
           const S ang = S(0.375) * sr5 + r3inv;
           const S base = r0 * r1inv;
           const S u = P.cube_root_pow ? pow16_3_fast<S>(base) : fex(fmx(P.pexp * lg(base), S(-700)));
           const S fd = frcp(S(1) + S(6) * u);
-          const S e = c9 * (ang * fd);
-          const S share = mjk ? S(2) : S(1);           // 1 + m_jk
+          const S e = act[kk] ? c9 * (ang * fd) : S(0);
+          const S share = mjk[kk] ? S(2) : S(1);       // 1 + m_jk
           const S es = e * share;
-          Eia += mjk ? e + e : S(0);
-          Ek += es;
-          vals[0] = es;
+          Eia += mjk[kk] ? e + e : S(0);
+          Ek[kk] += es;
+          vals[0] += es;
           if (WANT_G) {
             const S dfd0 = (S(3) * P.pexp) * (u * (fd * fd));
             const S qt = q * tt, pt = p * tt, pq = p * q;
@@ -284,26 +309,26 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
             const S common = k1 - k0 * (S(0.9375) * sr5 + S(1.5) * r3inv);
             const S k0r5 = S(0.375) * (k0 * r5inv);
             const S inv_c = r1inv2 * ab2;
-            const S w6 = (mjk ? gi + gi : S(0)) + (j5_.a + gk) * share;
+            const S w6 = act[kk] ? (mjk[kk] ? gi + gi : S(0)) + (j5_.a + gk[kk]) * share : S(0);
             const S we = w6 * e;
-            const S fa = w6 * (k0r5 * (qt + pt - pq) + common * inv_a);
-            const S fb = w6 * (k0r5 * (pt + pq - qt) + common * inv_b);
-            const S fc = w6 * (k0r5 * (qt + pq - pt) + common * inv_c);
-            Sfb += fb;
-            Swe += we;
-            const S vx = fc * dxjk, vy = fc * dyjk, vz = fc * dzjk;
-            Vx += vx; Vy += vy; Vz += vz;
+            const S fa = act[kk] ? w6 * (k0r5 * (qt + pt - pq) + common * inv_a) : S(0);
+            const S fb = act[kk] ? w6 * (k0r5 * (pt + pq - qt) + common * inv_b[kk]) : S(0);
+            const S fc = act[kk] ? w6 * (k0r5 * (qt + pq - pt) + common * inv_c) : S(0);
+            Sfb[kk] += fb;
+            Swe[kk] += we;
+            const S vx = fc * dxjk[kk], vy = fc * dyjk[kk], vz = fc * dzjk[kk];
+            Vx[kk] += vx; Vy[kk] += vy; Vz[kk] += vz;
             const Pair2<S>* Td2 = reinterpret_cast<const Pair2<S>*>(Tjp + tdoff);
             S Td[8];
 #pragma unroll
             for (int q2 = 0; q2 < 4; ++q2) { const Pair2<S> pp = Td2[q2]; Td[2 * q2] = pp.a; Td[2 * q2 + 1] = pp.b; }
-            S dk = wsh[wid][kNRef][lane] * Tj[0], dj = wsh[wid][0][lane] * Td[0];
+            S dk = wsh[wid][kk][kNRef][lane] * Tj[0], dj = wsh[wid][kk][0][lane] * Td[0];
 #pragma unroll
-            for (int a = 1; a < kNRef; ++a) { dk += wsh[wid][kNRef + a][lane] * Tj[a]; dj += wsh[wid][a][lane] * Td[a]; }
-            const S qc = we * frcp(c6jk);
-            Dk += qc * dk;
-            vals[1 % NV] = fa; vals[2 % NV] = we; vals[3 % NV] = vx; vals[4 % NV] = vy; vals[5 % NV] = vz;
-            vals[6 % NV] = qc * dj;
+            for (int a = 1; a < kNRef; ++a) { dk += wsh[wid][kk][kNRef + a][lane] * Tj[a]; dj += wsh[wid][kk][a][lane] * Td[a]; }
+            const S qc = act[kk] ? we * frcp(c6jk) : S(0);
+            Dk[kk] += qc * dk;
+            vals[1 % NV] += fa; vals[2 % NV] += we; vals[3 % NV] += vx; vals[4 % NV] += vy; vals[5 % NV] += vz;
+            vals[6 % NV] += qc * dj;
           }
         }
         // ---- j side of this step: sums over the 32 lanes, five atomics
@@ -326,18 +351,21 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
         }
       }
       // ---- k side of the tile
-      if (kvalid) {
-        const int kidx = as_int(rk[1].b);
-        red_add(A.energy + kidx, sixth * Ek);
-        if (WANT_G) {
-          const S cki = rk[3].b, ckk = rk[4].a;
-          const S dxik = ai.x - akx, dyik = ai.y - aky, dzik = ai.z - akz;
-          red_add(A.grad + 3 * (size_t)kidx, -two6 * (Sfb * dxik + Vx));
-          red_add(A.grad + 3 * (size_t)kidx + 1, -two6 * (Sfb * dyik + Vy));
-          red_add(A.grad + 3 * (size_t)kidx + 2, -two6 * (Sfb * dzik + Vz));
-          red_add(A.decn + kidx, half6 * (Swe * ckk + Dk));
-          Gix += Sfb * dxik; Giy += Sfb * dyik; Giz += Sfb * dzik;
-          Di += Swe * cki;
+#pragma unroll
+      for (int kk = 0; kk < KPL; ++kk) {
+        if (kvalid[kk]) {
+          const int kidx = as_int(rk[kk][1].b);
+          red_add(A.energy + kidx, sixth * Ek[kk]);
+          if (WANT_G) {
+            const S cki = rk[kk][3].b, ckk = rk[kk][4].a;
+            const S dxik = ai.x - akx[kk], dyik = ai.y - aky[kk], dzik = ai.z - akz[kk];
+            red_add(A.grad + 3 * (size_t)kidx, -two6 * (Sfb[kk] * dxik + Vx[kk]));
+            red_add(A.grad + 3 * (size_t)kidx + 1, -two6 * (Sfb[kk] * dyik + Vy[kk]));
+            red_add(A.grad + 3 * (size_t)kidx + 2, -two6 * (Sfb[kk] * dzik + Vz[kk]));
+            red_add(A.decn + kidx, half6 * (Swe[kk] * ckk + Dk[kk]));
+            Gix += Sfb[kk] * dxik; Giy += Sfb[kk] * dyik; Giz += Sfb[kk] * dzik;
+            Di += Swe[kk] * cki;
+          }
         }
       }
     }
