@@ -447,11 +447,11 @@ def main():
             "gpu_launches": launches,
             "roofline": {
                 "bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": achieved, "peak": peak_tflops,
-                "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": 15.8e6 if args.dtype == "f64" else None,
+                "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": 15.83e6 if args.dtype == "f64" else None,
                 "kernel": "d3::molecule_kernel_v2<%s, true>" % ("double" if args.dtype == "f64" else "float"),
                 "peak_source": "FMA-chain probe of the same type measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "fp64_pipe_active_pct_ncu": 54.3 if args.dtype == "f64" else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1f_molecule_kernel_v2_raw.csv",
+                "fp64_pipe_active_pct_ncu": 53.7 if args.dtype == "f64" else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1h_molecule_kernel_v2_raw.csv",
                 "flops_model": "140/pair-term (r<=25 Bohr), 89 (25<r<=50), SURVEY.md 8(d)",
                 "hbm_gbs_measured_peak": _measured_hbm(),
             },
@@ -722,7 +722,8 @@ def run_c5a(args, rank, local, world, dev):
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     e2e_err = float((g_h.to(dev) - grad).abs().max())
-    t = torch.tensor([float(np.mean(t_atm)), float(np.mean(t_all)), e2e_ms], dtype=torch.double, device=dev)
+    # median over the timed steps: single steps are occasionally disturbed by allocator growth
+    t = torch.tensor([float(np.median(t_atm)), float(np.median(t_all)), e2e_ms], dtype=torch.double, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_atm, ms_all, e2e_ms = float(t[0]), float(t[1]), float(t[2])
@@ -740,6 +741,7 @@ def run_c5a(args, rank, local, world, dev):
                    "entry": "SystemPlan + d3b200_system_{cn,weights,tvec,pair,atm,cnbwd}_f64; value = triples / whole step "
                             "(max over ranks, CUDA events); the three-body sweep alone in atm_ms",
                    "atm_ms": ms_atm, "triples_per_s_atm_kernel": triples / (ms_atm * 1e-3),
+                   "atm_ms_per_step": [round(v, 3) for v in t_atm],
                    "total_energy": float(energy.sum()),
                    "parallelism": f"centres of the three-body term and rows of the two-body sweeps over {world} GPU(s); "
                                   "all-reduce of CN, dL/dCN, E, grad"},
