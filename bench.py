@@ -283,6 +283,9 @@ def main():
     from tad_dftd3_b200 import synthetic as syn
     from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
 
+    # one process per GPU: keep this rank's host thread and its page-locked buffers on the
+    # NUMA node of its GPU (matters for the end-to-end number when 8 ranks share the host)
+    numa_bound = d3.bind_host_thread_to_gpu(local) if os.environ.get("D3B200_NO_NUMA_BIND") != "1" else False
     lib = _lib.lib()
     dt = torch.double if args.dtype == "f64" else torch.float32
     if args.workload == "c5a":
@@ -443,6 +446,7 @@ def main():
                 "api": f"tad_dftd3_b200.dftd3_host(): pinned host buffers in, pinned host energies + gradient out; "
                        f"{n_e2e_launch} chunks pipelined H2D / kernel / D2H (d3b200_batch_vjp_host_{args.dtype}), "
                        "synchronised every step",
+                "host_thread_bound_to_gpu_numa_node": bool(numa_bound),
             },
             "gpu_launches": launches,
             "roofline": {

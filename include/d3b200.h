@@ -300,8 +300,9 @@ int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* p
  * every triple is evaluated once: persistent CTAs take centre atoms from a
  * counter, compact the centre's neighbour list into the scratch and walk the
  * pairs of neighbours (see csrc/d3_atm3.cuh).  The launch owns the centres of
- * the row tiles row_begin/128 + k*tile_stride below row_end (tile_stride <= 1:
- * all tiles of the range), which is how ranks shard the term. */
+ * the 32-atom sub-tiles row_begin/32 + k*tile_stride below row_end (row range
+ * aligned to 32; tile_stride <= 1: the whole range), which is how ranks shard
+ * the term. */
 size_t d3b200_system_atm_workspace_bytes_f64(int natoms);
 size_t d3b200_system_atm_workspace_bytes_f32(int natoms);
 int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par,

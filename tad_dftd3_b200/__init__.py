@@ -13,12 +13,12 @@ derivatives wired into torch autograd / torch.func.
 """
 from . import damping, data, defaults, disp, model, ncoord, reference
 from .disp import dftd3
-from .host import HostPipeline, dftd3_host
+from .host import HostPipeline, bind_host_thread_to_gpu, dftd3_host
 from .reference import Reference
 
 __version__ = "0.1.0"
 
 __all__ = [
-    "dftd3", "dftd3_host", "HostPipeline", "damping", "data", "defaults", "disp", "model", "ncoord", "reference",
+    "dftd3", "dftd3_host", "HostPipeline", "bind_host_thread_to_gpu", "damping", "data", "defaults", "disp", "model", "ncoord", "reference",
     "Reference", "__version__",
 ]

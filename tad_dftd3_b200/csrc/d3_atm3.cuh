@@ -13,7 +13,7 @@
 //
 // Work decomposition
 //  * persistent CTAs take centres i from a global counter (a launch owns the
-//    centres of the row tiles row_begin/128 + k * tile_stride below row_end, which
+//    centres of the 32-atom sub-tiles row_begin/32 + k * tile_stride below row_end, which
 //    is also how ranks shard the term: results are ADDED, so an all-reduce follows);
 //  * the CTA compacts the neighbours of i (r <= c), in index order, into its own
 //    list in global scratch, with one self-contained record per neighbour n:
@@ -52,7 +52,9 @@ struct AtmArgs3 {
   int* list;       // [gridDim.x][natoms]          neighbour indices of the CTA's current centre
   S* rec;          // [gridDim.x][natoms][kAtm3Rec] neighbour records
   int* counter;    // zero before the launch
-  int tile_stride; // the launch owns the row tiles row_begin/128 + k * tile_stride below row_end
+  int tile_stride; // the launch owns the 32-atom sub-tiles row_begin/32 + k * tile_stride below row_end
+  int parts;       // a centre is split into `parts` work units (every parts-th tile of its list): keeps
+                   // the persistent CTAs busy when a launch owns few centres (several GPUs)
 };
 
 template <typename S>
@@ -131,8 +133,8 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
   const int natoms = A.natoms;
   const int nsub = natoms / kSysSub;
   const int tstride = Q.tile_stride > 0 ? Q.tile_stride : 1;
-  const int ntile_own = ((A.row_end - A.row_begin) / kSysTile + tstride - 1) / tstride;
-  const int nrows = ntile_own * kSysTile;
+  const int nsub_own = ((A.row_end - A.row_begin) / kSysSub + tstride - 1) / tstride;
+  const int nrows = nsub_own * kSysSub;
   int* list = Q.list + (size_t)blockIdx.x * natoms;
   S* rec = Q.rec + (size_t)blockIdx.x * natoms * kAtm3Rec;
   S* redw = red + wid * 7 * kAtm3RedStride;
@@ -149,9 +151,11 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
     __syncthreads();                       // previous centre completely finished (list, wiS, isum reusable)
     if (tid == 0) s_center = atomicAdd(Q.counter, 1);
     __syncthreads();
-    const int c = s_center;
+    const int parts = Q.parts > 0 ? Q.parts : 1;
+    const int part = s_center % parts;
+    const int c = s_center / parts;
     if (c >= nrows) break;
-    const int i = A.row_begin + (c / kSysTile) * tstride * kSysTile + (c % kSysTile);
+    const int i = A.row_begin + (c / kSysSub) * tstride * kSysSub + (c % kSysSub);
     const int ei = P.eidx[i];
     if (ei < 0) continue;                  // padding row (CTA-uniform)
     const Atom4<S> ai = A.atoms[i];
@@ -202,7 +206,8 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       q.a = d_n * ic6; q.b = rv[ei * E + en]; r[4] = q;
       q.a = A.aux[nn].b; q.b = int_as(en, S(0)); r[5] = q;
     }
-    if (tid == 0) s_tile = (n + TK - 1) / TK - 1;
+    const int ntile = (n + TK - 1) / TK;
+    if (tid == 0) s_tile = (ntile - 1 - part + parts) / parts - 1;   // tiles part, part + parts, ... of this unit
     __syncthreads();
 
     // ---- tiles of 32 * KPL list entries (each lane owns KPL of them), largest tile first
@@ -213,6 +218,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       if (lane == 0) t = atomicSub(&s_tile, 1);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t < 0) break;
+      t = t * parts + part;
       int kpos[KPL];
       bool kvalid[KPL];
       const Pair2<S>* rk[KPL];

@@ -315,11 +315,11 @@ template <> struct SysOf<double> { using type = d3b200_system_f64; };
 template <> struct SysOf<float> { using type = d3b200_system_f32; };
 
 template <typename B>
-int sys_fill(d3::SysArgs<B>& a, const typename SysOf<B>::type* s, const d3b200_params* par) {
+int sys_fill(d3::SysArgs<B>& a, const typename SysOf<B>::type* s, const d3b200_params* par, int align = d3::kSysTile) {
   if (!s || !par) return fail(D3B200_EINVAL, "null argument%s");
   if (s->natoms <= 0 || s->natoms % d3::kSysTile) return fail(D3B200_EINVAL, "natoms must be a positive multiple of 128%s");
   if (s->row_begin < 0 || s->row_end > s->natoms || s->row_begin > s->row_end ||
-      s->row_begin % d3::kSysTile || s->row_end % d3::kSysTile)
+      s->row_begin % align || s->row_end % align)
     return fail(D3B200_EINVAL, "row range must be tile aligned%s");
   if (!s->atoms || !s->z || !s->box) return fail(D3B200_EINVAL, "null system array%s");
   memset(&a, 0, sizeof(a));
@@ -472,7 +472,7 @@ int atm3_grid() {
 template <typename B>
 int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int want_grad, void* stream) {
   d3::AtmArgs<B> p;
-  int rc = sys_fill<B>(p.sys, s, par);
+  int rc = sys_fill<B>(p.sys, s, par, d3::kSysSub);
   if (rc) return rc;
   if (!rvdw || !s->aux || !s->w || !s->dw || !s->refc6 || !s->energy) return fail(D3B200_EINVAL, "null ATM argument%s");
   if (want_grad && (!s->grad || !s->decn)) return fail(D3B200_EINVAL, "null ATM gradient output%s");
@@ -498,6 +498,12 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       r.a = q;
       r.tile_stride = s->tile_stride > 0 ? s->tile_stride : 1;
       const int grid = atm3_grid();
+      {
+        // about four work units per persistent CTA, at most 8 per centre
+        const int owned = (rows + r.tile_stride - 1) / r.tile_stride;
+        int parts = owned > 0 ? (4 * grid + owned - 1) / owned : 1;
+        r.parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
+      }
       char* wsp = reinterpret_cast<char*>(s->atm_work);
       r.counter = reinterpret_cast<int*>(wsp);
       r.rec = reinterpret_cast<B*>(wsp + 256);

@@ -28,7 +28,27 @@ from torch import Tensor
 from . import _lib, defaults
 from .ops import Settings, _params, _sfx
 
-__all__ = ["dftd3_host", "HostPipeline"]
+__all__ = ["dftd3_host", "HostPipeline", "bind_host_thread_to_gpu"]
+
+
+def bind_host_thread_to_gpu(device_index: int) -> bool:
+    """Pin the calling thread to the CPU cores next to GPU `device_index` (NVML's ideal
+    affinity), so that page-locked buffers allocated afterwards sit on the GPU's NUMA
+    node.  With one process per GPU on a two-socket host this keeps the host <-> device
+    copies of `dftd3_host` off the socket interconnect.  Returns False when NVML is
+    not available (nothing is changed then)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+            pynvml.nvmlDeviceSetCpuAffinity(handle)
+        finally:
+            pynvml.nvmlShutdown()
+        return True
+    except Exception:
+        return False
 
 
 class HostPipeline:

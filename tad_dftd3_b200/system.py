@@ -257,14 +257,14 @@ class SystemRunner:
         self._call("cnbwd", rows)
 
     def atm_partition(self, rank: int, world: int):
-        """Centres of the three-body term this rank owns: every `world`-th row tile
-        starting at tile `rank` (interleaved, so surface and core tiles are spread
-        evenly); needs the triples-once kernel."""
+        """Centres of the three-body term this rank owns: every `world`-th 32-atom
+        sub-tile starting at sub-tile `rank` (interleaved, so surface and core regions
+        are spread evenly); needs the triples-once kernel."""
         if world <= 1 or not self.use_tvec or os.environ.get("TAD_DFTD3_B200_ATM2") == "1":
             self._atm_stride = 1
             return row_partition(self.plan.npad, world)[rank]
         self._atm_stride = world
-        return (min(rank * TILE, self.plan.npad), self.plan.npad)
+        return (min(rank * SUB, self.plan.npad), self.plan.npad)
 
     def sweep_atm(self, want_grad: bool, rows=None):
         """Three-body term (adds to energy / grad / decn); no-op when s9 == 0."""
