@@ -251,7 +251,8 @@ def main():
     ap.add_argument("--ref-nmol", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=0,
-                    help="c3 end-to-end: structures per pipeline chunk of dftd3_host (0 = library default, one wave of CTAs)")
+                    help="c3 end-to-end: 0 = zero-copy form of dftd3_host (default); > 0 = staged form with this many "
+                         "structures per pipeline chunk")
     ap.add_argument("--cutoff", type=float, default=25.0, help="c5a: dispersion/triple cutoff in Bohr")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5a", "c5b"],
                     help="c3: 4096-molecule batch (default, the headline metric); "
@@ -373,7 +374,7 @@ def main():
         # into chunks of structures and pipelines H2D copy / fused kernel / D2H copy
         # (d3b200_batch_vjp_host_f64); it returns after the results are in e_h / g_h.
         host_chunk = max(0, args.e2e_chunk)
-        n_e2e_launch = d3.HostPipeline.chunks(args.nmol, host_chunk)
+        n_e2e_launch = 1 if host_chunk == 0 else d3.HostPipeline.chunks(args.nmol, host_chunk)
         positions_e2e, ref_e2e = positions_h, ref
 
         def step_e2e():
@@ -443,9 +444,12 @@ def main():
                 "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * positions_h.element_size()),
                 "d2h_bytes_per_step": int((e_h.numel() + g_h.numel()) * e_h.element_size()),
                 "ms_per_step": e2e_ms,
-                "api": f"tad_dftd3_b200.dftd3_host(): pinned host buffers in, pinned host energies + gradient out; "
-                       f"{n_e2e_launch} chunks pipelined H2D / kernel / D2H (d3b200_batch_vjp_host_{args.dtype}), "
-                       "synchronised every step",
+                "api": f"tad_dftd3_b200.dftd3_host(): pinned host buffers in, pinned host energies + gradient out "
+                       f"(d3b200_batch_vjp_host_{args.dtype}); "
+                       + ("one launch of the fused kernel reading and writing host memory directly (zero-copy, "
+                          "coalesced), " if host_chunk == 0 else
+                          f"{n_e2e_launch} chunks pipelined H2D / kernel / D2H, ")
+                       + "synchronised every step",
                 "host_thread_bound_to_gpu_numa_node": bool(numa_bound),
             },
             "gpu_launches": launches,

@@ -159,7 +159,13 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
  * live in HOST memory (page-locked for the copies to be asynchronous), as a
  * caller of the reference's CPU `dftd3()` + autograd holds them.
  *
- * The batch is independent per structure, so it is cut into chunks of
+ * Two forms.  (1) Zero-copy, taken when chunk <= 0, par->s9 == 0 and every host
+ * buffer is page-locked and mapped (cudaHostAlloc / cudaHostRegister under UVA):
+ * ONE launch of the fused kernel on `stream` reads the inputs and writes the
+ * results directly in host memory; all its global accesses are coalesced, and
+ * the PCIe traffic of each resident CTA overlaps the arithmetic of the others.
+ * No workspace is used.  (2) Staged, otherwise (pageable memory, ATM, chunk > 0):
+ * the batch is independent per structure, so it is cut into chunks of
  * `chunk` structures and pipelined over the streams of a `d3b200_pipe`:
  * H2D of chunk k+1, the fused kernel of chunk k (two alternating compute
  * streams, so that the tail of one launch overlaps the head of the next) and
@@ -176,7 +182,9 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
  *   h_g       : cotangent `[nbatch][natoms]` or NULL (unit cotangent)
  *   h_energy  : `[nbatch][natoms]` or NULL;  h_grad: `[nbatch][natoms][3]`
  *   workspace : DEVICE staging, `d3b200_batch_host_workspace_bytes_*` bytes
- *   chunk     : structures per chunk; <= 0 picks one (about one wave of CTAs) */
+ *   chunk     : > 0: staged form with this many structures per chunk;
+ *               <= 0: zero-copy when possible, else staged with about one wave of
+ *               CTAs per chunk */
 typedef struct d3b200_pipe d3b200_pipe;
 int d3b200_pipe_create(d3b200_pipe** pipe);
 int d3b200_pipe_destroy(d3b200_pipe* pipe);

@@ -157,10 +157,11 @@ int energy_impl(int nbatch, int natoms, const int64_t* numbers, const B* positio
 template <typename B>
 int vjp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
              const typename ModelOf<B>::type* model, const d3b200_params* par, const B* g,
-             B* energy, B* grad, B* pgrad, void* workspace, size_t wbytes, void* stream) {
+             B* energy, B* grad, B* pgrad, void* workspace, size_t wbytes, void* stream, int host_io = 0) {
   d3::MolArgs<B> a;
   int rc = fill_common<B, B>(a, nbatch, natoms, numbers, positions, model, par, nullptr);
   if (rc) return rc;
+  a.host_io = host_io;
   if (!grad) return fail(D3B200_EINVAL, "null gradient output%s");  // g == NULL: unit cotangent
   if (nbatch == 0 || natoms == 0) return D3B200_OK;
   a.g = g;
@@ -225,6 +226,13 @@ namespace {
 
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// page-locked host memory that kernels of the current device can address (UVA)
+bool device_visible(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost && a.devicePointer == p;
+}
+
 template <typename B>
 size_t host_workspace_bytes(int nbatch, int natoms, int with_g, int atm) {
   if (nbatch <= 0 || natoms <= 0) return 0;
@@ -247,6 +255,14 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
     return fail(D3B200_EINVAL, "host entry takes per-element rcov / r4r2 / rvdw tables only%s");
   if (nbatch == 0 || natoms == 0) return D3B200_OK;
   const int atm = par->s9 != 0.0;
+  // Zero-copy form (chunk <= 0, two-body + CN, all buffers page-locked and mapped): ONE launch of the
+  // fused kernel on the host pointers.  Every CTA reads its structure over PCIe at its start and writes
+  // its results at its end -- all accesses of the kernel are coalesced for that purpose -- so the transfers
+  // of the 592 resident CTAs overlap the arithmetic of the others without any staging or chunking.
+  if (chunk <= 0 && !atm && v2_fits<B>(natoms) && device_visible(h_numbers) && device_visible(h_positions) &&
+      device_visible(h_grad) && (!h_energy || device_visible(h_energy)) && (!h_g || device_visible(h_g)))
+    return vjp_impl<B>(nbatch, natoms, h_numbers, h_positions, model, par, h_g, h_energy, h_grad, nullptr,
+                       nullptr, 0, stream, 1);
   const size_t need = host_workspace_bytes<B>(nbatch, natoms, h_g != nullptr, atm);
   if (!workspace || wbytes < need)
     return fail(D3B200_EINVAL, "host-entry workspace too small%s: %ld < %ld bytes", "", (long)wbytes, (long)need);

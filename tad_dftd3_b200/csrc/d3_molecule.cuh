@@ -55,6 +55,8 @@ struct MolArgs {
   B* dgrad;
   B* dpgrad;
   S* work;                  // ATM scratch: sqrt|C6| per structure, [nbatch][N][N]
+  int host_io;              // molecule_kernel_v2: numbers / positions / energy / grad may live in mapped HOST
+                            // memory -> every global access of these arrays fully coalesced
 };
 
 template <typename S> __device__ __forceinline__ S warp_sum(S v);

@@ -127,8 +127,21 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
   const S* pos = A.positions + (size_t)b * N * 3;
 
   // ---------------------------------------------------------------- phase 0
+  // host_io: the per-structure arrays may live in page-locked HOST memory (zero-copy
+  // over PCIe, `d3b200_batch_vjp_host_*`), so every global access of them is fully
+  // coalesced: positions are staged through shared memory and the outputs are gathered
+  // into the caller's atom order before they are written as contiguous blocks.
+  const bool hio = A.host_io != 0;                   // CTA-uniform
+  // raw positions: in the reduction tiles when they fit (idle until phase 1), else in acc
+  const bool pos_in_red = (size_t)3 * N <= (size_t)nw * 2 * kRedV * kRedStride;
+  const S* spos = hio ? (pos_in_red ? red : acc) : pos;
   for (int k = t; k < kMaxZ; k += nt) cnt[k] = 0;
-  for (int k = t; k < nw * 5 * N; k += nt) acc[k] = S(0);
+  if (hio) {
+    S* dst = pos_in_red ? red : acc;
+    for (int m = t; m < 3 * N; m += nt) dst[m] = pos[m];
+  }
+  if (!hio || pos_in_red)
+    for (int k = t; k < nw * 5 * N; k += nt) acc[k] = S(0);
   __syncthreads();
   for (int k = t; k < N; k += nt) {
     int Z = (int)numbers[k];
@@ -136,7 +149,7 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
     sorigZ[k] = (unsigned char)Z;
     if (Z > 0) {
       atomicAdd(&cnt[Z], 1);
-    } else {
+    } else if (!hio) {
       size_t o = (size_t)b * N + k;
       if (A.energy) A.energy[o] = S(0);
       if (WANT_G) { A.grad[3 * o] = S(0); A.grad[3 * o + 1] = S(0); A.grad[3 * o + 2] = S(0); }
@@ -186,7 +199,7 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
     S rc = A.rcov_per_element ? A.rcov[Z] : A.rcov[(size_t)b * N + k];
     S q = A.r4r2_per_element ? A.r4r2[Z] : A.r4r2[(size_t)b * N + k];
     Atom4<S> a4;
-    a4.x = pos[3 * k]; a4.y = pos[3 * k + 1]; a4.z = pos[3 * k + 2]; a4.rk = A.kcn * rc;
+    a4.x = spos[3 * k]; a4.y = spos[3 * k + 1]; a4.z = spos[3 * k + 2]; a4.rk = A.kcn * rc;
     sA[p] = a4;
     Pair2<S> b2;
     b2.a = sqr(q);
@@ -194,6 +207,10 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
     sB[p] = b2;
   }
   __syncthreads();
+  if (hio && !pos_in_red) {                          // (the staged positions are dead from here on)
+    for (int k = t; k < nw * 5 * N; k += nt) acc[k] = S(0);
+    __syncthreads();
+  }
 
   const S tiny = tiny_of<S>();
   const S eps = eps_of<S>();
@@ -410,14 +427,18 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
   }
   D3_PIECES_END
   __syncthreads();
+  S* se = sdecn + N;                                // second half of sB: energies in the caller's order
   for (int i = t; i < n; i += nt) {
     S e = S(0), d = S(0);
     for (int w = 0; w < nw; ++w) { e += acc[(size_t)w * 5 * N + i]; d += acc[((size_t)w * 5 + 4) * N + i]; }
-    if (A.energy) A.energy[(size_t)b * N + sperm[i]] = S(-0.5) * e;
+    if (hio) se[sperm[i]] = S(-0.5) * e;
+    else if (A.energy) A.energy[(size_t)b * N + sperm[i]] = S(-0.5) * e;
     sdecn[i] = d;
   }
-  if (!WANT_G) return;
   __syncthreads();
+  if (hio && A.energy)
+    for (int k = t; k < N; k += nt) A.energy[(size_t)b * N + k] = sorigZ[k] ? se[k] : S(0);
+  if (!WANT_G) return;
 
   // ---------------------------------------------------------------- phase 4
   // CN chain: (dL/dCN_i + dL/dCN_j) df_ij/dx, df/dx_i = -kcn rc r^-3 f(1-f) (x_i - x_j)
@@ -466,14 +487,33 @@ __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A
   __syncthreads();
 #undef D3_PIECES_BEGIN
 #undef D3_PIECES_END
+  // host_io: gradient gathered into the caller's order in the (spent) energy slots of
+  // warps 0..2, then written as one contiguous [N][3] block, zeros on padding
+  static_assert(kV2Warps >= 3, "three spare accumulator rows needed");
+  S* gxo = acc;
+  S* gyo = acc + (size_t)5 * N;
+  S* gzo = acc + (size_t)10 * N;
   for (int i = t; i < n; i += nt) {
     S gx = S(0), gy = S(0), gz = S(0);
     for (int w = 0; w < nw; ++w) {
       const S* a = acc + (size_t)w * 5 * N;
       gx += a[N + i]; gy += a[2 * N + i]; gz += a[3 * N + i];
     }
-    size_t o = (size_t)b * N + sperm[i];
-    A.grad[3 * o] = gx; A.grad[3 * o + 1] = gy; A.grad[3 * o + 2] = gz;
+    const int k = sperm[i];
+    if (hio) {
+      gxo[k] = gx; gyo[k] = gy; gzo[k] = gz;
+    } else {
+      const size_t o = (size_t)b * N + k;
+      A.grad[3 * o] = gx; A.grad[3 * o + 1] = gy; A.grad[3 * o + 2] = gz;
+    }
+  }
+  if (!hio) return;
+  __syncthreads();
+  S* gout = A.grad + (size_t)b * N * 3;
+  for (int m = t; m < 3 * N; m += nt) {
+    const int k = m / 3, c = m - 3 * k;
+    const S v = c == 0 ? gxo[k] : (c == 1 ? gyo[k] : gzo[k]);
+    gout[m] = sorigZ[k] ? v : S(0);
   }
 }
 

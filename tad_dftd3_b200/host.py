@@ -8,12 +8,15 @@ two results here from one call:
 
     energy, grad = tad_dftd3_b200.dftd3_host(numbers, positions, param)
 
-`numbers` / `positions` are CPU tensors (pinned memory makes the copies
-asynchronous); `energy [B, N]` and `grad [B, N, 3] = d(sum_i g_i E_i)/dx` come
-back as pinned CPU tensors.  Underneath, `d3b200_batch_vjp_host_*`
-(include/d3b200.h) cuts the batch into chunks of structures and pipelines
-H2D copy, fused kernel and D2H copy over the streams of a `d3b200_pipe`, so the
-PCIe transfers overlap the arithmetic instead of bracketing it.
+`numbers` / `positions` are CPU tensors; `energy [B, N]` and
+`grad [B, N, 3] = d(sum_i g_i E_i)/dx` come back as pinned CPU tensors.
+Underneath is `d3b200_batch_vjp_host_*` (include/d3b200.h).  With pinned inputs
+and the default `chunk=0` it is ONE launch of the fused kernel that reads the
+inputs and writes the results directly in host memory (zero-copy over PCIe, all
+accesses coalesced), so the transfers of each resident CTA overlap the
+arithmetic of the others.  With pageable inputs, the ATM term, or `chunk > 0`
+the batch is cut into chunks of structures and H2D copy, kernel and D2H copy
+are pipelined over the streams of a `d3b200_pipe`.
 
 There is no CPU arithmetic here either: the CUDA library is required.
 """
@@ -120,31 +123,37 @@ class HostPipeline:
 
         if ref is None:
             ref = disp._default_reference(dt, dev)
-        refcn, refc6, symmetric = ref._prepared(dev, dt)
-        if not symmetric:
-            raise ValueError("reference C6 table must be symmetric: c6[z1,z2,a,b] == c6[z2,z1,b,a]")
         atm = disp._atm_requested(param)
-        rcov_t = disp._element_table("COV_D3", dt, dev)
-        r4r2_t = disp._element_table("R4R2", dt, dev)
-        rvdw_t = disp._element_table("VDW_PAIRWISE", dt, dev) if atm else None
-        st = Settings(
-            rcov_per_element=True, r4r2_per_element=True, rvdw_mode=1 if atm else 0,
-            cutoff=defaults.D3_DISP_CUTOFF if cutoff is None else disp._scalar(cutoff),
-            cn_cutoff=defaults.D3_CN_CUTOFF, kcn=defaults.D3_KCN,
-            alp=disp._scalar(param.get("alp", defaults.ALP)),
-        )
         keys = ("s6", "s8", "a1", "a2", "s9")
         dflt = (defaults.S6, defaults.S8, defaults.A1, defaults.A2, 0.0)
         pv = [disp._scalar(param.get(k, d)) for k, d in zip(keys, dflt)]
         if not atm:
             pv[4] = 0.0
-        par = _params(pv, st)
-        m = _lib.Model()
-        m.rcov, m.r4r2 = rcov_t.data_ptr(), r4r2_t.data_ptr()
-        m.rcov_per_element = m.r4r2_per_element = 1
-        m.refcn, m.refc6 = refcn.data_ptr(), refc6.data_ptr()
-        m.rvdw = rvdw_t.data_ptr() if atm else None
-        m.rvdw_mode = 1 if atm else 0
+        cut = defaults.D3_DISP_CUTOFF if cutoff is None else disp._scalar(cutoff)
+        alp = disp._scalar(param.get("alp", defaults.ALP))
+        # the C structs of a (reference, parameters) combination are built once
+        key = (id(ref), dt, tuple(pv), cut, alp)
+        hit = self._tables.get(key)
+        if hit is None or hit[0] is not ref:
+            refcn, refc6, symmetric = ref._prepared(dev, dt)
+            if not symmetric:
+                raise ValueError("reference C6 table must be symmetric: c6[z1,z2,a,b] == c6[z2,z1,b,a]")
+            rcov_t = disp._element_table("COV_D3", dt, dev)
+            r4r2_t = disp._element_table("R4R2", dt, dev)
+            rvdw_t = disp._element_table("VDW_PAIRWISE", dt, dev) if atm else None
+            st = Settings(rcov_per_element=True, r4r2_per_element=True, rvdw_mode=1 if atm else 0, cutoff=cut,
+                          cn_cutoff=defaults.D3_CN_CUTOFF, kcn=defaults.D3_KCN, alp=alp)
+            par = _params(pv, st)
+            m = _lib.Model()
+            m.rcov, m.r4r2 = rcov_t.data_ptr(), r4r2_t.data_ptr()
+            m.rcov_per_element = m.r4r2_per_element = 1
+            m.refcn, m.refc6 = refcn.data_ptr(), refc6.data_ptr()
+            m.rvdw = rvdw_t.data_ptr() if atm else None
+            m.rvdw_mode = 1 if atm else 0
+            if len(self._tables) > 16:
+                self._tables.clear()
+            hit = self._tables[key] = (ref, par, m, (refcn, refc6, rcov_t, r4r2_t, rvdw_t))
+        _, par, m, _keep_tables = hit
 
         if g is not None:
             g = g.to(dt).expand(*lead, n).contiguous().reshape(nb, n)
@@ -157,11 +166,16 @@ class HostPipeline:
                 raise ValueError("output buffers must be contiguous CPU tensors of the positions' dtype and shape")
 
         if nb and n:
-            wsfn = getattr(self._lib, f"d3b200_batch_host_workspace_bytes_{sfx}")
-            wbytes = int(wsfn(nb, n, int(g is not None), int(atm)))
-            work = self._workspace(wbytes)
             fn = getattr(self._lib, f"d3b200_batch_vjp_host_{sfx}")
-            _lib.launch_count += self.chunks(nb, chunk)
+            zero_copy = (chunk <= 0 and not atm and z.is_pinned() and x.is_pinned() and energy_out.is_pinned()
+                         and grad_out.is_pinned() and (g is None or g.is_pinned()))
+            if zero_copy and self._work is not None:
+                work = self._work                     # not used by the zero-copy form
+            else:
+                wsfn = getattr(self._lib, f"d3b200_batch_host_workspace_bytes_{sfx}")
+                work = self._workspace(int(wsfn(nb, n, int(g is not None), int(atm))))
+            _lib.launch_count += 1 if zero_copy else self.chunks(nb, chunk)
+            self.last_mode = "zero-copy" if zero_copy else "staged"
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev)
                 _lib.check(fn(self._pipe, nb, n, C.c_void_p(z.data_ptr()), C.c_void_p(x.data_ptr()),
@@ -170,7 +184,7 @@ class HostPipeline:
                               C.c_void_p(work.data_ptr()), C.c_size_t(work.numel()), int(chunk),
                               C.c_void_p(stream.cuda_stream)))
                 # host inputs must outlive the asynchronous copies
-                self._keep = (z, x, g, refcn, refc6)
+                self._keep = (z, x, g, _keep_tables)
                 if sync:
                     stream.synchronize()
         return energy_out.reshape(*lead, n), grad_out.reshape(*lead, n, 3)
