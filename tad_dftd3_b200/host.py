@@ -169,11 +169,10 @@ class HostPipeline:
             fn = getattr(self._lib, f"d3b200_batch_vjp_host_{sfx}")
             zero_copy = (chunk <= 0 and not atm and z.is_pinned() and x.is_pinned() and energy_out.is_pinned()
                          and grad_out.is_pinned() and (g is None or g.is_pinned()))
-            if zero_copy and self._work is not None:
-                work = self._work                     # not used by the zero-copy form
-            else:
-                wsfn = getattr(self._lib, f"d3b200_batch_host_workspace_bytes_{sfx}")
-                work = self._workspace(int(wsfn(nb, n, int(g is not None), int(atm))))
+            # (the zero-copy form does not touch the workspace; it is sized for the staged form the
+            # library falls back to when a buffer turns out not to be mapped)
+            wsfn = getattr(self._lib, f"d3b200_batch_host_workspace_bytes_{sfx}")
+            work = self._workspace(int(wsfn(nb, n, int(g is not None), int(atm))))
             _lib.launch_count += 1 if zero_copy else self.chunks(nb, chunk)
             self.last_mode = "zero-copy" if zero_copy else "staged"
             with torch.cuda.device(dev):
