@@ -115,9 +115,11 @@ class HostPipeline:
         dt, dev = positions.dtype, self.device
         sfx = _sfx(dt)
         lead, n = positions.shape[:-2], positions.shape[-2]
-        z = numbers.to(torch.int64).contiguous().reshape(-1, n)
-        x = positions.contiguous().reshape(-1, n, 3)
-        nb = x.shape[0]
+        nb = 1
+        for d in lead:
+            nb *= int(d)
+        z = numbers.to(torch.int64).contiguous().reshape(nb, n)
+        x = positions.contiguous().reshape(nb, n, 3)
         if self._lib.d3b200_batch_max_atoms_f64(0) < n:
             raise ValueError("dftd3_host handles structures that fit the fused kernel; use dftd3() for larger ones")
 

@@ -99,14 +99,17 @@ class _Call:
         self.lead = lead = positions.shape[:-2]
         self.n = n = positions.shape[-2]
         self.dtype, self.device = dt, dev = positions.dtype, positions.device
+        nflat = 1
+        for d in lead:
+            nflat *= int(d)
         x = _as(positions, dt, dev)
-        self.x = x if x.dim() == 3 else x.reshape(-1, n, 3)
+        self.x = x if x.dim() == 3 else x.reshape(nflat, n, 3)     # (explicit sizes: n or nflat may be 0)
         z = numbers
         if z.shape != positions.shape[:-1]:
             z = z.expand(*lead, n)
         z = _as(z, torch.int64, dev)
-        self.z = z if z.dim() == 2 else z.reshape(-1, n)
-        self.nflat = nflat = self.x.shape[0]
+        self.z = z if z.dim() == 2 else z.reshape(nflat, n)
+        self.nflat = nflat
         self.st = st
 
         def atomwise(t, trailing=()):

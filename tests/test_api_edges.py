@@ -1,0 +1,123 @@
+"""
+GPU tests of the call surface at its edges: empty and degenerate shapes, extra leading
+batch dimensions, non-contiguous views, int32 numbers, parameters of another dtype or
+device -- everything `tad_dftd3.dftd3` accepts (reference disp.py:79-165) has to be
+accepted here with the same result.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, oracle_energy, tables
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+PARAM = {"s6": 1.0, "s8": 0.78981345, "a1": 0.49484001, "a2": 5.73083694}
+
+
+def _ref(dtype=torch.double):
+    import tad_dftd3_b200 as d3
+
+    refcn, refc6, *_ = tables(dtype, DEV)
+    return d3.Reference(cn=refcn, c6=refc6)
+
+
+def _batch(nmol=6, seed=2):
+    from tad_dftd3_b200 import synthetic as syn
+
+    return syn.drug_like_batch(nmol, seed=seed, nmin=8, nmax=20)
+
+
+def test_empty_shapes():
+    import tad_dftd3_b200 as d3
+
+    par = {k: torch.tensor(v, dtype=torch.double) for k, v in PARAM.items()}
+    for shape in ((0,), (0, 7), (3, 0)):
+        z = torch.zeros(shape, dtype=torch.int64, device=DEV)
+        x = torch.zeros(*shape, 3, dtype=torch.double, device=DEV, requires_grad=True)
+        e = d3.dftd3(z, x, par, ref=_ref())
+        assert e.shape == shape and e.dtype == torch.double
+        (g,) = torch.autograd.grad(e.sum(), x, allow_unused=True)
+        assert g is None or g.shape == x.shape
+    e, g = d3.dftd3_host(torch.zeros(0, 5, dtype=torch.int64), torch.zeros(0, 5, 3, dtype=torch.double), par, ref=_ref())
+    assert e.shape == (0, 5) and g.shape == (0, 5, 3)
+
+
+def test_all_padding_structure_and_ghost_only_rows():
+    import tad_dftd3_b200 as d3
+
+    numbers, positions = _batch()
+    numbers = numbers.clone()
+    numbers[2] = 0                                   # a structure that is padding only
+    par = {k: torch.tensor(v, dtype=torch.double) for k, v in PARAM.items()}
+    x = positions.to(DEV).requires_grad_(True)
+    e = d3.dftd3(numbers.to(DEV), x, par, ref=_ref())
+    (g,) = torch.autograd.grad(e.sum(), x)
+    assert (e[2] == 0).all() and (g[2] == 0).all()
+    eo = oracle_energy(numbers, positions, par, 50.0, torch.double)
+    assert_close(e.detach().cpu(), eo, 1e-10, 1e-12, "energies with an empty row")
+
+
+def test_extra_leading_dimensions_and_views():
+    """[2, 3, N] batches, a transposed (non-contiguous) positions view, int32 numbers."""
+    import tad_dftd3_b200 as d3
+
+    numbers, positions = _batch(6)
+    par = {k: torch.tensor(v, dtype=torch.double) for k, v in PARAM.items()}
+    ref = _ref()
+    flat = d3.dftd3(numbers.to(DEV), positions.to(DEV), par, ref=ref)
+    n = numbers.shape[-1]
+    e = d3.dftd3(numbers.reshape(2, 3, n).to(DEV), positions.reshape(2, 3, n, 3).to(DEV), par, ref=ref)
+    assert e.shape == (2, 3, n) and torch.equal(e.reshape(6, n), flat)
+    xt = positions.transpose(-1, -2).contiguous().to(DEV).transpose(-1, -2)      # strides (.., 1, N)
+    assert not xt.is_contiguous()
+    xt.requires_grad_(True)
+    e2 = d3.dftd3(numbers.to(DEV), xt, par, ref=ref)
+    # (the energy + gradient kernel is another instantiation than the energy-only one: last-bit differences)
+    assert_close(e2.detach().cpu(), flat.cpu(), 1e-13, 1e-18, "energies from a non-contiguous view")
+    (g2,) = torch.autograd.grad(e2.sum(), xt)
+    x = positions.to(DEV).requires_grad_(True)
+    e1 = d3.dftd3(numbers.to(DEV), x, par, ref=ref)
+    (g1,) = torch.autograd.grad(e1.sum(), x)
+    assert torch.equal(e1.detach(), e2.detach()) and torch.equal(g1, g2)
+    e3 = d3.dftd3(numbers.to(torch.int32).to(DEV), positions.to(DEV), par, ref=ref)
+    assert torch.equal(e3, flat)
+
+
+def test_parameters_of_other_dtype_and_device():
+    """float32 / CPU / python-float parameters with float64 CUDA positions: values are used as stored
+    (reference README: `torch.tensor(0.49484001)` is float32)."""
+    import tad_dftd3_b200 as d3
+
+    numbers, positions = _batch(3)
+    ref = _ref()
+    z, x = numbers.to(DEV), positions.to(DEV)
+    p32 = {k: torch.tensor(v) for k, v in PARAM.items()}                        # float32 on CPU
+    p32_cuda = {k: v.to(DEV) for k, v in p32.items()}
+    p_as64 = {k: torch.tensor(float(v), dtype=torch.double) for k, v in p32.items()}
+    p_float = {k: float(v) for k, v in p32.items()}
+    e = d3.dftd3(z, x, p_as64, ref=ref)
+    for p in (p32, p32_cuda, p_float):
+        assert torch.equal(d3.dftd3(z, x, p, ref=ref), e)
+    eo = oracle_energy(numbers, positions, p_as64, 50.0, torch.double)
+    assert_close(e.cpu(), eo, 1e-10, 1e-12, "float32-rounded parameters")
+    exact = d3.dftd3(z, x, {k: torch.tensor(v, dtype=torch.double) for k, v in PARAM.items()}, ref=ref)
+    assert not torch.equal(exact, e)                                            # 1e-7 relative apart
+
+
+def test_host_entry_pageable_and_pinned_inputs_agree():
+    """Pageable inputs take the staged pipeline, pinned ones the zero-copy launch: same bits."""
+    import tad_dftd3_b200 as d3
+
+    numbers, positions = _batch(40, seed=5)
+    par = {k: torch.tensor(v, dtype=torch.double) for k, v in PARAM.items()}
+    ref = _ref()
+    e1, g1 = d3.dftd3_host(numbers, positions, par, ref=ref)                     # pageable -> staged
+    e2, g2 = d3.dftd3_host(numbers.pin_memory(), positions.pin_memory(), par, ref=ref)   # pinned -> zero-copy
+    assert np.array_equal(e1.numpy(), e2.numpy()) and np.array_equal(g1.numpy(), g2.numpy())
+    pad = (numbers == 0).numpy()
+    assert (e2.numpy()[pad] == 0).all() and (g2.numpy()[pad] == 0).all()
+    x = positions.to(DEV).requires_grad_(True)
+    ed = d3.dftd3(numbers.to(DEV), x, par, ref=ref)
+    (gd,) = torch.autograd.grad(ed.sum(), x)
+    assert np.array_equal(e2.numpy(), ed.detach().cpu().numpy()) and np.array_equal(g2.numpy(), gd.cpu().numpy())
