@@ -146,3 +146,16 @@ def test_data_tables():
         assert VDW_PAIRWISE(torch.double).shape == (104, 104)
     finally:
         set_vdw_pairwise(None)
+
+
+def test_exception_and_typing_modules_mirror_the_reference():
+    """tad_dftd3.exception.DFTD3Error (reference test_exception.py) and the typing aliases exist under the same names."""
+    import tad_dftd3_b200 as d3
+
+    with pytest.raises(d3.exception.DFTD3Error):
+        raise d3.exception.DFTD3Error
+    assert issubclass(d3.exception.DFTD3Error, Exception)
+    for name in ("DD", "CountingFunction", "DampingFunction", "WeightingFunction", "Molecule", "Size", "Tensor",
+                 "TensorOrTensors", "get_default_device", "get_default_dtype"):
+        assert hasattr(d3.typing, name), name
+    assert d3.typing.get_default_dtype() == torch.get_default_dtype()
