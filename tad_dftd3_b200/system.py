@@ -221,6 +221,12 @@ class SystemRunner:
         # TAD_DFTD3_B200_FULLROW=1 / =0 forces one or the other.
         force = os.environ.get("TAD_DFTD3_B200_FULLROW")
         self.symmetric = self.use_tvec and (force == "0" or (force != "1" and self.jsplit <= 8))
+        # experiment knob: pairs-once sweeps with a capped j-split (fewer, longer CTAs)
+        cap = os.environ.get("TAD_DFTD3_B200_SYM_JSPLIT")
+        if cap and self.use_tvec:
+            self.symmetric = True
+            self.jsplit = int(max(1, min(self.jsplit, int(cap))))
+            s.jsplit = self.jsplit
         s.symmetric, s.tile_stride = int(self.symmetric), 1
         self.sys = s
 
