@@ -33,6 +33,9 @@ from .ops import Settings, _params, _sfx
 
 __all__ = ["dftd3_host", "HostPipeline", "bind_host_thread_to_gpu"]
 
+_PKEYS = (("s6", defaults.S6), ("s8", defaults.S8), ("a1", defaults.A1), ("a2", defaults.A2), ("s9", 0.0),
+          ("alp", defaults.ALP))
+
 
 def bind_host_thread_to_gpu(device_index: int) -> bool:
     """Pin the calling thread to the CPU cores next to GPU `device_index` (NVML's ideal
@@ -67,6 +70,7 @@ class HostPipeline:
             _lib.check(self._lib.d3b200_pipe_create(C.byref(self._pipe)))
         self._work: Optional[Tensor] = None
         self._tables: dict = {}
+        self._fast = None          # (key, weakrefs, prepared call) of the last call with caller-owned outputs
 
     def close(self):
         if self._pipe:
@@ -102,6 +106,24 @@ class HostPipeline:
             grad_out: Optional[Tensor] = None, chunk: int = 0, sync: bool = True):
         from . import disp
 
+        # Repeated calls on the same buffers (MD / optimisation loops, the bench): everything
+        # below was validated and converted before, go straight to the library call.
+        atm = disp._atm_requested(param)
+        pkey = tuple(disp._scalar(param.get(k, d)) for k, d in _PKEYS) + (
+            None if cutoff is None else disp._scalar(cutoff), atm, int(chunk))
+        fkey = (id(numbers), numbers._version, id(positions), id(energy_out), id(grad_out), id(ref), id(g), pkey)
+        hit = self._fast
+        if hit is not None and hit[0] == fkey and energy_out is not None and grad_out is not None \
+                and all(r() is o for r, o in zip(hit[1], (numbers, positions, energy_out, grad_out))):
+            fn, args, nlaunch, outs = hit[2]
+            _lib.launch_count += nlaunch
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream(self.device)
+                _lib.check(fn(*args, C.c_void_p(stream.cuda_stream)))
+                if sync:
+                    stream.synchronize()
+            return outs
+
         if numbers.device.type != "cpu" or positions.device.type != "cpu":
             raise RuntimeError("dftd3_host takes CPU tensors; use dftd3() for tensors already on the GPU")
         if numbers.shape != positions.shape[:-1]:
@@ -125,7 +147,6 @@ class HostPipeline:
 
         if ref is None:
             ref = disp._default_reference(dt, dev)
-        atm = disp._atm_requested(param)
         keys = ("s6", "s8", "a1", "a2", "s9")
         dflt = (defaults.S6, defaults.S8, defaults.A1, defaults.A2, 0.0)
         pv = [disp._scalar(param.get(k, d)) for k, d in zip(keys, dflt)]
@@ -157,6 +178,8 @@ class HostPipeline:
             hit = self._tables[key] = (ref, par, m, (refcn, refc6, rcov_t, r4r2_t, rvdw_t))
         _, par, m, _keep_tables = hit
 
+        g_in = g
+        caller_outputs = energy_out is not None and grad_out is not None
         if g is not None:
             g = g.to(dt).expand(*lead, n).contiguous().reshape(nb, n)
         if energy_out is None:
@@ -177,17 +200,24 @@ class HostPipeline:
             work = self._workspace(int(wsfn(nb, n, int(g is not None), int(atm))))
             _lib.launch_count += 1 if zero_copy else self.chunks(nb, chunk)
             self.last_mode = "zero-copy" if zero_copy else "staged"
+            args = (self._pipe, nb, n, C.c_void_p(z.data_ptr()), C.c_void_p(x.data_ptr()),
+                    C.byref(m), C.byref(par), None if g is None else C.c_void_p(g.data_ptr()),
+                    C.c_void_p(energy_out.data_ptr()), C.c_void_p(grad_out.data_ptr()),
+                    C.c_void_p(work.data_ptr()), C.c_size_t(work.numel()), int(chunk))
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev)
-                _lib.check(fn(self._pipe, nb, n, C.c_void_p(z.data_ptr()), C.c_void_p(x.data_ptr()),
-                              C.byref(m), C.byref(par), None if g is None else C.c_void_p(g.data_ptr()),
-                              C.c_void_p(energy_out.data_ptr()), C.c_void_p(grad_out.data_ptr()),
-                              C.c_void_p(work.data_ptr()), C.c_size_t(work.numel()), int(chunk),
-                              C.c_void_p(stream.cuda_stream)))
+                _lib.check(fn(*args, C.c_void_p(stream.cuda_stream)))
                 # host inputs must outlive the asynchronous copies
-                self._keep = (z, x, g, _keep_tables)
+                self._keep = (z, x, g, work, _keep_tables, m, par)
                 if sync:
                     stream.synchronize()
+            outs = (energy_out.reshape(*lead, n), grad_out.reshape(*lead, n, 3))
+            if caller_outputs and g_in is None:
+                import weakref
+
+                self._fast = (fkey, tuple(weakref.ref(t) for t in (numbers, positions, energy_out, grad_out)),
+                              (fn, args, 1 if zero_copy else self.chunks(nb, chunk), outs), self._keep)
+            return outs
         return energy_out.reshape(*lead, n), grad_out.reshape(*lead, n, 3)
 
 

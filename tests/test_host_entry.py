@@ -90,3 +90,38 @@ def test_host_entry_rejects_device_tensors():
         d3.dftd3_host(z, x, {})
     with pytest.raises(ValueError):
         d3.dftd3_host(torch.tensor([1]), torch.zeros(2, 3), {})
+
+
+def test_host_entry_repeated_calls_follow_the_buffer_contents():
+    """The prepared-call fast path (same buffers again) must see new positions, a changed
+    parameter set must not reuse it, and in-place edits of `numbers` are re-validated."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+
+    numbers, positions = syn.drug_like_batch(9, seed=8, nmin=10, nmax=30)
+    nh, ph = numbers.pin_memory(), positions.pin_memory()
+    e_h = torch.empty(numbers.shape, dtype=torch.double).pin_memory()
+    g_h = torch.empty(*numbers.shape, 3, dtype=torch.double).pin_memory()
+    ref = _ref(torch.double)
+    par = {"s8": torch.tensor(0.7898, dtype=torch.double), "a1": torch.tensor(0.4948, dtype=torch.double),
+           "a2": torch.tensor(5.7308, dtype=torch.double)}
+
+    def device_result(p):
+        x = ph.to(DEV).requires_grad_(True)
+        e = d3.dftd3(nh.to(DEV), x, p, ref=ref)
+        (g,) = torch.autograd.grad(e.sum(), x)
+        return e.detach().cpu().numpy(), g.cpu().numpy()
+
+    for step in range(3):
+        if step:
+            ph.mul_(1.01)                                   # same buffer, new geometry
+        d3.dftd3_host(nh, ph, par, ref=ref, energy_out=e_h, grad_out=g_h)
+        e_d, g_d = device_result(par)
+        assert np.array_equal(e_h.numpy(), e_d) and np.array_equal(g_h.numpy(), g_d)
+    par2 = dict(par, s8=torch.tensor(1.2576, dtype=torch.double))
+    d3.dftd3_host(nh, ph, par2, ref=ref, energy_out=e_h, grad_out=g_h)
+    e_d, g_d = device_result(par2)
+    assert np.array_equal(e_h.numpy(), e_d) and np.array_equal(g_h.numpy(), g_d)
+    nh[0, 0] = 110                                          # in-place edit bumps the version: re-validated
+    with pytest.raises(ValueError):
+        d3.dftd3_host(nh, ph, par2, ref=ref, energy_out=e_h, grad_out=g_h)
