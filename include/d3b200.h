@@ -291,6 +291,13 @@ int d3b200_system_weights_f64(const d3b200_system_f64* sys, const d3b200_params*
 int d3b200_system_tvec_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
 int d3b200_system_pair_f64(const d3b200_system_f64* sys, const d3b200_params* par, int want_grad, void* stream);
 int d3b200_system_cnbwd_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
+/* Damping-parameter gradient of the two-body term for the tiled path (needs the T vectors):
+ * writes the per-row sums scratch[q][jsplit][natoms], q = 0..3 <-> s6, s8, a1, a2
+ * (sum_j C6 dP/dq of rows row_begin..row_end-1; all other scratch entries untouched);
+ * dL/dq = sum_i -1/2 g_i sum_k scratch[q][k][i].  Reference: autograd through
+ * disp.py:300-301, damping/rational.py:68. */
+int d3b200_system_pgrad_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
+int d3b200_system_pgrad_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
 int d3b200_system_cn_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
 int d3b200_system_weights_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);
 int d3b200_system_tvec_f32(const d3b200_system_f32* sys, const d3b200_params* par, void* stream);

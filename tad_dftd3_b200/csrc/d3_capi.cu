@@ -456,6 +456,22 @@ int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int wan
 }
 
 template <typename B>
+int sys_pgrad(const typename SysOf<B>::type* s, const d3b200_params* par, void* stream) {
+  d3::SysArgs<B> a;
+  int rc = sys_fill<B>(a, s, par);
+  if (rc) return rc;
+  if (!s->aux || !s->w) return fail(D3B200_EINVAL, "null pgrad argument%s");
+  if (!a.nelem) return fail(D3B200_EINVAL, "the parameter-gradient sweep needs the T vectors (nelem <= 8)%s");
+  const int nblk = (a.row_end - a.row_begin) / d3::kSysTile;
+  if (nblk == 0) return D3B200_OK;
+  const size_t smem = d3::pair_t_smem_bytes<B>(a.nelem);
+  auto kern = d3::system_pgrad_kernel<B>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<dim3(nblk, a.jsplit), d3::kSysTile, smem, (cudaStream_t)stream>>>(a);
+  return launched("system_pgrad_kernel");
+}
+
+template <typename B>
 int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* stream) {
   d3::SysArgs<B> a;
   int rc = sys_fill<B>(a, s, par);
@@ -637,6 +653,8 @@ int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, co
 int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int g, void* st) { return sys_atm<float>(s, p, r, g, st); }
 int d3b200_system_tvec_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_tvec<double>(s, p, st); }
 int d3b200_system_tvec_f32(const d3b200_system_f32* s, const d3b200_params* p, void* st) { return sys_tvec<float>(s, p, st); }
+int d3b200_system_pgrad_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_pgrad<double>(s, p, st); }
+int d3b200_system_pgrad_f32(const d3b200_system_f32* s, const d3b200_params* p, void* st) { return sys_pgrad<float>(s, p, st); }
 int d3b200_system_cn_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_cn<double>(s, p, st); }
 int d3b200_system_weights_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_weights<double>(s, p, st); }
 int d3b200_system_pair_f64(const d3b200_system_f64* s, const d3b200_params* p, int g, void* st) { return sys_pair<double>(s, p, g, st); }

@@ -402,6 +402,93 @@ __global__ void __launch_bounds__(kSysTile) system_pair_t_kernel(SysArgs<S> A) {
   }
 }
 
+// ---------------------------------------------------------------- parameter gradient (T vectors)
+// Per-row sums behind dL/d(s6, s8, a1, a2) of the two-body term, full-row form
+// (autograd through reference disp.py:300-301 and damping/rational.py:68):
+//   part[0] = sum_j C6 t6                         (dE_i/ds6 = -1/2 ...)
+//   part[1] = sum_j C6 qq t8                      (dE_i/ds8)
+//   part[2] = sum_j C6 (s6 dt6/dR0 + s8 qq dt8/dR0) sqrt(qq)     (dE_i/da1, dR0/da1 = sqrt(qq))
+//   part[3] = sum_j C6 (s6 dt6/dR0 + s8 qq dt8/dR0)              (dE_i/da2)
+// with t_n = 1/(r^n + R0^n), dt6/dR0 = -6 R0^5 t6^2, dt8/dR0 = -8 R0^7 t8^2.  The host
+// contracts them with -1/2 g_i.  Same staging and culling as `system_pair_t_kernel`.
+template <typename S>
+__global__ void __launch_bounds__(kSysTile) system_pgrad_kernel(SysArgs<S> A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int E = A.nelem;
+  Atom4<S>* sj = reinterpret_cast<Atom4<S>*>(smem_raw);
+  Pair2<S>* sb = reinterpret_cast<Pair2<S>*>(sj + kSysTile);
+  S* sT = reinterpret_cast<S*>(sb + kSysTile);                 // [128][E][8]
+  int* sej = reinterpret_cast<int*>(sT + (size_t)kSysTile * E * 8);
+  const int t = threadIdx.x, wsub = t >> 5;
+  const int itile = A.row_begin / kSysTile + blockIdx.x;
+  const int i = itile * kSysTile + t;
+  const Atom4<S> ai = A.atoms[i];
+  const Pair2<S> bi = A.aux[i];
+  const int ei = A.eidx[i];
+  const int eic = ei < 0 ? 0 : ei;
+  const S tiny = tiny_of<S>();
+  S wi[kNRef];
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) wi[a] = A.w[8 * (size_t)i + a];
+  S ibox[6], wbox[6];
+  tile_box(A.box, itile, ibox);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) wbox[k] = A.box[((size_t)itile * 4 + wsub) * 6 + k];
+  const int ntiles = A.natoms / kSysTile;
+  const S s3qi = sqr(S(3)) * bi.a;
+  S p6 = S(0), p8 = S(0), pa1 = S(0), pa2 = S(0);
+  for (int jt = blockIdx.y; jt < ntiles; jt += A.jsplit) {
+    S jbox[6];
+    tile_box(A.box, jt, jbox);
+    if (box_dist2(ibox, jbox) > A.cutoff2) continue;   // CTA-uniform
+    __syncthreads();
+    {
+      const size_t j = (size_t)jt * kSysTile + t;
+      sj[t] = A.atoms[j];
+      sb[t] = A.aux[j];
+      sej[t] = A.eidx[j];
+      const Pair2<S>* src = reinterpret_cast<const Pair2<S>*>(A.tvec + j * E * 8);
+      Pair2<S>* dst = reinterpret_cast<Pair2<S>*>(sT + (size_t)t * E * 8);
+      for (int k = 0; k < 4 * E; ++k) dst[k] = src[k];
+    }
+    __syncthreads();
+    for (int sub = 0; sub < kSysTile / kSysSub; ++sub) {
+      if (box_dist2(wbox, A.box + ((size_t)jt * 4 + sub) * 6) > A.cutoff2) continue;  // warp-uniform
+      for (int jj = 0; jj < kSysSub; ++jj) {
+        const int jl = sub * kSysSub + jj;
+        if (sej[jl] < 0) continue;                    // padding (warp-uniform)
+        const Atom4<S> aj = sj[jl];
+        S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+        S r2 = dx * dx + dy * dy + dz * dz;
+        if (ei >= 0 && r2 <= A.cutoff2 && (jt * kSysTile + jl) != i) {
+          r2 = r2 + tiny;
+          const S* tv = sT + ((size_t)jl * E + eic) * 8;
+          S c6 = wi[0] * tv[0];
+#pragma unroll
+          for (int a = 1; a < kNRef; ++a) c6 += wi[a] * tv[a];
+          const S tq = s3qi * sb[jl].a;               // sqrt(3 q_i q_j)
+          const S qq = tq * tq;
+          const S r0 = A.a1 * tq + A.a2;
+          const S r02 = r0 * r0, r04 = r02 * r02;
+          const S r05 = r04 * r0, r06 = r04 * r02, r07 = r06 * r0, r08 = r04 * r04;
+          const S r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+          const S t6 = frcp(r6 + r06), t8 = frcp(r8 + r08);
+          p6 += c6 * t6;
+          p8 += c6 * (qq * t8);
+          const S dr0 = c6 * (A.s6 * (S(-6) * r05 * (t6 * t6)) + (A.s8 * qq) * (S(-8) * r07 * (t8 * t8)));
+          pa1 += dr0 * tq;
+          pa2 += dr0;
+        }
+      }
+    }
+  }
+  const size_t n = A.natoms, js = A.jsplit, o = (size_t)blockIdx.y * n + i;
+  A.part[o] = p6;
+  A.part[js * n + o] = p8;
+  A.part[2 * js * n + o] = pa1;
+  A.part[3 * js * n + o] = pa2;
+}
+
 template <typename S>
 inline size_t pair_t_smem_bytes(int nelem) {
   return kSysTile * (sizeof(Atom4<S>) + sizeof(Pair2<S>) + sizeof(int)) + (size_t)kSysTile * nelem * 8 * sizeof(S);

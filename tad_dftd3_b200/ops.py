@@ -178,7 +178,7 @@ def _tiled(c: "_Call", order: int) -> bool:
     return c.n > _fused_limit(c.sfx, order)
 
 
-def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None):
+def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None, want_p: bool = False):
     from .system import SystemPlan, SystemRunner
 
     if c.par.s9 != 0.0 and c.st.rvdw_mode != 1:
@@ -187,7 +187,7 @@ def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None):
             "rvdw table only (pass rvdw=None); a dense per-pair rvdw is limited to "
             "structures that fit the fused kernel"
         )
-    es, gs = [], []
+    es, gs, ps = [], [], []
     for b in range(c.nflat):
         z = numbers if (c.nflat == 1 and numbers.dim() == 1 and numbers.dtype == torch.int64) else c.z[b]
         rcov = c.rcov if c.st.rcov_per_element else c.rcov[b]
@@ -199,7 +199,11 @@ def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None):
             gs.append(gr)
         else:
             e = run.run_energy()
+        if want_p:
+            ps.append(run.param_gradient())
         es.append(e)
+    if want_p:
+        return torch.stack(es), (torch.stack(gs) if want_grad else None), torch.stack(ps)
     return torch.stack(es), (torch.stack(gs) if want_grad else None)
 
 
@@ -220,10 +224,8 @@ def _run_vjp(numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6, st, want_
     c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 0)
     if _tiled(c, 0):
         if want_p:
-            raise NotImplementedError(
-                "damping-parameter gradients for structures beyond the fused-kernel "
-                f"limit ({c.n} atoms) are not available yet"
-            )
+            _, gr, pg = _tiled_run(c, c.per_atom(g), True, numbers, True)
+            return gr.reshape(*c.lead, c.n, 3), pg.reshape(*c.lead, NPAR)
         _, gr = _tiled_run(c, c.per_atom(g), True, numbers)
         return gr.reshape(*c.lead, c.n, 3), c.new(c.nflat, NPAR, zero=True).reshape(*c.lead, NPAR)
     grad = c.new(c.nflat, c.n, 3)

@@ -290,6 +290,37 @@ class SystemRunner:
         finally:
             self.sys.tile_stride = keep
 
+    def param_gradient(self) -> Tensor:
+        """dL/d(s6, s8, a1, a2, s9) with L = sum_i g_i E_i for this structure (single GPU; after
+        `weights()`).  Two-body part: one more full-row sweep (`d3b200_system_pgrad_*`) whose
+        per-row sums are contracted with -g/2; s9: the three-body energies alone, divided by s9."""
+        if not self.use_tvec:
+            raise NotImplementedError(
+                "damping-parameter gradients of structures beyond the fused-kernel limit need "
+                "the T-vector sweeps (at most 8 distinct elements)")
+        npad, js = self.plan.npad, self.jsplit
+        self.scratch.zero_()
+        keep = self.sys.symmetric
+        self.sys.symmetric = 0
+        try:
+            self._call("pgrad", None)
+        finally:
+            self.sys.symmetric = keep
+        rows = self.scratch[: 4 * js * npad].view(4, js, npad).sum(1)           # [4, npad]
+        g = self.auxt[:, 1]
+        out = torch.zeros(5, dtype=self.plan.dtype, device=self.plan.device)
+        out[:4] = rows @ (-0.5 * g)
+        if self.par.s9 != 0.0:
+            e_atm = torch.zeros(npad, dtype=self.plan.dtype, device=self.plan.device)
+            keep_e = self.sys.energy
+            self.sys.energy = e_atm.data_ptr()
+            try:
+                self.sweep_atm(False)
+            finally:
+                self.sys.energy = keep_e
+            out[4] = (e_atm * g).sum() / self.par.s9
+        return out
+
     # single-GPU drivers -----------------------------------------------------
     def run_energy(self) -> Tensor:
         self.sweep_cn()

@@ -234,6 +234,18 @@ def test_tiled_path_reference_runs(runs, case, force_tiled):
         assert_close(out["grad"], c["grad"], RTOL, ATOL, case + " grad")
 
 
+@pytest.mark.parametrize("case", ["c1_f64", "c2_f64", "mols6_f64", "c1_atm_f64", "c2_atm_f64", "mols6_atm_f64"])
+def test_tiled_path_parameter_gradients(runs, case, force_tiled):
+    """dL/d(s6, s8, a1, a2) through the tiled sweeps (`d3b200_system_pgrad_*`), with and without the
+    three-body term, against the unmodified reference's autograd values."""
+    c = runs.case(case)
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    out = run_cuda(numbers, positions, param, cutoff, dtype, g=g, pgrad=True, rvdw_table=is_atm(c))
+    assert_close(out["energy"], c["energy"], RTOL, ATOL, case + " energy")
+    assert_close(out["grad"], c["grad"], RTOL, ATOL, case + " grad")
+    assert_close(out["pgrad"], c["pgrad"], RTOL, ATOL, case + " pgrad")
+
+
 def test_tiled_equals_fused_on_cluster(monkeypatch):
     """700-atom water cluster (several tiles, culling active at cutoff 20):
     tiled path vs fused one-CTA kernel vs CPU oracle."""
