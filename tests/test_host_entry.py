@@ -125,3 +125,26 @@ def test_host_entry_repeated_calls_follow_the_buffer_contents():
     nh[0, 0] = 110                                          # in-place edit bumps the version: re-validated
     with pytest.raises(ValueError):
         d3.dftd3_host(nh, ph, par2, ref=ref, energy_out=e_h, grad_out=g_h)
+
+
+def test_host_entry_zero_copy_large_structures():
+    """Structures of 500-600 atoms: the staged positions no longer fit the reduction tiles
+    (other shared-memory path of the zero-copy form); pinned zero-copy == device path bitwise."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+
+    numbers, positions = syn.drug_like_batch(3, nmin=500, nmax=600, seed=12)
+    par = {"s8": torch.tensor(0.7898, dtype=torch.double), "a1": torch.tensor(0.4948, dtype=torch.double),
+           "a2": torch.tensor(5.7308, dtype=torch.double)}
+    ref = _ref(torch.double)
+    pipe = d3.HostPipeline()
+    e, g = pipe.run(numbers.pin_memory(), positions.pin_memory(), par, ref=ref)
+    assert pipe.last_mode == "zero-copy"
+    x = positions.to(DEV).requires_grad_(True)
+    ed = d3.dftd3(numbers.to(DEV), x, par, ref=ref)
+    (gd,) = torch.autograd.grad(ed.sum(), x)
+    assert np.array_equal(e.numpy(), ed.detach().cpu().numpy())
+    assert np.array_equal(g.numpy(), gd.cpu().numpy())
+    pad = (numbers == 0).numpy()
+    assert pad.any() and (e.numpy()[pad] == 0).all() and (g.numpy()[pad] == 0).all()
+    pipe.close()
