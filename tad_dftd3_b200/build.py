@@ -23,7 +23,7 @@ STAMP = os.path.join(HERE, ".libd3b200.stamp")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--use_fast_math=false" if False else "-Xptxas=-v",
+    "-Xptxas=-v",            # register / spill report -> ptxas_info.log (no fast-math: fp64 parity)
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
