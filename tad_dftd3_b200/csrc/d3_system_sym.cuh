@@ -34,15 +34,73 @@ __device__ __forceinline__ bool sym_row_tile(const SymArgs<S>& P, int& itile) {
   return itile * kSysTile < P.sys.row_end;
 }
 
+// squared distance of a point to a box {min xyz, max xyz}
+template <typename S>
+__device__ __forceinline__ S box_point_dist2(const S* box, const Atom4<S>& a) {
+  S d2 = S(0);
+  const S x[3] = {a.x, a.y, a.z};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const S lo = box[k] - x[k], hi = x[k] - box[3 + k];
+    S d = lo > hi ? lo : hi;
+    d = d > S(0) ? d : S(0);
+    d2 += d * d;
+  }
+  return d2;
+}
+
+// Candidate partners of one warp in the staged j-tile: those within `cut2` of the box of the
+// warp's 32 rows (a 32-atom box test alone lets through about as many partners that no row can
+// reach as ones that count).  The warp compacts their tile-local indices, in order, into
+// `cand` (padded with 255 up to a multiple of the chunk) and returns their number.  On the
+// diagonal tile only partners at or behind the warp's first row can have j > i.
+template <typename S>
+__device__ __forceinline__ int sym_candidates(const Atom4<S>* sj, const S* box, const S* wbox, int jt, int itile,
+                                              int wsub, S cut2, unsigned char* cand, int lane) {
+  int n = 0;
+#pragma unroll
+  for (int sub = 0; sub < kSysTile / kSysSub; ++sub) {
+    if (jt == itile && sub < wsub) continue;
+    if (box_dist2(wbox, box + ((size_t)jt * 4 + sub) * 6) > cut2) continue;   // warp-uniform
+    const int jl = sub * kSysSub + lane;
+    const bool ok = box_point_dist2(wbox, sj[jl]) <= cut2;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) cand[n + __popc(m & ((1u << lane) - 1))] = (unsigned char)jl;
+    n += __popc(m);
+  }
+  if (lane < kSymChunk) cand[n + lane] = 255;        // tail of the last chunk
+  __syncwarp();
+  return n;
+}
+
+// The j-tiles a CTA walks are itile + blockIdx.y + k * jsplit, k = 0, 1, ...; most of them are
+// out of reach.  Lanes test 32 of them at once (tile box against the row tile's box) and the
+// warp then visits only the set bits -- every warp of the CTA computes the same mask, so the
+// CTA-wide staging barriers stay aligned.
+template <typename S>
+__device__ __forceinline__ unsigned sym_tile_mask(const S* box, const S* ibox, int jt_first, int jsplit, int k0,
+                                                  int ntiles, S cut2, int lane) {
+  const int jt = jt_first + (k0 + lane) * jsplit;
+  bool ok = false;
+  if (jt < ntiles) {
+    S jbox[6];
+    tile_box(box, jt, jbox);
+    ok = box_dist2(ibox, jbox) <= cut2;
+  }
+  return __ballot_sync(0xffffffffu, ok);
+}
+
 // ---------------------------------------------------------------- CN sweep
 template <typename S>
 __global__ void __launch_bounds__(kSysTile) sym_cn_kernel(SymArgs<S> P) {
   const SysArgs<S>& A = P.sys;
   __shared__ Atom4<S> sj[kSysTile];
   __shared__ S sS[kSysTile / 32][kSymChunk * kSymPitch];
+  __shared__ unsigned char scand[kSysTile / 32][kSysTile + kSymChunk];
   int itile;
   if (!sym_row_tile(P, itile)) return;
   const int t = threadIdx.x, lane = t & 31, wsub = t >> 5;
+  unsigned char* cand = scand[wsub];
   const int i = itile * kSysTile + t;
   const Atom4<S> ai = A.atoms[i];
   const S tiny = tiny_of<S>();
@@ -53,30 +111,32 @@ __global__ void __launch_bounds__(kSysTile) sym_cn_kernel(SymArgs<S> P) {
   const int ntiles = A.natoms / kSysTile;
   S* S_ = sS[wsub];
   S cn = S(0);
-  for (int jt = itile + blockIdx.y; jt < ntiles; jt += A.jsplit) {
-    S jbox[6];
-    tile_box(A.box, jt, jbox);
-    if (box_dist2(ibox, jbox) > A.cn_cutoff2) continue;   // CTA-uniform
+  const int jt_first = itile + blockIdx.y;
+  for (int k0 = 0; jt_first + k0 * A.jsplit < ntiles; k0 += 32)
+  for (unsigned tmask = sym_tile_mask<S>(A.box, ibox, jt_first, A.jsplit, k0, ntiles, A.cn_cutoff2, lane); tmask;
+       tmask &= tmask - 1) {
+    const int jt = jt_first + (k0 + __ffs(tmask) - 1) * A.jsplit;      // CTA-uniform
     __syncthreads();
     sj[t] = A.atoms[(size_t)jt * kSysTile + t];
     __syncthreads();
-    for (int sub = 0; sub < kSysTile / kSysSub; ++sub) {
-      if (jt == itile && sub < wsub) continue;            // partners below the diagonal
-      if (box_dist2(wbox, A.box + ((size_t)jt * 4 + sub) * 6) > A.cn_cutoff2) continue;  // warp-uniform
-      for (int c0 = 0; c0 < kSysSub; c0 += kSymChunk) {
+    {
+      const int ncand = sym_candidates<S>(sj, A.box, wbox, jt, itile, wsub, A.cn_cutoff2, cand, lane);
+      for (int c0 = 0; c0 < ncand; c0 += kSymChunk) {
 #pragma unroll 4
         for (int jj = 0; jj < kSymChunk; ++jj) {
-          const int jl = sub * kSysSub + c0 + jj;
-          const int j = jt * kSysTile + jl;
-          const Atom4<S> aj = sj[jl];
-          S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
-          S r2 = dx * dx + dy * dy + dz * dz;
+          const int jl = cand[c0 + jj];
           S v = S(0);
-          if (r2 <= A.cn_cutoff2 && j > i) {
-            S rinv = frsq(r2 + tiny);
-            S x = fmx(A.kcn - (ai.rk + aj.rk) * rinv, S(-700));
-            v = frcp(S(1) + fex(x));
-            cn += v;
+          if (jl < kSysTile) {                            // warp-uniform (255 = chunk padding)
+            const int j = jt * kSysTile + jl;
+            const Atom4<S> aj = sj[jl];
+            S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+            S r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 <= A.cn_cutoff2 && j > i) {
+              S rinv = frsq(r2 + tiny);
+              S x = fmx(A.kcn - (ai.rk + aj.rk) * rinv, S(-700));
+              v = frcp(S(1) + fex(x));
+              cn += v;
+            }
           }
           S_[jj * kSymPitch + lane] = v;
         }
@@ -89,7 +149,7 @@ __global__ void __launch_bounds__(kSysTile) sym_cn_kernel(SymArgs<S> P) {
           for (int r = 0; r < kSymChunk; ++r) s += S_[col * kSymPitch + r0 + r];
 #pragma unroll
           for (int o = kSymChunk; o < 32; o <<= 1) s += shx(s, o);
-          if (lane < kSymChunk && s != S(0)) red_add(A.cn + (size_t)jt * kSysTile + sub * kSysSub + c0 + col, s);
+          if (lane < kSymChunk && s != S(0)) red_add(A.cn + (size_t)jt * kSysTile + cand[c0 + col], s);
         }
         __syncwarp();
       }
@@ -130,16 +190,18 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
   for (int k = 0; k < 6; ++k) wbox[k] = A.box[((size_t)itile * 4 + wsub) * 6 + k];
   S* S_ = sSall + (size_t)wsub * 3 * kSymChunk * kSymPitch;
   S* Xi = sXi + wsub * 32 * 4;
+  unsigned char* cand = reinterpret_cast<unsigned char*>(sej + kSysTile) + wsub * (kSysTile + kSymChunk);
   Xi[lane * 4] = ai.x; Xi[lane * 4 + 1] = ai.y; Xi[lane * 4 + 2] = ai.z;
   __syncwarp();
   const int ntiles = A.natoms / kSysTile;
   const S gi = bi.b;
   const S s3qi = sqr(S(3)) * bi.a;
   S e_i = S(0), gx = S(0), gy = S(0), gz = S(0), decn = S(0);
-  for (int jt = itile + blockIdx.y; jt < ntiles; jt += A.jsplit) {
-    S jbox[6];
-    tile_box(A.box, jt, jbox);
-    if (box_dist2(ibox, jbox) > A.cutoff2) continue;   // CTA-uniform
+  const int jt_first = itile + blockIdx.y;
+  for (int k0 = 0; jt_first + k0 * A.jsplit < ntiles; k0 += 32)
+  for (unsigned tmask = sym_tile_mask<S>(A.box, ibox, jt_first, A.jsplit, k0, ntiles, A.cutoff2, lane); tmask;
+       tmask &= tmask - 1) {
+    const int jt = jt_first + (k0 + __ffs(tmask) - 1) * A.jsplit;      // CTA-uniform
     __syncthreads();
     {
       const size_t j = (size_t)jt * kSysTile + t;
@@ -156,15 +218,15 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
       }
     }
     __syncthreads();
-    for (int sub = 0; sub < kSysTile / kSysSub; ++sub) {
-      if (jt == itile && sub < wsub) continue;
-      if (box_dist2(wbox, A.box + ((size_t)jt * 4 + sub) * 6) > A.cutoff2) continue;  // warp-uniform
-      for (int c0 = 0; c0 < kSysSub; c0 += kSymChunk) {
+    {
+      const int ncand = sym_candidates<S>(sj, A.box, wbox, jt, itile, wsub, A.cutoff2, cand, lane);
+      for (int c0 = 0; c0 < ncand; c0 += kSymChunk) {
 #pragma unroll 2
         for (int jj = 0; jj < kSymChunk; ++jj) {
-          const int jl = sub * kSysSub + c0 + jj;
+          const int jlr = cand[c0 + jj];                  // 255 = chunk padding (warp-uniform)
+          const int jl = jlr & (kSysTile - 1);
           const int j = jt * kSysTile + jl;
-          const int ej = sej[jl];
+          const int ej = jlr < kSysTile ? sej[jl] : -1;
           const Atom4<S> aj = sj[jl];
           S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
           S r2 = dx * dx + dy * dy + dz * dz;
@@ -226,7 +288,7 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
         __syncwarp();
         {
           const int col = lane % kSymChunk, r0 = (lane / kSymChunk) * kSymChunk;
-          const int jl = sub * kSysSub + c0 + col;
+          const int jl = cand[c0 + col] & (kSysTile - 1);  // (padding columns sum to zero: no atomics)
           const Atom4<S> aj = sj[jl];
           S se = S(0), sf = S(0), sfx = S(0), sfy = S(0), sfz = S(0), sd = S(0);
 #pragma unroll 4
@@ -273,7 +335,8 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
 template <typename S>
 inline size_t sym_pair_smem_bytes(int nelem) {
   return kSysTile * (sizeof(Atom4<S>) + sizeof(Pair2<S>) + sizeof(int)) +
-         ((size_t)kSysTile * nelem * 16 + 4 * 3 * kSymChunk * kSymPitch + 4 * 32 * 4) * sizeof(S) + 64;
+         ((size_t)kSysTile * nelem * 16 + 4 * 3 * kSymChunk * kSymPitch + 4 * 32 * 4) * sizeof(S) +
+         4 * (kSysTile + kSymChunk) + 64;
 }
 
 // ---------------------------------------------------------------- CN backward
@@ -284,9 +347,11 @@ __global__ void __launch_bounds__(kSysTile) sym_cnbwd_kernel(SymArgs<S> P) {
   __shared__ S sd[kSysTile];
   __shared__ S sS[kSysTile / 32][kSymChunk * kSymPitch];
   __shared__ S sXi[kSysTile / 32][32 * 4];
+  __shared__ unsigned char scand[kSysTile / 32][kSysTile + kSymChunk];
   int itile;
   if (!sym_row_tile(P, itile)) return;
   const int t = threadIdx.x, lane = t & 31, wsub = t >> 5;
+  unsigned char* cand = scand[wsub];
   const int i = itile * kSysTile + t;
   const Atom4<S> ai = A.atoms[i];
   const S dci = A.decn[i];
@@ -301,27 +366,28 @@ __global__ void __launch_bounds__(kSysTile) sym_cnbwd_kernel(SymArgs<S> P) {
   __syncwarp();
   const int ntiles = A.natoms / kSysTile;
   S gx = S(0), gy = S(0), gz = S(0);
-  for (int jt = itile + blockIdx.y; jt < ntiles; jt += A.jsplit) {
-    S jbox[6];
-    tile_box(A.box, jt, jbox);
-    if (box_dist2(ibox, jbox) > A.cn_cutoff2) continue;
+  const int jt_first = itile + blockIdx.y;
+  for (int k0 = 0; jt_first + k0 * A.jsplit < ntiles; k0 += 32)
+  for (unsigned tmask = sym_tile_mask<S>(A.box, ibox, jt_first, A.jsplit, k0, ntiles, A.cn_cutoff2, lane); tmask;
+       tmask &= tmask - 1) {
+    const int jt = jt_first + (k0 + __ffs(tmask) - 1) * A.jsplit;      // CTA-uniform
     __syncthreads();
     sj[t] = A.atoms[(size_t)jt * kSysTile + t];
     sd[t] = A.decn[(size_t)jt * kSysTile + t];
     __syncthreads();
-    for (int sub = 0; sub < kSysTile / kSysSub; ++sub) {
-      if (jt == itile && sub < wsub) continue;
-      if (box_dist2(wbox, A.box + ((size_t)jt * 4 + sub) * 6) > A.cn_cutoff2) continue;
-      for (int c0 = 0; c0 < kSysSub; c0 += kSymChunk) {
+    {
+      const int ncand = sym_candidates<S>(sj, A.box, wbox, jt, itile, wsub, A.cn_cutoff2, cand, lane);
+      for (int c0 = 0; c0 < ncand; c0 += kSymChunk) {
 #pragma unroll 2
         for (int jj = 0; jj < kSymChunk; ++jj) {
-          const int jl = sub * kSysSub + c0 + jj;
+          const int jlr = cand[c0 + jj];                  // 255 = chunk padding (warp-uniform)
+          const int jl = jlr & (kSysTile - 1);
           const int j = jt * kSysTile + jl;
           const Atom4<S> aj = sj[jl];
           S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
           S r2 = dx * dx + dy * dy + dz * dz;
           S c = S(0);
-          if (r2 <= A.cn_cutoff2 && r2 >= eps && j > i) {
+          if (jlr < kSysTile && r2 <= A.cn_cutoff2 && r2 >= eps && j > i) {
             S rinv = frsq(r2 + tiny);
             S rk = ai.rk + aj.rk;
             S e = fex(fmx(A.kcn - rk * rinv, S(-700)));
@@ -335,7 +401,7 @@ __global__ void __launch_bounds__(kSysTile) sym_cnbwd_kernel(SymArgs<S> P) {
         __syncwarp();
         {
           const int col = lane % kSymChunk, r0 = (lane / kSymChunk) * kSymChunk;
-          const int jl = sub * kSysSub + c0 + col;
+          const int jl = cand[c0 + col] & (kSysTile - 1);
           const Atom4<S> aj = sj[jl];
           S sc = S(0), sx = S(0), sy = S(0), sz = S(0);
 #pragma unroll 4
