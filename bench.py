@@ -320,6 +320,10 @@ def main():
 
     # ---- the hot path, inputs resident: one fused launch = energies + gradient
     call = ops._Call(numbers, positions, p, rcov_t, r4r2_t, None, refcn, refc6, st, 0)
+    # scheduling hint, as dftd3() applies it from the second call with the same numbers tensor on:
+    # largest structures first (computed once, outside the timed region)
+    order_hint = ops.batch_order(call.z) if os.environ.get("D3B200_NO_ORDER_HINT") != "1" else None
+    call.model.batch_order = order_hint.data_ptr() if order_hint is not None else None
     energy = torch.empty(numbers.shape, dtype=dt, device=dev)
     grad = torch.empty(*numbers.shape, 3, dtype=dt, device=dev)
     fn = getattr(lib, f"d3b200_batch_vjp_{args.dtype}")
@@ -437,6 +441,9 @@ def main():
                           "1 s untimed pre-heat under the clock sampler",
                 "parallelism": f"structures sharded over {world} GPU(s), no data-path collective",
                 "tables": "synthetic C6 table (reference-c6.pt unavailable offline)",
+                "schedule": "CTAs take the structures largest first (d3b200_model.batch_order, computed once per numbers "
+                            "tensor; dftd3() does the same from the second call with the same tensor on; not used by the zero-copy "
+                            "end-to-end form, where it bunches the PCIe requests)",
                 "checks": {"all_outputs_finite": True, "max_net_force_per_structure": net_force},
             },
             "e2e": {

@@ -67,7 +67,11 @@ typedef struct d3b200_params {
  *               must be symmetric, K[z1][z2][a][b] == K[z2][z1][b][a];
  *  rvdw       : ATM only. rvdw_mode 0: absent, 1: `[104][104]` element-pair
  *               table, 2: dense `[nbatch][natoms][natoms]` (the reference's
- *               `rvdw=` keyword, disp.py:143-146). */
+ *               `rvdw=` keyword, disp.py:143-146).
+ *  batch_order: optional scheduling hint `[nbatch]` (a permutation of 0..nbatch-1,
+ *               device or mapped host memory; NULL = identity): CTA k works on
+ *               structure batch_order[k].  Largest structures first keeps the last
+ *               wave of CTAs short; results do not depend on it. */
 typedef struct d3b200_model_f64 {
   const double* rcov;
   const double* r4r2;
@@ -77,6 +81,7 @@ typedef struct d3b200_model_f64 {
   const double* refc6;
   const double* rvdw;
   int rvdw_mode;
+  const int32_t* batch_order;
 } d3b200_model_f64;
 
 typedef struct d3b200_model_f32 {
@@ -88,6 +93,7 @@ typedef struct d3b200_model_f32 {
   const float* refc6;
   const float* rvdw;
   int rvdw_mode;
+  const int32_t* batch_order;
 } d3b200_model_f32;
 
 int d3b200_abi_version(void);

@@ -35,6 +35,7 @@ class Model(C.Structure):
         ("refc6", C.c_void_p),
         ("rvdw", C.c_void_p),
         ("rvdw_mode", C.c_int),
+        ("batch_order", C.c_void_p),
     ]
 
 

@@ -104,6 +104,7 @@ int fill_common(d3::MolArgs<S>& a, int nbatch, int natoms, const int64_t* number
   a.refc6 = m->refc6;
   a.rvdw = m->rvdw;
   a.rvdw_mode = m->rvdw_mode;
+  a.order = m->batch_order;
   auto mk = [&](double v, double d) { return d3::make<S, B>((B)v, (B)d); };
   a.s6 = mk(par->s6, dpar ? dpar->s6 : 0.0);
   a.s8 = mk(par->s8, dpar ? dpar->s8 : 0.0);
@@ -297,6 +298,8 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
   char* d_atm = w;
   const size_t atm_per = workspace_bytes<B>(1, natoms, atm);
 
+  typename ModelOf<B>::type chunk_model = *model;
+  chunk_model.batch_order = nullptr;                 // the hint refers to the whole batch, not to a chunk
   cudaError_t e;
 #define D3_CK(call, what) if ((e = (call)) != cudaSuccess) return cuda_fail(e, what)
   D3_CK(cudaEventRecord(pipe->start, (cudaStream_t)stream), "cudaEventRecord");
@@ -310,7 +313,7 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
     D3_CK(cudaEventRecord(pipe->ev_in[k], pipe->in), "cudaEventRecord");
     cudaStream_t cs = pipe->comp[k & 1];
     D3_CK(cudaStreamWaitEvent(cs, pipe->ev_in[k], 0), "cudaStreamWaitEvent");
-    int rc = vjp_impl<B>(nb, natoms, d_z + o, d_x + 3 * o, model, par, h_g ? d_g + o : nullptr,
+    int rc = vjp_impl<B>(nb, natoms, d_z + o, d_x + 3 * o, &chunk_model, par, h_g ? d_g + o : nullptr,
                          h_energy ? d_e + o : nullptr, d_gr + 3 * o, nullptr,
                          atm ? d_atm + (size_t)lo * atm_per : nullptr, (size_t)nb * atm_per, cs);
     if (rc) return rc;

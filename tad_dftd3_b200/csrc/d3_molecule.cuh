@@ -55,6 +55,7 @@ struct MolArgs {
   B* dgrad;
   B* dpgrad;
   S* work;                  // ATM scratch: sqrt|C6| per structure, [nbatch][N][N]
+  const int* order;         // optional: CTA k works on structure order[k] (scheduling hint)
   int host_io;              // molecule_kernel_v2: numbers / positions / energy / grad may live in mapped HOST
                             // memory -> every global access of these arrays fully coalesced
 };
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = A.natoms;
-  const int b = blockIdx.x;
+  const int b = A.order ? A.order[blockIdx.x] : blockIdx.x;
   const int t = threadIdx.x;
   const int nt = blockDim.x;
 

@@ -98,7 +98,7 @@ template <typename S, bool WANT_G, bool QE>
 __global__ void __launch_bounds__(32 * kV2Warps) molecule_kernel_v2(MolArgs<S> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = A.natoms;
-  const int b = blockIdx.x;
+  const int b = A.order ? A.order[blockIdx.x] : blockIdx.x;
   const int t = threadIdx.x;
   constexpr int nt = 32 * kV2Warps;
   constexpr int nw = kV2Warps;

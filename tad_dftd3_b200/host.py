@@ -200,6 +200,8 @@ class HostPipeline:
             work = self._workspace(int(wsfn(nb, n, int(g is not None), int(atm))))
             _lib.launch_count += 1 if zero_copy else self.chunks(nb, chunk)
             self.last_mode = "zero-copy" if zero_copy else "staged"
+            # (no `batch_order` hint here: with largest-first scheduling the CTAs of a wave finish
+            # together and their PCIe requests arrive in bursts -- measured 0.65 ms against 0.61 ms)
             args = (self._pipe, nb, n, C.c_void_p(z.data_ptr()), C.c_void_p(x.data_ptr()),
                     C.byref(m), C.byref(par), None if g is None else C.c_void_p(g.data_ptr()),
                     C.c_void_p(energy_out.data_ptr()), C.c_void_p(grad_out.data_ptr()),

@@ -86,6 +86,42 @@ def _as(t: Tensor, dtype, device) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_order_cache: dict = {}   # id(numbers) -> [weakref, version, calls seen, order tensor or None]
+ORDER_MIN_BATCH = 1184    # two waves of CTAs on 148 SMs: below that the schedule does not matter
+
+
+def batch_order(z: Tensor) -> Tensor:
+    """Scheduling hint of the batch kernels (`d3b200_model.batch_order`): structures sorted by
+    their number of real atoms, largest first, so that the last wave of CTAs consists of the
+    cheapest structures.  `z` is the flattened `[nflat, N]` numbers tensor (any device)."""
+    counts = (z != 0).sum(-1)
+    return torch.argsort(counts, descending=True, stable=True).to(torch.int32)
+
+
+def _cached_order(numbers: Tensor, z: Tensor):
+    """Order hint for a numbers tensor that keeps coming back (MD / optimisation loops, repeated
+    evaluations): computed on the second call with the same tensor, reused afterwards; a one-off
+    call never pays for it."""
+    import weakref
+
+    if z.shape[0] < ORDER_MIN_BATCH or _is_functorch(numbers) or os.environ.get("D3B200_NO_ORDER_HINT") == "1":
+        return None
+    key = id(numbers)
+    hit = _order_cache.get(key)
+    if hit is None or hit[0]() is not numbers or hit[1] != numbers._version:
+        if len(_order_cache) > 64:
+            _order_cache.clear()
+        try:
+            _order_cache[key] = [weakref.ref(numbers), numbers._version, 1, None]
+        except TypeError:  # pragma: no cover
+            pass
+        return None
+    hit[2] += 1
+    if hit[3] is None:
+        hit[3] = batch_order(z)
+    return hit[3] if hit[3].shape[0] == z.shape[0] else None
+
+
 class _Call:
     """Flattened, contiguous device views of one call + the C structs."""
 
@@ -134,6 +170,8 @@ class _Call:
         m.refcn, m.refc6 = self.refcn.data_ptr(), self.refc6.data_ptr()
         m.rvdw = self.rvdw.data_ptr() if self.rvdw is not None else None
         m.rvdw_mode = int(st.rvdw_mode)
+        self.order = _cached_order(numbers, self.z) if order == 0 else None
+        m.batch_order = self.order.data_ptr() if self.order is not None else None
         self.model = m
         self.sfx = _sfx(dt)
         # ATM scratch (sqrt|C6| matrix per structure)

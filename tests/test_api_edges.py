@@ -121,3 +121,38 @@ def test_host_entry_pageable_and_pinned_inputs_agree():
     ed = d3.dftd3(numbers.to(DEV), x, par, ref=ref)
     (gd,) = torch.autograd.grad(ed.sum(), x)
     assert np.array_equal(e2.numpy(), ed.detach().cpu().numpy()) and np.array_equal(g2.numpy(), gd.cpu().numpy())
+
+
+def test_batch_order_hint_does_not_change_results():
+    """From the second call with the same numbers tensor on, CTAs take the structures largest first
+    (`d3b200_model.batch_order`); energies and gradients must stay bitwise the same."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import ops
+    from tad_dftd3_b200 import synthetic as syn
+
+    numbers, positions = syn.drug_like_batch(1300, seed=21, nmin=4, nmax=14)
+    assert numbers.shape[0] >= ops.ORDER_MIN_BATCH
+    par = {k: torch.tensor(v, dtype=torch.double) for k, v in PARAM.items()}
+    ref = _ref()
+    z = numbers.to(DEV)
+    outs = []
+    for _ in range(3):
+        x = positions.to(DEV).requires_grad_(True)
+        e = d3.dftd3(z, x, par, ref=ref)
+        (g,) = torch.autograd.grad(e.sum(), x)
+        outs.append((e.detach().clone(), g.clone()))
+    assert ops._order_cache[id(z)][3] is not None            # the hint was in use for calls 2 and 3
+    order = ops._order_cache[id(z)][3].long()
+    counts = (z != 0).sum(-1)
+    assert torch.equal(torch.sort(order).values, torch.arange(z.shape[0], device=DEV))
+    assert bool((counts[order][:-1] >= counts[order][1:]).all())
+    for e, g in outs[1:]:
+        assert torch.equal(e, outs[0][0]) and torch.equal(g, outs[0][1])
+    nh, ph = numbers.pin_memory(), positions.pin_memory()
+    e_h = torch.empty(numbers.shape, dtype=torch.double).pin_memory()
+    g_h = torch.empty(*numbers.shape, 3, dtype=torch.double).pin_memory()
+    for _ in range(3):
+        e_h.zero_(); g_h.zero_()
+        d3.dftd3_host(nh, ph, par, ref=ref, energy_out=e_h, grad_out=g_h)
+        assert np.array_equal(e_h.numpy(), outs[0][0].cpu().numpy())
+        assert np.array_equal(g_h.numpy(), outs[0][1].cpu().numpy())
