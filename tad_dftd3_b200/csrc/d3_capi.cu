@@ -383,7 +383,7 @@ int sys_cn(const typename SysOf<B>::type* s, const d3b200_params* par, void* str
   if (nblk == 0) return D3B200_OK;
   if (s->symmetric) {
     d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
-    d3::sym_cn_kernel<B><<<dim3(sym_tiles(s), a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    d3::sym_cn_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
     return launched("sym_cn_kernel");
   }
   d3::system_cn_kernel<B><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
@@ -428,7 +428,7 @@ int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int wan
     if (!s->energy) return fail(D3B200_EINVAL, "symmetric pair sweep needs the energy array%s");
     d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
     const size_t smem = d3::sym_pair_smem_bytes<B>(a.nelem);
-    const dim3 grid(sym_tiles(s), a.jsplit);
+    const dim3 grid(a.jsplit, sym_tiles(s));
     if (want_grad) {
       auto kern = d3::sym_pair_t_kernel<B, true>;
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -484,7 +484,7 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
   if (nblk == 0) return D3B200_OK;
   if (s->symmetric) {
     d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
-    d3::sym_cnbwd_kernel<B><<<dim3(sym_tiles(s), a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    d3::sym_cnbwd_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
     return launched("sym_cnbwd_kernel");
   }
   d3::system_cnbwd_kernel<B><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);

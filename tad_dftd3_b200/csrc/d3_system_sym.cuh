@@ -30,7 +30,9 @@ struct SymArgs {
 
 template <typename S>
 __device__ __forceinline__ bool sym_row_tile(const SymArgs<S>& P, int& itile) {
-  itile = P.sys.row_begin / kSysTile + blockIdx.x * P.tile_stride;
+  // grid = (jsplit, row tiles): the CTAs of the early row tiles (which walk the most j-tiles of the
+  // triangle J >= I) are scheduled first, the cheap ones make up the tail
+  itile = P.sys.row_begin / kSysTile + blockIdx.y * P.tile_stride;
   return itile * kSysTile < P.sys.row_end;
 }
 
@@ -73,7 +75,7 @@ __device__ __forceinline__ int sym_candidates(const Atom4<S>* sj, const S* box, 
   return n;
 }
 
-// The j-tiles a CTA walks are itile + blockIdx.y + k * jsplit, k = 0, 1, ...; most of them are
+// The j-tiles a CTA walks are itile + blockIdx.x + k * jsplit, k = 0, 1, ...; most of them are
 // out of reach.  Lanes test 32 of them at once (tile box against the row tile's box) and the
 // warp then visits only the set bits -- every warp of the CTA computes the same mask, so the
 // CTA-wide staging barriers stay aligned.
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kSysTile) sym_cn_kernel(SymArgs<S> P) {
   const int ntiles = A.natoms / kSysTile;
   S* S_ = sS[wsub];
   S cn = S(0);
-  const int jt_first = itile + blockIdx.y;
+  const int jt_first = itile + blockIdx.x;
   for (int k0 = 0; jt_first + k0 * A.jsplit < ntiles; k0 += 32)
   for (unsigned tmask = sym_tile_mask<S>(A.box, ibox, jt_first, A.jsplit, k0, ntiles, A.cn_cutoff2, lane); tmask;
        tmask &= tmask - 1) {
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
   const S gi = bi.b;
   const S s3qi = sqr(S(3)) * bi.a;
   S e_i = S(0), gx = S(0), gy = S(0), gz = S(0), decn = S(0);
-  const int jt_first = itile + blockIdx.y;
+  const int jt_first = itile + blockIdx.x;
   for (int k0 = 0; jt_first + k0 * A.jsplit < ntiles; k0 += 32)
   for (unsigned tmask = sym_tile_mask<S>(A.box, ibox, jt_first, A.jsplit, k0, ntiles, A.cutoff2, lane); tmask;
        tmask &= tmask - 1) {
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(kSysTile) sym_cnbwd_kernel(SymArgs<S> P) {
   __syncwarp();
   const int ntiles = A.natoms / kSysTile;
   S gx = S(0), gy = S(0), gz = S(0);
-  const int jt_first = itile + blockIdx.y;
+  const int jt_first = itile + blockIdx.x;
   for (int k0 = 0; jt_first + k0 * A.jsplit < ntiles; k0 += 32)
   for (unsigned tmask = sym_tile_mask<S>(A.box, ibox, jt_first, A.jsplit, k0, ntiles, A.cn_cutoff2, lane); tmask;
        tmask &= tmask - 1) {
