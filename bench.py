@@ -462,10 +462,10 @@ def main():
             "gpu_launches": launches,
             "roofline": {
                 "bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": achieved, "peak": peak_tflops,
-                "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": 15.83e6 if args.dtype == "f64" else None,
+                "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": 15.85e6 if args.dtype == "f64" else None,
                 "kernel": "d3::molecule_kernel_v2<%s, true>" % ("double" if args.dtype == "f64" else "float"),
                 "peak_source": "FMA-chain probe of the same type measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "fp64_pipe_active_pct_ncu": 53.5 if args.dtype == "f64" else None,
+                "fp64_pipe_active_pct_ncu": 53.6 if args.dtype == "f64" else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1h_molecule_kernel_v2_raw.csv",
                 "flops_model": "140/pair-term (r<=25 Bohr), 89 (25<r<=50), SURVEY.md 8(d)",
                 "hbm_gbs_measured_peak": _measured_hbm(),
@@ -769,8 +769,8 @@ def run_c5a(args, rank, local, world, dev):
                 "max_abs_grad_diff_vs_resident": e2e_err},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s",
                      "frac": achieved / (peak * world),
-                     "traffic": 100.6e6 if (world == 1 and args.cutoff == 25.0 and nwater == 3334) else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (6.5 + 94.1 MB, mostly the "
+                     "traffic": 100.9e6 if (world == 1 and args.cutoff == 25.0 and nwater == 3334) else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (6.0 + 94.9 MB, mostly the "
                                        "per-centre neighbour records leaving L2), profiles/r1h_system_atm3_raw.csv",
                      "fp64_pipe_active_pct_ncu": 40.3,
                      "kernel": "d3::system_atm3_kernel<double, true> (every triple once), all ranks",
