@@ -159,3 +159,35 @@ def test_exception_and_typing_modules_mirror_the_reference():
                  "TensorOrTensors", "get_default_device", "get_default_dtype"):
         assert hasattr(d3.typing, name), name
     assert d3.typing.get_default_dtype() == torch.get_default_dtype()
+
+
+def test_batch_order_hint_is_a_size_sorted_permutation():
+    """`ops.batch_order` (host logic of d3b200_model.batch_order): a permutation, largest structures first, stable."""
+    from tad_dftd3_b200 import ops
+
+    gen = torch.Generator().manual_seed(3)
+    z = (torch.rand(50, 9, generator=gen) < 0.6).long() * 6
+    order = ops.batch_order(z)
+    assert order.dtype == torch.int32 and sorted(order.tolist()) == list(range(50))
+    counts = (z != 0).sum(-1)[order.long()]
+    assert bool((counts[:-1] >= counts[1:]).all())
+    same = counts[:-1] == counts[1:]
+    assert bool((order[:-1][same] < order[1:][same]).all())      # stable within equal sizes
+
+
+def test_model_struct_layout_matches_header():
+    """The ctypes mirror of d3b200_model_* has one member per member of the C struct, in order."""
+    from tad_dftd3_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "d3b200.h")).read()
+    body = re.search(r"typedef struct d3b200_model_f64 \{(.*?)\} d3b200_model_f64;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"(\w+);", body)
+    assert names == [f[0] for f in _lib.Model._fields_]
+    body = re.search(r"typedef struct d3b200_system_f64 \{(.*?)\} d3b200_system_f64;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n for decl in re.findall(r"([^;]+);", body) for n in re.findall(r"(\w+)\s*(?:,|$)", decl.strip())]
+    assert names == [f[0] for f in _lib.System._fields_]
+    body = re.search(r"typedef struct d3b200_params \{(.*?)\} d3b200_params;", text, flags=re.S).group(1)
+    names = [n for decl in re.findall(r"double ([^;]+);", body) for n in re.split(r"\s*,\s*", decl.strip())]
+    assert names == [f[0] for f in _lib.Params._fields_]
