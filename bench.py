@@ -820,6 +820,16 @@ def run_c5b(args, rank, local, world, dev):
         if it >= args.warmup:
             times.append(time.perf_counter() - t0)
     sym = float((h.reshape(600, 600) - h.reshape(600, 600).T).abs().max())
+    # the same Hessian from one launch of the second-order kernel (tad_dftd3_b200.hessian), without functorch
+    direct = []
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        hd = d3.hessian(numbers, positions, param, ref=ref)
+        torch.cuda.synchronize(dev)
+        if it >= args.warmup:
+            direct.append(time.perf_counter() - t0)
+    direct_err = float((hd - h).abs().max())
     # end to end: positions from pinned host memory, Hessian back into pinned host memory
     from tad_dftd3_b200 import _lib
 
@@ -841,6 +851,11 @@ def run_c5b(args, rank, local, world, dev):
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "c5b: examples/hessian.py construction on one 200-atom chain-grown molecule",
                        "hessian_shape": list(h.shape), "max_asymmetry": sym,
+                       "direct_hessian_ms": float(np.mean(direct)) * 1e3,
+                       "direct_hessian_note": "tad_dftd3_b200.hessian(): one d3b200_batch_hvp_f64 launch on the 3N unit "
+                                              "tangents; the jacrev o jacrev value above is dominated by ~3 ms of functorch "
+                                              "host overhead (tools/hessian_probe.py)",
+                       "direct_vs_jacrev_max_abs_diff": direct_err,
                        "entry": "one d3b200_batch_energy_f64, one d3b200_batch_vjp_f64 and one d3b200_batch_hvp_f64 "
                                 "launch (cotangent batch of 600) per Hessian",
                        "reference_cpu_seconds_survey": 10.6},

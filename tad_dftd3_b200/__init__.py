@@ -12,14 +12,14 @@ kernels behind the C ABI in `include/d3b200.h`, with analytic first and second
 derivatives wired into torch autograd / torch.func.
 """
 from . import damping, data, defaults, disp, exception, model, ncoord, reference, typing
-from .disp import dftd3
+from .disp import dftd3, hessian
 from .host import HostPipeline, bind_host_thread_to_gpu, dftd3_host
 from .reference import Reference
 
 __version__ = "0.1.0"
 
 __all__ = [
-    "dftd3", "dftd3_host", "HostPipeline", "bind_host_thread_to_gpu", "damping", "data", "defaults", "disp", "exception",
+    "dftd3", "hessian", "dftd3_host", "HostPipeline", "bind_host_thread_to_gpu", "damping", "data", "defaults", "disp", "exception",
     "model", "ncoord", "reference", "typing",
     "Reference", "__version__",
 ]

@@ -25,7 +25,7 @@ from .ncoord import exp_count
 from .ops import Settings, d3_energy
 from .reference import Reference
 
-__all__ = ["dftd3", "dispersion", "dispersion2", "dispersion3"]
+__all__ = ["dftd3", "hessian", "dispersion", "dispersion2", "dispersion3"]
 
 _Z2S_104 = "Rf"  # element 104, named in the reference's error message (disp.py:134)
 
@@ -132,6 +132,7 @@ def dftd3(
     weighting_function=gaussian_weight,
     damping_function=rational_damping,
     chunk_size: int | None = None,
+    _raw: bool = False,
 ) -> Tensor:
     """
     Atom-resolved DFT-D3 dispersion energy of a structure `(N,)` or a
@@ -203,7 +204,44 @@ def dftd3(
         alp=_scalar(param.get("alp", defaults.ALP)),
     )
     p = _param_vector(param if atm else {k: v for k, v in param.items() if k != "s9"}, dtype)
+    if _raw:
+        return p, rcov_t, r4r2_t, rvdw_t, refcn, refc6, st
     return d3_energy(numbers, positions, p, rcov_t, r4r2_t, rvdw_t, refcn, refc6, st)
+
+
+def hessian(numbers: Tensor, positions: Tensor, param: dict, **kwargs) -> Tensor:
+    """
+    Nuclear Hessian of the total dispersion energy of ONE structure,
+    `H[i, a, j, b] = d2 (sum_k E_k) / dx_ia dx_jb`, shape `(N, 3, N, 3)` -- what
+    `jacrev(jacrev(lambda x: dftd3(numbers, x, param).sum(-1)))(positions)` returns
+    (reference examples/hessian.py:84-94, test/test_grad/test_hessian.py), from ONE
+    launch of the second-order kernel (`d3b200_batch_hvp_*` with the 3N unit
+    tangents as a batch) instead of two nested functorch transforms, whose host
+    overhead (about 3 ms) exceeds the kernel time for a few hundred atoms.
+    Keyword arguments as for `dftd3()`.  Not differentiable further.
+    """
+    from .ops import _run_hvp
+
+    if numbers.dim() != 1 or positions.shape != (numbers.shape[0], 3):
+        raise ValueError("hessian() expects one structure: numbers (N,), positions (N, 3)")
+    n = numbers.shape[0]
+    p, rcov_t, r4r2_t, rvdw_t, refcn, refc6, st = dftd3(numbers, positions.detach(), param, _raw=True, **kwargs)
+    dtype, device = positions.dtype, positions.device
+    if n == 0:
+        return torch.zeros(0, 3, 0, 3, dtype=dtype, device=device)
+    nb = 3 * n
+    vx = torch.eye(nb, dtype=dtype, device=device).reshape(nb, n, 3)
+    g = torch.ones(nb, n, dtype=dtype, device=device)
+
+    def per_batch(t, per_element):
+        return t if (t is None or per_element) else t.unsqueeze(0).expand(nb, *t.shape)
+
+    _, dgrad, _ = _run_hvp(
+        numbers.unsqueeze(0).expand(nb, n), positions.detach().unsqueeze(0).expand(nb, n, 3), p.detach(), g, vx,
+        torch.zeros(5, dtype=dtype), per_batch(rcov_t, st.rcov_per_element), per_batch(r4r2_t, st.r4r2_per_element),
+        per_batch(rvdw_t, st.rvdw_mode != 2), refcn, refc6, st)
+    # row k of dgrad is H e_k, i.e. column k of the (symmetric) Hessian
+    return dgrad.reshape(n, 3, n, 3).permute(2, 3, 0, 1).contiguous()
 
 
 _default_refs: dict = {}

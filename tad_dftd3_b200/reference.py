@@ -125,8 +125,10 @@ class Reference:
         if hit is None:
             from .disp import _plain
 
-            cn = _plain(self.cn.detach()).to(device=device, dtype=dtype).contiguous()
-            c6 = _plain(self.c6.detach()).to(device=device, dtype=dtype).contiguous()
+            # (inside jacrev / vmap even `detach()` of a plain tensor comes back wrapped at the live
+            # levels; only plain tensors may be cached, so unwrap the results as well)
+            cn = _plain(_plain(self.cn).detach().to(device=device, dtype=dtype).contiguous())
+            c6 = _plain(_plain(self.c6).detach().to(device=device, dtype=dtype).contiguous())
             sym = bool(torch.allclose(c6, c6.permute(1, 0, 3, 2), rtol=1e-6 if dtype == torch.float32 else 1e-12, atol=0))
             hit = (cn, c6, sym)
             self._cache[key] = hit

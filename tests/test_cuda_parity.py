@@ -158,6 +158,43 @@ def test_hessian_jacrev(runs, case):
     assert_close(h.cpu(), c["hessian"], 1e-9, 1e-12, case)
 
 
+@pytest.mark.parametrize("case", ["pbh4_hess_f64", "pbh4_hess_atm_f64", "two_atoms_f64"])
+def test_direct_hessian_equals_reference(runs, case):
+    """`d3.hessian()` (one launch of the second-order kernel on the 3N unit tangents) against the
+    reference's jacrev(jacrev) Hessian, and against our own functorch path."""
+    import tad_dftd3_b200 as d3
+
+    c = runs.case(case)
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    refcn, refc6, rcov, r4r2, rvdw = tables(dtype, DEV)
+    z, x = numbers.to(DEV), positions.to(DEV)
+    par = {k: v.to(DEV) for k, v in param.items()}
+    kw = dict(ref=d3.Reference(cn=refcn, c6=refc6), rvdw=rvdw[z.unsqueeze(-1), z.unsqueeze(-2)])
+    h = d3.hessian(z, x, par, **kw)
+    assert h.shape == (z.shape[0], 3, z.shape[0], 3)
+    assert_close(h.cpu(), c["hessian"], 1e-9, 1e-12, case + " direct hessian")
+    hf = torch.func.jacrev(torch.func.jacrev(lambda xx: d3.dftd3(z, xx, par, **kw).sum(-1)))(x)
+    assert_close(h.cpu(), hf.cpu(), 1e-12, 1e-16, case + " direct vs functorch")
+
+
+def test_reference_cache_filled_inside_a_transform_stays_usable(runs):
+    """A fresh Reference whose prepared tables are first built inside jacrev(jacrev(...)) must
+    still work in a plain call afterwards (regression: a cached functorch wrapper without storage)."""
+    import tad_dftd3_b200 as d3
+
+    c = runs.case("two_atoms_f64")
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    refcn, refc6, *_ = tables(dtype, DEV)
+    ref = d3.Reference(cn=refcn.clone(), c6=refc6.clone())          # nothing cached yet
+    z, x = numbers.to(DEV), positions.to(DEV)
+    par = {k: v.to(DEV) for k, v in param.items() if k != "s9"}
+    hf = torch.func.jacrev(torch.func.jacrev(lambda xx: d3.dftd3(z, xx, par, ref=ref).sum(-1)))(x)
+    e = d3.dftd3(z, x, par, ref=ref)                                  # plain call on the cached tables
+    h = d3.hessian(z, x, par, ref=ref)
+    assert torch.isfinite(e).all()
+    assert_close(h.cpu(), hf.cpu(), 1e-12, 1e-16, "direct vs functorch after a transform-first cache fill")
+
+
 def test_hessian_vmap_batch(runs):
     """vmap(jacrev(jacrev)) over a padded batch (reference test_hessian.py:140-202)."""
     import tad_dftd3_b200 as d3
