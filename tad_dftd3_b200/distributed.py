@@ -108,7 +108,7 @@ def dftd3_sharded(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, 
     the same inputs and receives the full atom-resolved energy; `.backward()`
     gives the full gradient on every rank).
     """
-    from . import _lib, data
+    from . import _lib
     from .disp import _check_numbers, _default_reference, _scalar
 
     if numbers.dim() != 1 or positions.shape != (numbers.shape[0], 3):

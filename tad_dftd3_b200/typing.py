@@ -4,7 +4,7 @@ Type aliases under the names the reference exports from `tad_dftd3.typing`
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Dict, List, Tuple, TypedDict, Union
+from typing import Callable, List, Tuple, TypedDict, Union
 
 import torch
 from torch import Size, Tensor

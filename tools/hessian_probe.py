@@ -1,7 +1,7 @@
 import time, torch, sys
 sys.path.insert(0, '/root/repo')
 import tad_dftd3_b200 as d3
-from tad_dftd3_b200 import synthetic as syn, _lib
+from tad_dftd3_b200 import synthetic as syn
 from tad_dftd3_b200.data import REFCN
 dev = torch.device('cuda:0'); dt = torch.double
 ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
