@@ -582,11 +582,16 @@ def run_c4(args, rank, local, world, dev):
         for _ in range(args.warmup):
             step_e2e()
         barrier()
-        t0 = time.perf_counter()
+        e2e_steps = []
         for _ in range(args.steps):
+            t0 = time.perf_counter()
             step_e2e()
+            torch.cuda.synchronize(dev)
+            e2e_steps.append((time.perf_counter() - t0) * 1e3)
         barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        # median: a fresh process occasionally shows one step of tens of ms here (allocator growth while
+        # the plan of every step is rebuilt for a new numbers tensor)
+        e2e_ms = float(np.median(e2e_steps))
     launches = _lib.launch_count - l0
     peak = fp64_peak(lib, dev, stream)
     t = torch.tensor([ms, e2e_ms], dtype=torch.double, device=dev)
@@ -604,7 +609,7 @@ def run_c4(args, rank, local, world, dev):
                 "workload": f"c4: {numbers.shape[0]}-atom water cluster, D3(BJ) two-body + CN (cutoffs 50 / 25 Bohr), "
                             "energy+grad fp64, rows sharded over the GPUs",
                 "pair_terms": pairs, "pairs_within_25_bohr": near,
-                "entry": "SystemPlan (Morton + element sort) + d3b200_system_{cn,weights,pair,cnbwd}_f64",
+                "entry": "SystemPlan (cached Morton order, d3b200_system_pack_f64) + d3b200_system_{cn,weights,tvec,pair,cnbwd}_f64",
                 "l2": "per-atom arrays (10 MB) stream from L2/HBM every sweep; structure larger than one CTA's reach",
                 "timing": "max(CUDA events, wall clock) per step incl. the plan build, max over ranks",
                 "parallelism": f"rows of one structure over {world} GPU(s); all-reduce of CN, dL/dCN, E, grad",
@@ -612,7 +617,8 @@ def run_c4(args, rank, local, world, dev):
             "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "pair-terms/s",
                     "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * 8),
                     "d2h_bytes_per_step": int(e_h.numel() * 8 + g_h.numel() * 8), "ms_per_step": e2e_ms,
-                    "api": "tad_dftd3_b200.distributed.dftd3_sharded() + autograd.grad, pinned host buffers"},
+                    "api": "tad_dftd3_b200.distributed.dftd3_sharded() + autograd.grad, pinned host buffers; "
+                           "median of the timed steps"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved * world and achieved, "peak": peak * world,
                          "unit": "TFLOP/s", "frac": achieved / (peak * world), "traffic": None,

@@ -297,6 +297,18 @@ int d3b200_system_weights_f64(const d3b200_system_f64* sys, const d3b200_params*
 int d3b200_system_tvec_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
 int d3b200_system_pair_f64(const d3b200_system_f64* sys, const d3b200_params* par, int want_grad, void* stream);
 int d3b200_system_cnbwd_f64(const d3b200_system_f64* sys, const d3b200_params* par, void* stream);
+/* Packs the position-dependent arrays of a plan in one launch (instead of a dozen tensor
+ * operations on the host side): atoms[natoms][4] = {positions[perm[i]] for i < nreal, else the
+ * far-away padding position of the template; kcn*rcov from the template} and
+ * box[natoms/32][6] = bounding box of every 32-atom sub-tile over its real atoms (z != 0; a
+ * sub-tile of padding only: its first atom).  perm: sorted slot -> original atom index. */
+int d3b200_system_pack_f64(int natoms, int nreal, const int64_t* perm, const double* positions,
+                           const double* atoms_template, const int32_t* z, double* atoms, double* box,
+                           void* stream);
+int d3b200_system_pack_f32(int natoms, int nreal, const int64_t* perm, const float* positions,
+                           const float* atoms_template, const int32_t* z, float* atoms, float* box,
+                           void* stream);
+
 /* Damping-parameter gradient of the two-body term for the tiled path (needs the T vectors):
  * writes the per-row sums scratch[q][jsplit][natoms], q = 0..3 <-> s6, s8, a1, a2
  * (sum_j C6 dP/dq of rows row_begin..row_end-1; all other scratch entries untouched);

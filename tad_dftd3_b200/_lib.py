@@ -77,6 +77,7 @@ for _sfx in ("f64", "f32"):
     _SIGNATURES[f"d3b200_probe_fma_{_sfx}"] = ([_I, _I, _P, _P], C.c_int)
     for _k in ("cn", "weights", "cnbwd", "pgrad"):
         _SIGNATURES[f"d3b200_system_{_k}_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _P], C.c_int)
+    _SIGNATURES[f"d3b200_system_pack_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, _P, _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_system_pair_{_sfx}"] = ([C.POINTER(System), C.POINTER(Params), _I, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_cn_{_sfx}"] = ([_I, _I, _P, _P, _P, C.c_double, C.c_double, _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_weights_{_sfx}"] = ([C.c_size_t, _P, _P, _P, _P, _P], C.c_int)

@@ -459,6 +459,17 @@ int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int wan
 }
 
 template <typename B>
+int sys_pack(int natoms, int nreal, const int64_t* perm, const B* positions, const B* tmpl, const int32_t* z,
+             B* atoms, B* box, void* stream) {
+  if (natoms <= 0 || natoms % d3::kSysTile || nreal < 0 || nreal > natoms)
+    return fail(D3B200_EINVAL, "system_pack: natoms must be a positive multiple of 128 and 0 <= nreal <= natoms%s");
+  if ((nreal && (!perm || !positions)) || !tmpl || !z || !atoms || !box) return fail(D3B200_EINVAL, "system_pack: null argument%s");
+  const int nsub = natoms / d3::kSysSub;
+  d3::system_pack_kernel<B><<<(nsub + 3) / 4, 128, 0, (cudaStream_t)stream>>>(natoms, nreal, perm, positions, tmpl, z, atoms, box);
+  return launched("system_pack_kernel");
+}
+
+template <typename B>
 int sys_pgrad(const typename SysOf<B>::type* s, const d3b200_params* par, void* stream) {
   d3::SysArgs<B> a;
   int rc = sys_fill<B>(a, s, par);
@@ -656,6 +667,8 @@ int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, co
 int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int g, void* st) { return sys_atm<float>(s, p, r, g, st); }
 int d3b200_system_tvec_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_tvec<double>(s, p, st); }
 int d3b200_system_tvec_f32(const d3b200_system_f32* s, const d3b200_params* p, void* st) { return sys_tvec<float>(s, p, st); }
+int d3b200_system_pack_f64(int n, int nr, const int64_t* perm, const double* x, const double* t, const int32_t* z, double* a, double* b, void* st) { return sys_pack<double>(n, nr, perm, x, t, z, a, b, st); }
+int d3b200_system_pack_f32(int n, int nr, const int64_t* perm, const float* x, const float* t, const int32_t* z, float* a, float* b, void* st) { return sys_pack<float>(n, nr, perm, x, t, z, a, b, st); }
 int d3b200_system_pgrad_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_pgrad<double>(s, p, st); }
 int d3b200_system_pgrad_f32(const d3b200_system_f32* s, const d3b200_params* p, void* st) { return sys_pgrad<float>(s, p, st); }
 int d3b200_system_cn_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_cn<double>(s, p, st); }

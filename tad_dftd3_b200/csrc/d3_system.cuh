@@ -119,6 +119,50 @@ __device__ __forceinline__ void tile_box(const S* box, int tile, S* out) {
   }
 }
 
+// ---------------------------------------------------------------- plan packing
+// What the host plan needs from the current positions, in one launch: the sorted AoS atom
+// array (x, y, z from positions[perm[i]] for the real atoms, the far-away padding positions
+// and kcn * rcov from the static template) and the bounding box of every 32-atom sub-tile
+// over its real atoms (a sub-tile of padding only: the position of its first atom).
+// One warp per sub-tile.
+template <typename S>
+__global__ void system_pack_kernel(int natoms, int nreal, const int64_t* perm, const S* positions,
+                                   const S* tmpl, const int* z, S* atoms, S* box) {
+  const int sub = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (sub * kSysSub >= natoms) return;
+  const int i = sub * kSysSub + lane;
+  S x = tmpl[4 * (size_t)i], y = tmpl[4 * (size_t)i + 1], zc = tmpl[4 * (size_t)i + 2];
+  const S rk = tmpl[4 * (size_t)i + 3];
+  if (i < nreal) {
+    const size_t src = (size_t)perm[i];
+    x = positions[3 * src]; y = positions[3 * src + 1]; zc = positions[3 * src + 2];
+  }
+  atoms[4 * (size_t)i] = x; atoms[4 * (size_t)i + 1] = y; atoms[4 * (size_t)i + 2] = zc; atoms[4 * (size_t)i + 3] = rk;
+  const bool real = z[i] != 0;
+  const unsigned any_real = __ballot_sync(0xffffffffu, real);
+  const S x0 = __shfl_sync(0xffffffffu, x, 0), y0 = __shfl_sync(0xffffffffu, y, 0), z0 = __shfl_sync(0xffffffffu, zc, 0);
+  S lo[3] = {x, y, zc}, hi[3] = {x, y, zc};
+  if (!real) {                          // padding inside a partly real sub-tile does not widen its box
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k] = S(3.0e38); hi[k] = S(-3.0e38); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const S l2 = __shfl_xor_sync(0xffffffffu, lo[k], o), h2 = __shfl_xor_sync(0xffffffffu, hi[k], o);
+      lo[k] = l2 < lo[k] ? l2 : lo[k];
+      hi[k] = h2 > hi[k] ? h2 : hi[k];
+    }
+  }
+  if (lane == 0) {
+    S* b = box + (size_t)sub * 6;
+    if (any_real) { b[0] = lo[0]; b[1] = lo[1]; b[2] = lo[2]; b[3] = hi[0]; b[4] = hi[1]; b[5] = hi[2]; }
+    else { b[0] = x0; b[1] = y0; b[2] = z0; b[3] = x0; b[4] = y0; b[5] = z0; }
+  }
+}
+
 // ---------------------------------------------------------------- CN sweep
 template <typename S>
 __global__ void __launch_bounds__(kSysTile) system_cn_kernel(SysArgs<S> A) {

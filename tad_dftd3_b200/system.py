@@ -141,6 +141,23 @@ class SystemPlan:
         self.static = st
         self.n, self.npad, self.perm, self.z, self.sqrtq = st.n, st.npad, st.perm, st.z, st.sqrtq
         n, npad = st.n, st.npad
+        self.dtype, self.device = dt, dev
+        if dev.type == "cuda" and os.environ.get("TAD_DFTD3_B200_TORCH_PACK") != "1":
+            # one launch: gather + AoS packing + sub-tile boxes (d3b200_system_pack_*)
+            x = positions.detach()
+            x = x if x.is_contiguous() else x.contiguous()
+            self.atoms = torch.empty(npad, 4, dtype=dt, device=dev)
+            self.box = torch.empty(npad // SUB, 6, dtype=dt, device=dev)
+            fn = getattr(_lib.lib(), "d3b200_system_pack_" + ("f64" if dt == torch.float64 else "f32"))
+            _lib.launch_count += 1
+            with torch.cuda.device(dev):
+                _lib.check(fn(npad, n, C.c_void_p(st.perm.data_ptr()), C.c_void_p(x.data_ptr()),
+                              C.c_void_p(st.template.data_ptr()), C.c_void_p(st.z.data_ptr()),
+                              C.c_void_p(self.atoms.data_ptr()), C.c_void_p(self.box.data_ptr()),
+                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            self._keep = x
+            return
+        # host tensors (the CPU tests of the sharding logic): the same arrays with tensor operations
         atoms = st.template.clone()
         atoms[:n, :3] = positions.detach()[st.perm]
         self.atoms = atoms
@@ -152,7 +169,6 @@ class SystemPlan:
         lo = torch.where(st.empty, xyz[:, 0, :], lo)
         hi = torch.where(st.empty, xyz[:, 0, :], hi)
         self.box = torch.cat([lo, hi], 1).contiguous()
-        self.dtype, self.device = dt, dev
 
     def elements(self):
         """(zlist int32 [E], eidx int8 [npad]) -- distinct elements and each atom's index (-1 = padding)."""

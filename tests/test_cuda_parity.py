@@ -283,6 +283,27 @@ def test_tiled_path_parameter_gradients(runs, case, force_tiled):
     assert_close(out["pgrad"], c["pgrad"], RTOL, ATOL, case + " pgrad")
 
 
+def test_plan_packing_kernel_equals_tensor_path(monkeypatch):
+    """`d3b200_system_pack_*` (one launch) against the tensor-operation path of SystemPlan: sorted
+    AoS atoms and sub-tile boxes, with ghost atoms and a partly filled last tile."""
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2
+    from tad_dftd3_b200.system import SystemPlan
+
+    for dtype in (torch.double, torch.float32):
+        numbers, positions = syn.water_cluster(150, seed=6)          # 450 atoms -> 512 padded
+        numbers = numbers.clone()
+        numbers[[0, 7, 300]] = 0
+        z, x = numbers.to(DEV), positions.to(DEV).to(dtype)
+        rc, q = COV_D3(dtype, DEV), R4R2(dtype, DEV)
+        a = SystemPlan(z, x, rc, q, 16.0, True, True)
+        monkeypatch.setenv("TAD_DFTD3_B200_TORCH_PACK", "1")
+        b = SystemPlan(z.clone(), x, rc, q, 16.0, True, True)
+        monkeypatch.delenv("TAD_DFTD3_B200_TORCH_PACK")
+        assert a.npad == b.npad == 512 and torch.equal(a.perm, b.perm)
+        assert torch.equal(a.atoms, b.atoms) and torch.equal(a.box, b.box)
+
+
 def test_tiled_equals_fused_on_cluster(monkeypatch):
     """700-atom water cluster (several tiles, culling active at cutoff 20):
     tiled path vs fused one-CTA kernel vs CPU oracle."""
