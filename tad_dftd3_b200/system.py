@@ -46,6 +46,7 @@ def morton_order(pos: Tensor) -> Tensor:
     return torch.argsort(code, stable=True)
 
 
+_atm_work_cache: dict = {}  # (device, stream) -> scratch of the triples-once ATM kernel
 _static_cache: dict = {}   # key -> _Static
 ORDER_MAX_AGE = 20         # calls after which the Morton / element order is rebuilt
 
@@ -297,8 +298,15 @@ class SystemRunner:
         if self.use_tvec and self.sys.atm_work is None and os.environ.get("TAD_DFTD3_B200_ATM2") != "1":
             # scratch of the triples-once kernel (per-CTA neighbour lists and records)
             nbytes = int(getattr(_lib.lib(), f"d3b200_system_atm_workspace_bytes_{self.sfx}")(self.plan.npad))
-            self._atm_work = torch.empty(nbytes, dtype=torch.uint8, device=self.plan.device)
-            self.sys.atm_work, self.sys.atm_work_bytes = self._atm_work.data_ptr(), nbytes
+            # several hundred MB: one buffer per device and stream, reused by every runner (work on one
+            # stream is ordered, so consecutive calls cannot overlap in it)
+            dev = self.plan.device
+            key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+            buf = _atm_work_cache.get(key)
+            if buf is None or buf.numel() < nbytes:
+                buf = _atm_work_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._atm_work = buf
+            self.sys.atm_work, self.sys.atm_work_bytes = buf.data_ptr(), buf.numel()
         keep = self.sys.tile_stride
         self.sys.tile_stride = getattr(self, "_atm_stride", 1)
         try:

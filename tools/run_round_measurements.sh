@@ -4,7 +4,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1h_bench_ref
 python bench.py --steps 20 --warmup 3 > gpurun_out/r1h_bench_c3.json 2>gpurun_out/r1h_c3.err
 python bench.py --steps 20 --warmup 3 --dtype f32 --no-cpu-baseline > gpurun_out/r1h_bench_c3_f32.json 2>>gpurun_out/r1h_c3.err
 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/r1h_bench_c4.json 2>gpurun_out/r1h_c4.err
-python bench.py --workload c5a --steps 2 --warmup 3 > gpurun_out/r1h_bench_c5a.json 2>gpurun_out/r1h_c5a.err
+python bench.py --workload c5a --steps 5 --warmup 3 > gpurun_out/r1h_bench_c5a.json 2>gpurun_out/r1h_c5a.err
 python bench.py --workload c5a --cutoff 50 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r1h_bench_c5a_cut50.json 2>>gpurun_out/r1h_c5a.err
 python bench.py --workload c5b --steps 5 --warmup 3 > gpurun_out/r1h_bench_c5b.json 2>gpurun_out/r1h_c5b.err
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_c3.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1h_launches_bench_c3.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_c3.log 2>&1
