@@ -194,6 +194,9 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
 typedef struct d3b200_pipe d3b200_pipe;
 int d3b200_pipe_create(d3b200_pipe** pipe);
 int d3b200_pipe_destroy(d3b200_pipe* pipe);
+/* Chunk schedule of the staged form (= its number of kernel launches): returns the number of chunks
+ * and, if `bounds` is not NULL, writes the chunk boundaries bounds[0..n] (room for 65 ints). */
+int d3b200_batch_host_chunks(int nbatch, int chunk, int* bounds);
 size_t d3b200_batch_host_workspace_bytes_f64(int nbatch, int natoms, int with_g, int atm);
 size_t d3b200_batch_host_workspace_bytes_f32(int nbatch, int natoms, int with_g, int atm);
 int d3b200_batch_vjp_host_f64(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_numbers,

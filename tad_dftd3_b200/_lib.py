@@ -60,6 +60,7 @@ _SIGNATURES = {
     "d3b200_batch_max_atoms_f32": ([_I], C.c_int),
     "d3b200_pipe_create": ([C.POINTER(C.c_void_p)], C.c_int),
     "d3b200_pipe_destroy": ([_P], C.c_int),
+    "d3b200_batch_host_chunks": ([_I, _I, C.POINTER(C.c_int)], C.c_int),
 }
 for _sfx in ("f64", "f32"):
     _SIGNATURES[f"d3b200_batch_energy_{_sfx}"] = (

@@ -245,6 +245,26 @@ size_t host_workspace_bytes(int nbatch, int natoms, int with_g, int atm) {
   return b;
 }
 
+// Chunk boundaries of the staged form: `chunk` structures per chunk (<= 0: one wave of CTAs of the
+// fused kernel, 148 SMs x 4), quarter- and half-size chunks at both ends so that the un-overlapped
+// first H2D copy and last D2H copy are short; at most kPipeMaxChunks chunks.  bounds[0..n], returns n.
+int pipe_schedule(int nbatch, int chunk, int* bounds) {
+  if (chunk <= 0) chunk = 592;
+  if ((nbatch + chunk - 1) / chunk + 4 > kPipeMaxChunks) chunk = (nbatch + kPipeMaxChunks - 5) / (kPipeMaxChunks - 4);
+  int nchunk = 0;
+  const int q = chunk / 4, h = chunk / 2;
+  int lo = 0, hi = nbatch;
+  int head[2], tail[2], nh = 0, nt = 0;
+  if (q > 0 && nbatch >= 2 * chunk) { head[nh++] = q; head[nh++] = h; tail[nt++] = q; tail[nt++] = h; }
+  bounds[nchunk++] = 0;
+  for (int k = 0; k < nh; ++k) { lo += head[k]; bounds[nchunk++] = lo; }
+  for (int k = 0; k < nt; ++k) hi -= tail[k];
+  while (lo + chunk < hi) { lo += chunk; bounds[nchunk++] = lo; }
+  if (lo < hi) bounds[nchunk++] = hi;
+  for (int k = nt - 1; k >= 0; --k) { hi += tail[k]; bounds[nchunk++] = hi; }
+  return nchunk - 1;
+}
+
 template <typename B>
 int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_numbers, const B* h_positions,
                   const typename ModelOf<B>::type* model, const d3b200_params* par, const B* h_g,
@@ -267,25 +287,8 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
   const size_t need = host_workspace_bytes<B>(nbatch, natoms, h_g != nullptr, atm);
   if (!workspace || wbytes < need)
     return fail(D3B200_EINVAL, "host-entry workspace too small%s: %ld < %ld bytes", "", (long)wbytes, (long)need);
-  if (chunk <= 0) chunk = 592;  // 148 SMs x 4 resident CTAs of the fused kernel
-  if ((nbatch + chunk - 1) / chunk + 4 > kPipeMaxChunks) chunk = (nbatch + kPipeMaxChunks - 5) / (kPipeMaxChunks - 4);
-  // chunk boundaries: quarter- and half-size chunks at both ends, so that the
-  // un-overlapped first H2D copy and last D2H copy are short
   int bounds[kPipeMaxChunks + 1];
-  int nchunk = 0;
-  {
-    const int q = chunk / 4, h = chunk / 2;
-    int lo = 0, hi = nbatch;
-    int head[2], tail[2], nh = 0, nt = 0;
-    if (q > 0 && nbatch >= 2 * chunk) { head[nh++] = q; head[nh++] = h; tail[nt++] = q; tail[nt++] = h; }
-    bounds[nchunk++] = 0;
-    for (int k = 0; k < nh; ++k) { lo += head[k]; bounds[nchunk++] = lo; }
-    for (int k = 0; k < nt; ++k) hi -= tail[k];
-    while (lo + chunk < hi) { lo += chunk; bounds[nchunk++] = lo; }
-    if (lo < hi) bounds[nchunk++] = hi;
-    for (int k = nt - 1; k >= 0; --k) { hi += tail[k]; bounds[nchunk++] = hi; }
-    --nchunk;  // bounds[0..nchunk]
-  }
+  const int nchunk = pipe_schedule(nbatch, chunk, bounds);
 
   const size_t na = (size_t)nbatch * natoms;
   char* w = reinterpret_cast<char*>(workspace);
@@ -777,6 +780,13 @@ int d3b200_pipe_destroy(d3b200_pipe* p) {
   }
   free(p);
   return D3B200_OK;
+}
+int d3b200_batch_host_chunks(int nbatch, int chunk, int* bounds) {
+  if (nbatch <= 0) return 0;
+  int local[kPipeMaxChunks + 1];
+  const int n = pipe_schedule(nbatch, chunk, local);
+  if (bounds) for (int k = 0; k <= n; ++k) bounds[k] = local[k];
+  return n;
 }
 size_t d3b200_batch_host_workspace_bytes_f64(int nbatch, int natoms, int with_g, int atm) {
   return host_workspace_bytes<double>(nbatch, natoms, with_g, atm);

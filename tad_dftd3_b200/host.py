@@ -87,14 +87,8 @@ class HostPipeline:
 
     @staticmethod
     def chunks(nbatch: int, chunk: int = 0) -> int:
-        """Number of chunks (= kernel launches) `d3b200_batch_vjp_host_*` cuts a batch into."""
-        c = chunk if chunk > 0 else 592
-        if -(-nbatch // c) + 4 > 64:
-            c = (nbatch + 59) // 60
-        if c // 4 > 0 and nbatch >= 2 * c:
-            inner = nbatch - 2 * (c // 4 + c // 2)
-            return 4 + -(-inner // c)
-        return -(-nbatch // c)
+        """Number of chunks (= kernel launches) the staged form of `d3b200_batch_vjp_host_*` cuts a batch into."""
+        return int(_lib.lib().d3b200_batch_host_chunks(int(nbatch), int(chunk), None))
 
     def _workspace(self, nbytes: int) -> Tensor:
         if self._work is None or self._work.numel() < nbytes:

@@ -191,3 +191,27 @@ def test_model_struct_layout_matches_header():
     body = re.search(r"typedef struct d3b200_params \{(.*?)\} d3b200_params;", text, flags=re.S).group(1)
     names = [n for decl in re.findall(r"double ([^;]+);", body) for n in re.split(r"\s*,\s*", decl.strip())]
     assert names == [f[0] for f in _lib.Params._fields_]
+
+
+def test_staged_host_entry_chunk_schedule(lib):
+    """d3b200_batch_host_chunks: boundaries start at 0, end at nbatch, strictly increase, at most 64 chunks,
+    quarter / half chunks at both ends of a long batch."""
+    import ctypes as C
+    import random
+
+    from tad_dftd3_b200 import HostPipeline
+
+    rng = random.Random(0)
+    for _ in range(3000):
+        n = rng.randint(1, 200000)
+        chunk = rng.choice([0, 1, 2, 3, 5, 16, 100, 592, 5000])
+        b = (C.c_int * 65)()
+        k = lib.d3b200_batch_host_chunks(n, chunk, b)
+        bounds = list(b[: k + 1])
+        assert 1 <= k <= 64 and bounds[0] == 0 and bounds[-1] == n
+        assert all(x < y for x, y in zip(bounds, bounds[1:]))
+        assert HostPipeline.chunks(n, chunk) == k
+    b = (C.c_int * 65)()
+    k = lib.d3b200_batch_host_chunks(4096, 0, b)
+    assert list(b[: k + 1]) == [0, 148, 444, 1036, 1628, 2220, 2812, 3404, 3652, 3948, 4096]
+    assert lib.d3b200_batch_host_chunks(0, 0, None) == 0
