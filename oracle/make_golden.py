@@ -241,7 +241,62 @@ def part2():
     print(f"reference_runs.npz: {len(store)} arrays, {sz/1024:.0f} kB")
 
 
+# ---------------------------------------------------------------- part 3
+def heavy_cluster(natoms=36, nelem=12, seed=21, box=13.0, dmin=2.3):
+    """Random cluster with `nelem` distinct elements up to uranium (more than the 8 that the
+    pre-contracted T-vector sweeps take: exercises the general tiled kernels)."""
+    rng = np.random.RandomState(seed)
+    pool = [1, 6, 7, 8, 9, 15, 16, 17, 26, 35, 53, 79, 82, 92]
+    zs = rng.choice(pool, size=nelem, replace=False)
+    numbers = np.concatenate([zs, rng.choice(zs, size=natoms - nelem)])
+    pos = []
+    while len(pos) < natoms:
+        c = rng.uniform(0.0, box, size=3)
+        if all(np.linalg.norm(c - q) >= dmin for q in pos):
+            pos.append(c)
+    return torch.from_numpy(numbers.astype(np.int64)), torch.from_numpy(np.asarray(pos))
+
+
+def part3():
+    """Second fixture file (kept separate so that `reference_runs.npz` stays byte-identical)."""
+    store = {}
+    rng = np.random.RandomState(23)
+
+    def add(case, numbers, positions, param, dtype=torch.double, **kw):
+        g = torch.from_numpy(rng.uniform(0.5, 1.5, size=tuple(numbers.shape)))
+        res = run_reference(numbers, positions, param, dtype, g=g, **kw)
+        store[f"{case}/numbers"] = numbers.numpy()
+        store[f"{case}/positions"] = positions.double().numpy()
+        store[f"{case}/g"] = g.numpy()
+        store[f"{case}/param_keys"] = np.asarray(list(param.keys()))
+        store[f"{case}/param_vals"] = np.asarray(list(param.values()), dtype=np.float64)
+        store[f"{case}/cutoff"] = np.asarray(kw.get("cutoff") or 50.0)
+        store[f"{case}/dtype"] = np.asarray(str(dtype))
+        for k, v in res.items():
+            store[f"{case}/{k}"] = v
+        print(f"  {case}: E_tot = {res['energy'].sum():.12e}")
+
+    nh, ph = heavy_cluster()
+    assert len(set(nh.tolist())) == 12
+    add("heavy12_f64", nh, ph, PAR_R2SCAN, want_param_grad=True)
+    add("heavy12_atm_f64", nh, ph, PAR_FULL, want_param_grad=True)
+    add("heavy12_atm_cut9_f64", nh, ph, PAR_FULL, cutoff=9.0)
+    add("heavy12_f32", nh, ph, PAR_R2SCAN, dtype=torch.float32)
+    add("heavy12_hess_atm_f64", nh[:10], ph[:10], PAR_FULL, want_hessian=True)
+    # ragged batch: one atom, forty atoms, three atoms, and a row of padding only
+    n40, p40 = syn.drug_like_batch(1, 40, 40, seed=9)
+    na, pa = tens(syn.README_BATCH[0])
+    rows_n = [torch.tensor([8]), n40[0], na[:3], torch.zeros(2, dtype=torch.int64)]
+    rows_p = [torch.zeros(1, 3, dtype=torch.double), p40[0], pa[:3], torch.zeros(2, 3, dtype=torch.double)]
+    add("ragged_atm_f64", syn.pack(rows_n), syn.pack(rows_p), PAR_TPSS0_ATM, want_param_grad=True)
+    np.savez_compressed(os.path.join(OUT, "reference_runs2.npz"), **store)
+    sz = os.path.getsize(os.path.join(OUT, "reference_runs2.npz"))
+    print(f"reference_runs2.npz: {len(store)} arrays, {sz/1024:.0f} kB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    part1()
-    part2()
+    if "--only-part3" not in sys.argv:
+        part1()
+        part2()
+    part3()

@@ -28,15 +28,20 @@ def pytest_collection_modifyitems(config, items):
 
 
 class Golden:
-    """npz with 'case/field' keys -> dict of cases."""
+    """npz files with 'case/field' keys -> dict of cases."""
 
-    def __init__(self, name):
-        self._z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
-        self.cases = sorted({k.split("/")[0] for k in self._z.files})
+    def __init__(self, *names):
+        self._z = {}
+        for name in names:
+            z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+            for k in z.files:
+                assert k not in self._z, f"duplicate fixture key {k}"
+                self._z[k] = z[k]
+        self.cases = sorted({k.split("/")[0] for k in self._z})
 
     def case(self, case):
         pre = case + "/"
-        return {k[len(pre):]: self._z[k] for k in self._z.files if k.startswith(pre)}
+        return {k[len(pre):]: v for k, v in self._z.items() if k.startswith(pre)}
 
 
 @pytest.fixture(scope="session")
@@ -46,4 +51,4 @@ def pins():
 
 @pytest.fixture(scope="session")
 def runs():
-    return Golden("reference_runs.npz")
+    return Golden("reference_runs.npz", "reference_runs2.npz")

@@ -66,8 +66,11 @@ def is_atm(c):
 def _case_names():
     import os
 
-    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_runs.npz"))
-    return sorted({k.split("/")[0] for k in z.files if not k.startswith("stages")})
+    names = set()
+    for f in ("reference_runs.npz", "reference_runs2.npz"):
+        z = np.load(os.path.join(os.path.dirname(__file__), "golden", f))
+        names |= {k.split("/")[0] for k in z.files if not k.startswith("stages")}
+    return sorted(names)
 
 
 @pytest.mark.parametrize("case", _case_names())
@@ -138,7 +141,7 @@ def test_pinned_cn_through_default_radii(pins, name):
     assert_close(cn, c["cn"], 0, 5e-11, name)
 
 
-@pytest.mark.parametrize("case", ["pbh4_hess_f64", "two_atoms_f64", "pbh4_hess_atm_f64"])
+@pytest.mark.parametrize("case", ["pbh4_hess_f64", "two_atoms_f64", "pbh4_hess_atm_f64", "heavy12_hess_atm_f64"])
 def test_hessian_jacrev(runs, case):
     """examples/hessian.py:84-94 construction: jacrev(jacrev(E_total))."""
     import tad_dftd3_b200 as d3
@@ -158,7 +161,7 @@ def test_hessian_jacrev(runs, case):
     assert_close(h.cpu(), c["hessian"], 1e-9, 1e-12, case)
 
 
-@pytest.mark.parametrize("case", ["pbh4_hess_f64", "pbh4_hess_atm_f64", "two_atoms_f64"])
+@pytest.mark.parametrize("case", ["pbh4_hess_f64", "pbh4_hess_atm_f64", "two_atoms_f64", "heavy12_hess_atm_f64"])
 def test_direct_hessian_equals_reference(runs, case):
     """`d3.hessian()` (one launch of the second-order kernel on the 3N unit tangents) against the
     reference's jacrev(jacrev) Hessian, and against our own functorch path."""
@@ -257,7 +260,8 @@ def force_tiled(monkeypatch):
 
 
 @pytest.mark.parametrize("case", ["c1_f64", "c2_f64", "c2_cut6_f64", "mols6_f64", "water64_f64",
-                                  "crowded_f64", "pbh4_hess_f64", "c2_tpss0_f64", "c2_f32"])
+                                  "crowded_f64", "pbh4_hess_f64", "c2_tpss0_f64", "c2_f32",
+                                  "heavy12_f64"])          # 12 elements: the general (non T-vector) sweeps
 def test_tiled_path_reference_runs(runs, case, force_tiled):
     """Same fixtures through the tiled sweeps (ghost atoms removed, Morton + element
     sort, padding to 128, box culling)."""
@@ -348,7 +352,8 @@ def test_tiled_degenerate_sizes(force_tiled):
 
 @pytest.mark.parametrize("case", ["c1_atm_f64", "c2_atm_f64", "c2_atm_cut8_f64", "mols6_atm_f64",
                                   "mols6_atm_cut12_f64", "water64_cut20_atm_f64", "close_f64", "ghost_f64",
-                                  "two_atoms_f64", "one_atom_f64", "c2_atm_f32"])
+                                  "two_atoms_f64", "one_atom_f64", "c2_atm_f32",
+                                  "heavy12_atm_f64", "heavy12_atm_cut9_f64", "ragged_atm_f64"])
 def test_tiled_atm_reference_runs(runs, case, force_tiled):
     """Three-body term of the tiled path (edge-owner enumeration, ordered cutoff rule)."""
     c = runs.case(case)

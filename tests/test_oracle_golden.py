@@ -78,7 +78,7 @@ def test_runs_energy_and_grad(runs):
             assert_close([float(x) for x in grads[1:]], c["pgrad"], rt, at, case + " pgrad")
 
 
-@pytest.mark.parametrize("case", ["pbh4_hess_f64", "pbh4_hess_atm_f64", "two_atoms_f64"])
+@pytest.mark.parametrize("case", ["pbh4_hess_f64", "pbh4_hess_atm_f64", "two_atoms_f64", "heavy12_hess_atm_f64"])
 def test_runs_hessian(runs, case):
     c = runs.case(case)
     dtype, numbers, positions, g, param, cutoff = case_inputs(c)
