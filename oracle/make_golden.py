@@ -289,6 +289,21 @@ def part3():
     rows_n = [torch.tensor([8]), n40[0], na[:3], torch.zeros(2, dtype=torch.int64)]
     rows_p = [torch.zeros(1, 3, dtype=torch.double), p40[0], pa[:3], torch.zeros(2, 3, dtype=torch.double)]
     add("ragged_atm_f64", syn.pack(rows_n), syn.pack(rows_p), PAR_TPSS0_ATM, want_param_grad=True)
+    # 300-atom water cluster, three-body term with a cutoff that cuts many triples partly: neighbour
+    # lists of 100-250 atoms, i.e. several 64-entry tiles per centre in the triples-once kernel
+    nw, pw = syn.water_cluster(100, seed=13)
+    add("water100_atm_cut18_f64", nw, pw, PAR_TPSS0_ATM, cutoff=18.0)
+    # stage outputs on the 12-element cluster (stage kernels on heavy elements)
+    refobj, rcov_t, r4r2_t, rvdw_t = ref_tables(torch.double)
+    cn = d3.ncoord.cn_d3(nh, ph, counting_function=d3.ncoord.exp_count, rcov=rcov_t[nh])
+    w = d3.model.weight_references(nh, cn, refobj)
+    c6 = d3.model.atomic_c6(nh, w, refobj)
+    e2 = d3.disp.dispersion(nh, ph, {k: torch.tensor(v, dtype=torch.double) for k, v in PAR_FULL.items()}, c6,
+                            rvdw_t[nh.unsqueeze(-1), nh.unsqueeze(-2)], r4r2_t[nh])
+    store["stages_heavy12/cn"] = cn.numpy()
+    store["stages_heavy12/weights"] = w.numpy()
+    store["stages_heavy12/c6"] = c6.numpy()
+    store["stages_heavy12/energy"] = e2.numpy()
     np.savez_compressed(os.path.join(OUT, "reference_runs2.npz"), **store)
     sz = os.path.getsize(os.path.join(OUT, "reference_runs2.npz"))
     print(f"reference_runs2.npz: {len(store)} arrays, {sz/1024:.0f} kB")

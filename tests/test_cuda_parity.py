@@ -353,7 +353,8 @@ def test_tiled_degenerate_sizes(force_tiled):
 @pytest.mark.parametrize("case", ["c1_atm_f64", "c2_atm_f64", "c2_atm_cut8_f64", "mols6_atm_f64",
                                   "mols6_atm_cut12_f64", "water64_cut20_atm_f64", "close_f64", "ghost_f64",
                                   "two_atoms_f64", "one_atom_f64", "c2_atm_f32",
-                                  "heavy12_atm_f64", "heavy12_atm_cut9_f64", "ragged_atm_f64"])
+                                  "heavy12_atm_f64", "heavy12_atm_cut9_f64", "ragged_atm_f64",
+                                  "water100_atm_cut18_f64"])
 def test_tiled_atm_reference_runs(runs, case, force_tiled):
     """Three-body term of the tiled path (edge-owner enumeration, ordered cutoff rule)."""
     c = runs.case(case)
@@ -378,12 +379,13 @@ def test_rvdw_table_equals_dense(runs):
 # ---------------------------------------------------------------------------
 # stage-level drop-ins (README.rst:238-261 operator API)
 # ---------------------------------------------------------------------------
-def test_stage_functions_match_reference_stages(runs):
-    """cn_d3 -> weight_references -> atomic_c6 -> dispersion on the README batch,
-    against the unmodified reference's own intermediates."""
+@pytest.mark.parametrize("stages, case", [("stages_c2", "c2_atm_f64"), ("stages_heavy12", "heavy12_atm_f64")])
+def test_stage_functions_match_reference_stages(runs, stages, case):
+    """cn_d3 -> weight_references -> atomic_c6 -> dispersion on the README batch and on the
+    12-element cluster, against the unmodified reference's own intermediates."""
     import tad_dftd3_b200 as d3
 
-    c, r = runs.case("stages_c2"), runs.case("c2_atm_f64")
+    c, r = runs.case(stages), runs.case(case)
     dt = torch.double
     numbers = torch.from_numpy(r["numbers"]).to(DEV)
     positions = torch.from_numpy(r["positions"]).to(DEV)
