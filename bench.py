@@ -119,6 +119,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm
+def all_host_cores():
+    """The CPU baseline gets every host core: undo the GPU-local affinity of bind_host_thread_to_gpu."""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(os.cpu_count() or 1)
+
+
 def reference_step_fn(nmol_sample, seed=0):
     """Callable running energy+gradient of the reference CPU path on a sample; returns
     (fn, kind, pair_terms, sample description)."""
@@ -473,7 +482,7 @@ def main():
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            torch.set_num_threads(os.cpu_count() or 1)
+            all_host_cores()
             stepf, kind, rp, desc = reference_step_fn(args.ref_nmol)
             stepf()  # warm-up (thread pools, allocator)
             t0 = time.perf_counter()
@@ -629,7 +638,7 @@ def run_c4(args, rank, local, world, dev):
         if world == 1 and not args.no_cpu_baseline:
             # the reference cannot hold 50k atoms (20 GB per dense N x N temporary): time a
             # 2000-atom sub-cluster of the same structure and report its dense pair rate
-            torch.set_num_threads(os.cpu_count() or 1)
+            all_host_cores()
             centre = positions.mean(0)
             sub = torch.argsort((positions - centre).norm(dim=1))[:2000]
             sn, sf = count_pairs_single(positions[sub])
@@ -785,7 +794,7 @@ def run_c5a(args, rank, local, world, dev):
     }
     if world == 1 and not args.no_cpu_baseline:
         # the reference's ATM is dense N^3 (216 MB per temporary at N = 300): time a 300-atom sub-cluster
-        torch.set_num_threads(os.cpu_count() or 1)
+        all_host_cores()
         centre = positions.mean(0)
         sub = torch.argsort((positions - centre).norm(dim=1))[:300]
         t_sub, _, _ = count_triples(positions[sub], args.cutoff)
@@ -871,7 +880,7 @@ def run_c5b(args, rank, local, world, dev):
                            "Hessian copied back to pinned host memory"},
             "gpu_launches": launches}
     if not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
+        all_host_cores()
         sec, kind = reference_single(numbers, positions, PARAM, hessian=True)
         line["cpu_baseline"] = {"value": sec, "unit": "s", "cores": torch.get_num_threads(), "kind": kind,
                                 "sample": "the same 200-atom molecule, jacrev o jacrev through the reference"}
