@@ -123,7 +123,7 @@ def all_host_cores():
     """The CPU baseline gets every host core: undo the GPU-local affinity of bind_host_thread_to_gpu."""
     try:
         os.sched_setaffinity(0, range(os.cpu_count() or 1))
-    except (AttributeError, OSError):
+    except (AttributeError, OSError, ValueError):
         pass
     torch.set_num_threads(os.cpu_count() or 1)
 
