@@ -238,3 +238,29 @@ def test_plan_sorting_and_padding(monkeypatch):
     vals = torch.arange(plan.npad, dtype=dt)
     back = plan.scatter(vals)
     assert back[3] == 0 and torch.equal(back[plan.perm], vals[: plan.n])
+
+
+def test_three_body_centre_ownership_covers_every_sub_tile_once():
+    """`SystemRunner.atm_partition` + the kernel's index arithmetic (csrc/d3_atm3.cuh: a launch owns the
+    32-atom sub-tiles row_begin/32 + k*stride below row_end): over the ranks every sub-tile exactly once."""
+    from tad_dftd3_b200 import _lib, synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+    from tad_dftd3_b200.system import SUB, SystemPlan, SystemRunner
+
+    dt = torch.double
+    numbers, positions = syn.water_cluster(150, seed=2)               # 450 atoms -> 512 padded, 16 sub-tiles
+    par = _lib.Params()
+    par.s6, par.s8, par.a1, par.a2, par.s9 = 1.0, 0.79, 0.49, 5.73, 1.0
+    par.cutoff, par.cn_cutoff, par.kcn = 20.0, 25.0, 16.0
+    plan = SystemPlan(numbers, positions, COV_D3(dt)[numbers], R4R2(dt)[numbers], par.kcn)
+    for world in (1, 2, 3, 8):
+        owned = []
+        for rank in range(world):
+            run = SystemRunner(plan, REFCN(dt), syn.synthetic_c6_table(dt), par, None, world, syn.synthetic_rvdw_table(dt))
+            begin, end = run.atm_partition(rank, world)
+            stride = run._atm_stride
+            assert begin % SUB == 0 and end % SUB == 0
+            nsub_own = ((end - begin) // SUB + stride - 1) // stride            # the kernel's count
+            owned += [begin // SUB + k * stride for k in range(nsub_own)]
+        owned = [s for s in owned if s < plan.npad // SUB]
+        assert sorted(owned) == list(range(plan.npad // SUB)), (world, sorted(owned))
