@@ -16,7 +16,7 @@ from .disp import dftd3, hessian
 from .host import HostPipeline, bind_host_thread_to_gpu, dftd3_host
 from .reference import Reference
 
-__version__ = "0.1.0"
+from .__version__ import __version__
 
 __all__ = [
     "dftd3", "hessian", "dftd3_host", "HostPipeline", "bind_host_thread_to_gpu", "damping", "data", "defaults", "disp", "exception",

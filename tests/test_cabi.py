@@ -215,3 +215,25 @@ def test_staged_host_entry_chunk_schedule(lib):
     k = lib.d3b200_batch_host_chunks(4096, 0, b)
     assert list(b[: k + 1]) == [0, 148, 444, 1036, 1628, 2220, 2812, 3404, 3652, 3948, 4096]
     assert lib.d3b200_batch_host_chunks(0, 0, None) == 0
+
+
+def test_module_paths_of_the_reference_exist():
+    """Every import path of the reference package resolves here too (drop-in `import tad_dftd3_b200 as tad_dftd3`)."""
+    import importlib
+
+    for mod, names in {
+        "tad_dftd3_b200": ["dftd3", "damping", "data", "defaults", "disp", "model", "ncoord", "reference", "typing", "__version__"],
+        "tad_dftd3_b200.damping.atm": ["dispersion_atm"],
+        "tad_dftd3_b200.damping.rational": ["rational_damping"],
+        "tad_dftd3_b200.data.r4r2": ["R4R2"],
+        "tad_dftd3_b200.model.c6": ["atomic_c6", "_atomic_c6_full", "_atomic_c6_chunked", "AtomicC6_V1", "AtomicC6_V2"],
+        "tad_dftd3_b200.model.weights": ["gaussian_weight", "weight_references"],
+        "tad_dftd3_b200.ncoord": ["cn_d3", "exp_count"],
+        "tad_dftd3_b200.disp": ["dftd3", "dispersion", "dispersion2", "dispersion3"],
+        "tad_dftd3_b200.reference": ["Reference"],
+        "tad_dftd3_b200.exception": ["DFTD3Error"],
+        "tad_dftd3_b200.__version__": ["__version__"],
+    }.items():
+        m = importlib.import_module(mod)
+        for n in names:
+            assert hasattr(m, n), f"{mod}.{n}"
