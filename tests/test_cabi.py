@@ -237,3 +237,18 @@ def test_module_paths_of_the_reference_exist():
         m = importlib.import_module(mod)
         for n in names:
             assert hasattr(m, n), f"{mod}.{n}"
+
+
+def test_check_memory_contract(monkeypatch):
+    """Reference test/test_model/test_util.py: MemoryError above the total, ResourceWarning above the free memory."""
+    from tad_dftd3_b200.model import c6
+
+    x = torch.zeros(1000000, dtype=torch.double)
+    monkeypatch.setattr(c6, "memory_device", lambda device: (0.0, 0.0))
+    with pytest.raises(MemoryError):
+        c6._check_memory(x, x)
+    monkeypatch.setattr(c6, "memory_device", lambda device: (0.0, 1e10))
+    with pytest.warns(ResourceWarning):
+        c6._check_memory(torch.zeros(10000, dtype=torch.double), x)
+    monkeypatch.undo()
+    c6._check_memory(torch.zeros(10, dtype=torch.int64), torch.zeros(10, 7))     # plenty of memory: silent
