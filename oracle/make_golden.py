@@ -293,6 +293,10 @@ def part3():
     # lists of 100-250 atoms, i.e. several 64-entry tiles per centre in the triples-once kernel
     nw, pw = syn.water_cluster(100, seed=13)
     add("water100_atm_cut18_f64", nw, pw, PAR_TPSS0_ATM, cutoff=18.0)
+    # every damping parameter left at the reference's defaults (defaults.py:41-60), without and with s9
+    n3, p3 = syn.drug_like_batch(4, 6, 25, seed=17)
+    add("defaults_f64", n3, p3, {})
+    add("defaults_s9_f64", n3, p3, {"s9": 1.0})
     # stage outputs on the 12-element cluster (stage kernels on heavy elements)
     refobj, rcov_t, r4r2_t, rvdw_t = ref_tables(torch.double)
     cn = d3.ncoord.cn_d3(nh, ph, counting_function=d3.ncoord.exp_count, rcov=rcov_t[nh])
