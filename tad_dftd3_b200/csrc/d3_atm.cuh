@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(32 * kAtmWarps) system_atm_kernel(AtmArgs<S> P
               S d = S(0);
 #pragma unroll
               for (int b = 0; b < kNRef; ++b) d += Udi[b] * wk[b];
-              dci += we * (d * frcp(c6ik));
+              dci += we * (d * rcp0(c6ik));
             }
             if (!mjk) {          // long edge jk: its j-end
               S f = w6 * dec;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(32 * kAtmWarps) system_atm_kernel(AtmArgs<S> P
               S d = S(0);
 #pragma unroll
               for (int b = 0; b < kNRef; ++b) d += Udj[b] * wk[b];
-              dcj += we * (d * frcp(c6jk));
+              dcj += we * (d * rcp0(c6jk));
             }
           }
         }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(32 * kAtmWarps) system_atm_kernel(AtmArgs<S> P
       S f = two6 * Fij;
       gix = two6 * gix + f * dxij; giy = two6 * giy + f * dyij; giz = two6 * giz + f * dzij;
       gjx = two6 * gjx - f * dxij; gjy = two6 * gjy - f * dyij; gjz = two6 * gjz - f * dzij;
-      S gc = half6 * (Gij * frcp(c6ij));
+      S gc = half6 * (Gij * rcp0(c6ij));
       dci = half6 * dci + gc * dc6_i;
       dcj = half6 * dcj + gc * dc6_j;
     }
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(32 * kAtmWarps, 4) system_atm2_kernel(AtmArgs2
                 S d = S(0);
 #pragma unroll
                 for (int a = 0; a < kNRef; ++a) d += wiS[8 + a] * Tki[a];
-                dci += we * (d * frcp(c6ik));
+                dci += we * (d * rcp0(c6ik));
               }
               if (!mjk) {
                 S f = w6 * (k0r5 * (qt + pq - pt) + common * frcp(c2));
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(32 * kAtmWarps, 4) system_atm2_kernel(AtmArgs2
                 S d = S(0);
 #pragma unroll
                 for (int a = 0; a < kNRef; ++a) d += dwj[a] * Tkj[a];
-                dcj += we * (d * frcp(c6jk));
+                dcj += we * (d * rcp0(c6jk));
               }
             }
           }
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(32 * kAtmWarps, 4) system_atm2_kernel(AtmArgs2
         S f = two6 * Fij;
         gix = two6 * gix + f * dxij; giy = two6 * giy + f * dyij; giz = two6 * giz + f * dzij;
         gjx = two6 * gjx - f * dxij; gjy = two6 * gjy - f * dyij; gjz = two6 * gjz - f * dzij;
-        S gc = half6 * (Gij * frcp(c6ij));
+        S gc = half6 * (Gij * rcp0(c6ij));
         dci = half6 * dci + gc * dc6_i;
         dcj = half6 * dcj + gc * dc6_j;
       }

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       S c6 = S(0), d_i = S(0), d_n = S(0);
 #pragma unroll
       for (int a = 0; a < kNRef; ++a) { c6 += wiS[a] * Tn[a]; d_i += wiS[8 + a] * Tn[a]; d_n += wiS[a] * Tdn[a]; }
-      const S ic6 = frcp(c6);
+      const S ic6 = rcp0(c6);
       Pair2<S>* r = reinterpret_cast<Pair2<S>*>(rec + (size_t)p * kAtm3Rec);
       Pair2<S> q;
       q.a = an.x; q.b = an.y; r[0] = q;
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
             S dk = wsh[wid][kk][kNRef][lane] * Tj[0], dj = wsh[wid][kk][0][lane] * Td[0];
 #pragma unroll
             for (int a = 1; a < kNRef; ++a) { dk += wsh[wid][kk][kNRef + a][lane] * Tj[a]; dj += wsh[wid][kk][a][lane] * Td[a]; }
-            const S qc = act[kk] ? we * frcp(c6jk) : S(0);
+            const S qc = act[kk] ? we * rcp0(c6jk) : S(0);
             Dk[kk] += qc * dk;
             vals[1 % NV] += fa; vals[2 % NV] += we; vals[3 % NV] += vx; vals[4 % NV] += vy; vals[5 % NV] += vz;
             vals[6 % NV] += qc * dj;

@@ -98,7 +98,8 @@ D3_HD float sqr(float a) { return sqrtf(a); }
 D3_HD double sqr(double a) { return sqrt(a); }
 template <typename T> D3_HD Dual<T> sqr(Dual<T> a) {
   T s = sqr(a.v);
-  return Dual<T>(s, T(0.5) * a.d / s);
+  // (sqrt at exactly 0: the reference clamps |C6 C6 C6| at eps before its sqrt, whose gradient is 0 there)
+  return Dual<T>(s, s > T(0) ? T(0.5) * a.d / s : T(0));
 }
 
 D3_HD float ex(float a) { return expf(a); }
@@ -205,6 +206,10 @@ template <typename T> D3_HD Dual<T> fex(Dual<T> a) {
   T e = fex(a.v);
   return Dual<T>(e, e * a.d);
 }
+
+// 1/c for the dC6/C6 factors of the three-body backward: a pair whose C6 is exactly 0 (zero block of a
+// custom table, underflow in float) has no C6 derivative in the reference (eps clamp before the sqrt).
+template <typename S> D3_HD S rcp0(S c) { return val(c) != val(S(0)) ? frcp(c) : S(0); }
 
 // max(a, lo) on the value (tangent follows the selected branch)
 D3_HD float fmx(float a, float lo) { return a < lo ? lo : a; }

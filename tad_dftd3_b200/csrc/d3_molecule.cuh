@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
             S c6 = U[0] * wj[0], dc6 = Ud[0] * wj[0];
 #pragma unroll
             for (int aa = 1; aa < kNRef; ++aa) { c6 += U[aa] * wj[aa]; dc6 += Ud[aa] * wj[aa]; }
-            decn += (B(0.5) * sixth) * (Gj * (dc6 * rcp(c6)));
+            decn += (B(0.5) * sixth) * (Gj * (dc6 * rcp0(c6)));
           }
         }
       }

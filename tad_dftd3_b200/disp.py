@@ -35,6 +35,10 @@ def _is_functorch(x: Tensor) -> bool:
     return bool(f.is_batchedtensor(x) or f.is_gradtrackingtensor(x))
 
 
+def _is_functorch_grad(x: Tensor) -> bool:
+    return bool(torch._C._functorch.is_gradtrackingtensor(x))
+
+
 def _plain(t: Tensor) -> Tensor:
     """Strip functorch grad-tracking wrappers from a CONSTANT tensor before it
     is cached (tensors created inside jacrev/vmap are wrapped at the live
@@ -186,6 +190,16 @@ def dftd3(
         if r4r2.shape != numbers.shape:
             raise ValueError("Shape of expectation values is not consistent with atomic numbers.")
         r4r2_t, r4r2_pe = r4r2, False
+
+    # The reference propagates gradients into every tensor argument through autograd; the kernels
+    # provide them for positions and s6, s8, a1, a2, s9 only.  Anything else that asks for a gradient
+    # is refused instead of being detached silently (same rule as the stage functions).
+    for name, t in (("alp", param.get("alp")), ("cutoff", cutoff), ("rcov", rcov), ("r4r2", r4r2), ("rvdw", rvdw)):
+        if isinstance(t, Tensor) and (t.requires_grad or _is_functorch_grad(t)):
+            raise NotImplementedError(
+                f"tad_dftd3_b200 does not provide derivatives with respect to `{name}` "
+                "(analytic derivatives exist for positions and s6, s8, a1, a2, s9)."
+            )
 
     atm = _atm_requested(param)
     rvdw_t, rvdw_mode = None, 0

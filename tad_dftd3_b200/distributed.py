@@ -92,7 +92,13 @@ class _ShardedD3(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gE):
         numbers, positions, rcov, r4r2, refcn, refc6 = ctx.saved_tensors
-        if ctx.grad1 is not None and gE.numel() > 1 and all(s == 0 for s in gE.stride()):
+        uniform = ctx.grad1 is not None and gE.numel() > 1 and all(s == 0 for s in gE.stride())
+        if _world(ctx.group)[1] > 1:
+            # every rank must take the same branch (the general path issues collectives): agree on it
+            flag = torch.tensor([1 if uniform else 0], dtype=torch.int32, device=positions.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=ctx.group)
+            uniform = bool(int(flag))
+        if uniform:
             return (None, ctx.grad1 * gE.reshape(-1)[0]) + (None,) * 8
         plan = SystemPlan(numbers, positions, rcov, r4r2, ctx.par.kcn, *ctx.tables)
         runner = SystemRunner(plan, refcn, refc6, ctx.par, gE, _world(ctx.group)[1], ctx.rvdw)

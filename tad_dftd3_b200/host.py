@@ -208,7 +208,12 @@ class HostPipeline:
                 if sync:
                     stream.synchronize()
             outs = (energy_out.reshape(*lead, n), grad_out.reshape(*lead, n, 3))
-            if caller_outputs and g_in is None:
+            # The fast path re-issues the prepared call with the SAME host pointers, so it is only
+            # valid when those pointers are the caller's own storage: a private contiguous / int64
+            # copy made above would go stale as soon as the caller updates its tensor in place.
+            aliased = (x.data_ptr() == positions.data_ptr() and z.data_ptr() == numbers.data_ptr()
+                       and positions.is_contiguous() and numbers.is_contiguous())
+            if caller_outputs and g_in is None and aliased:
                 import weakref
 
                 self._fast = (fkey, tuple(weakref.ref(t) for t in (numbers, positions, energy_out, grad_out)),

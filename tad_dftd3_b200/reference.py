@@ -119,10 +119,24 @@ class Reference:
 
     # ---- helpers for the CUDA path (not part of the reference API) ----------
     def _prepared(self, device: torch.device, dtype: torch.dtype):
-        """(cn, c6, symmetric) contiguous on `device`/`dtype`, cached per object."""
+        """(cn, c6, symmetric) contiguous on `device`/`dtype`, cached per object.
+
+        The kernels index the tables as `[104, 7]` / `[104, 104, 7, 7]` (`refc6 + (Zi*104+Zj)*49`),
+        so any other shape is rejected here instead of being read out of bounds.  The cache entry is
+        keyed on the identity and the version counters of `cn` / `c6`: reassigning or editing either
+        in place invalidates it."""
+        from .defaults import MAX_ELEMENT
+
+        nz, nref = MAX_ELEMENT, 7
+        if tuple(self.cn.shape) != (nz, nref) or tuple(self.c6.shape) != (nz, nz, nref, nref):
+            raise ValueError(
+                f"tad_dftd3_b200 kernels need reference tables of shape cn ({nz}, {nref}) and "
+                f"c6 ({nz}, {nz}, {nref}, {nref}); got cn {tuple(self.cn.shape)}, c6 {tuple(self.c6.shape)}"
+            )
         key = (str(device), dtype)
+        stamp = (id(self.cn), getattr(self.cn, "_version", 0), id(self.c6), getattr(self.c6, "_version", 0))
         hit = self._cache.get(key)
-        if hit is None:
+        if hit is None or hit[3] != stamp:
             from .disp import _plain
 
             # (inside jacrev / vmap even `detach()` of a plain tensor comes back wrapped at the live
@@ -130,6 +144,6 @@ class Reference:
             cn = _plain(_plain(self.cn).detach().to(device=device, dtype=dtype).contiguous())
             c6 = _plain(_plain(self.c6).detach().to(device=device, dtype=dtype).contiguous())
             sym = bool(torch.allclose(c6, c6.permute(1, 0, 3, 2), rtol=1e-6 if dtype == torch.float32 else 1e-12, atol=0))
-            hit = (cn, c6, sym)
+            hit = (cn, c6, sym, stamp)
             self._cache[key] = hit
-        return hit
+        return hit[:3]

@@ -221,3 +221,56 @@ def test_c5a_atm_10k_atoms_properties(ref):
         assert_close(g5.cpu(), g.cpu(), 1e-8, 1e-13, "edge-owner vs triples-once ATM gradients")
     finally:
         d3.data.set_vdw_pairwise(None)
+
+
+# ---------------------------------------------------------------------------
+# Full-size comparisons with the blocked fp64 C oracle (oracle/d3_blocked.c, pinned
+# against the unmodified reference by tests/test_blocked_oracle.py): EVERY atom,
+# energies and gradients, at BASELINE.json's tolerances (1e-10 relative, 1e-12 absolute).
+# ---------------------------------------------------------------------------
+def _blocked(numbers, positions, param, cutoff, g=None):
+    from d3_blocked import dftd3_blocked
+
+    refcn, refc6, rcov, r4r2, rvdw = tables(torch.double)
+    z = numbers.cpu()
+    return dftd3_blocked(z, positions.cpu(), param, refcn=refcn, refc6=refc6, rcov=rcov[z], r4r2=r4r2[z],
+                         rvdw_table=rvdw, g=None if g is None else g.cpu(), cutoff=cutoff)
+
+
+def test_c4_50k_atoms_every_atom_against_blocked_oracle(c4, ref):
+    """Config 4 at the default cutoffs (50 / 25 Bohr): energies AND gradients of all 50 001 atoms
+    (core and surface alike), unit cotangent and a random cotangent."""
+    import tad_dftd3_b200 as d3
+
+    numbers, positions = c4
+    e, g = run(numbers, positions, ref)
+    out = _blocked(numbers, positions, PARAM, 50.0)
+    assert_close(e.cpu(), out["energy"], 1e-10, 1e-12, "c4 energies, all atoms")
+    assert_close(g.cpu(), out["grad"], 1e-10, 1e-12, "c4 gradients, all atoms")
+    # general cotangent: takes the D3Vjp route of the tiled path
+    gen = torch.Generator().manual_seed(17)
+    w = (torch.rand(numbers.shape, dtype=torch.double, generator=gen) + 0.5)
+    par = {k: torch.tensor(v, dtype=torch.double) for k, v in PARAM.items()}
+    x = positions.clone().requires_grad_(True)
+    ew = d3.dftd3(numbers, x, par, ref=ref)
+    (gw,) = torch.autograd.grad((ew * w.to(DEV)).sum(), x)
+    outw = _blocked(numbers, positions, PARAM, 50.0, g=w)
+    assert_close(gw.cpu(), outw["grad"], 1e-10, 1e-12, "c4 gradients, random cotangent")
+
+
+def test_c5a_atm_10k_atoms_every_atom_against_blocked_oracle(ref):
+    """Config 5a (10 002 atoms, s9 = 1, cutoff 25 Bohr): energies and gradients of every atom."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+
+    numbers, positions = syn.water_cluster(3334, seed=0)
+    numbers, positions = numbers.to(DEV), positions.to(DEV)
+    d3.data.set_vdw_pairwise(syn.synthetic_rvdw_table(torch.double))
+    try:
+        par = dict(PARAM, s9=1.0)
+        e, g = run(numbers, positions, ref, par, cutoff=torch.tensor(25.0))
+    finally:
+        d3.data.set_vdw_pairwise(None)
+    out = _blocked(numbers, positions, par, 25.0)
+    assert_close(e.cpu(), out["energy"], 1e-10, 1e-12, "c5a energies, all atoms")
+    assert_close(g.cpu(), out["grad"], 1e-10, 1e-12, "c5a gradients, all atoms")
