@@ -32,7 +32,7 @@ import torch.distributed as dist
 from torch import Tensor
 
 from . import defaults
-from .system import SystemPlan, SystemRunner, row_partition
+from .system import TILE, SystemPlan, SystemRunner, row_partition
 
 __all__ = ["run_sharded", "dftd3_sharded"]
 
@@ -43,22 +43,50 @@ def _world(group):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
-def _gather_rows(t: Tensor, group) -> None:
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+def _equal_rows(npad: int, world: int) -> bool:
+    return world >= 1 and (npad // TILE) % world == 0
+
+
+def _exchange(t: Tensor, rows, group, mode: str) -> None:
+    """Complete a per-atom array on every rank.
+
+    mode "gather": every rank computed complete values for ITS rows (full-row sweeps, equal
+    contiguous row ranges): one in-place all-gather -- each rank sends N / world values.
+    mode "sum": contributions to any row may come from any rank (pairs-once sweeps, the
+    three-body term, ragged row ranges): all-reduce over arrays that are zero where a rank
+    did not contribute."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+        return
+    if mode == "gather":
+        flat = t.reshape(-1)
+        per = flat.numel() // t.shape[0]
+        dist.all_gather_into_tensor(flat, flat[rows[0] * per: rows[1] * per], group=group)
+    else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
-def run_sharded(runner, want_grad: bool, group=None):
+def run_sharded(runner, want_grad: bool, group=None, zero: bool = True):
     """Drive the sweeps of `runner` on this rank's rows and exchange the
     per-atom arrays.  Returns the rank's row range; afterwards `runner.energy`
-    (and `runner.grad`) are complete on every rank."""
+    (and `runner.grad`) are complete on every rank.
+
+    Exchange steps, exactly where the data dependencies force them: CN after the CN sweep,
+    dL/dCN after the pair (and three-body) sweep, E and dL/dx at the end.  Full-row sweeps on
+    equal row ranges use in-place all-gathers; everything else sums (see `_exchange`)."""
     rank, world = _world(group)
     part = getattr(runner, "partition", None)
     rows = part(rank, world) if part is not None else row_partition(runner.plan.npad, world)[rank]
-    for t in (runner.cn, runner.decn, runner.energy, runner.grad):
-        t.zero_()
+    npad = runner.plan.npad
+    contiguous = world > 1 and _equal_rows(npad, world) and rows == row_partition(npad, world)[rank] \
+        and not getattr(runner, "symmetric", False)
+    atm_on = getattr(runner, "sweep_atm", None) is not None and getattr(runner.par, "s9", 0.0) != 0.0
+    mode_cn = "gather" if contiguous else "sum"
+    mode_out = "gather" if (contiguous and not atm_on) else "sum"
+    if zero:
+        for t in (runner.cn, runner.decn, runner.energy, runner.grad):
+            t.zero_()
     runner.sweep_cn(rows)
-    _gather_rows(runner.cn, group)
+    _exchange(runner.cn, rows, group, mode_cn)
     runner.weights()
     runner.sweep_pair(want_grad, rows)
     atm = getattr(runner, "sweep_atm", None)
@@ -67,30 +95,38 @@ def run_sharded(runner, want_grad: bool, group=None):
         # adds to energy / grad / dL/dCN of every atom of a triple (no-op when s9 == 0)
         atm(want_grad, apart(rank, world) if apart is not None else rows)
     if want_grad:
-        _gather_rows(runner.decn, group)
+        _exchange(runner.decn, rows, group, mode_out)
         runner.sweep_cnbwd(rows)
-        _gather_rows(runner.grad, group)
-    _gather_rows(runner.energy, group)
+        _exchange(runner.grad, rows, group, mode_out)
+    _exchange(runner.energy, rows, group, mode_out)
     return rows
 
 
 class _ShardedD3(torch.autograd.Function):
+    """Energies of one structure with the rows sharded over `group`, through the cached
+    `SystemEngine` of the structure (plan, work arrays and the CUDA graph of the sweep
+    sequence are reused while the same `numbers` tensor keeps coming back)."""
+
     @staticmethod
     def forward(ctx, numbers, positions, rcov, r4r2, refcn, refc6, par, group, tables=(False, False), rvdw=None):
-        plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn, *tables)
-        runner = SystemRunner(plan, refcn, refc6, par, None, _world(group)[1], rvdw)
+        from .engine import engine_for
+
         # When the positions require grad the sweeps run with the gradient right away
         # (unit cotangent): `energy.sum().backward()` is then one multiply, as in
         # ops.D3Energy; any other cotangent repeats the sweeps in backward.
         spec = bool(positions.requires_grad)
-        run_sharded(runner, spec, group)
+        eng = engine_for(numbers, positions, rcov, r4r2, refcn, refc6, par, tables=tables, rvdw=rvdw, group=group,
+                         want_grad=spec)
+        e, gr = eng.step(positions)
         ctx.save_for_backward(numbers, positions, rcov, r4r2, refcn, refc6)
         ctx.par, ctx.group, ctx.tables, ctx.rvdw = par, group, tables, rvdw
-        ctx.grad1 = plan.scatter(runner.grad) if spec else None
-        return plan.scatter(runner.energy)
+        ctx.grad1 = gr.clone() if spec else None
+        return e.clone()
 
     @staticmethod
     def backward(ctx, gE):
+        from .engine import engine_for
+
         numbers, positions, rcov, r4r2, refcn, refc6 = ctx.saved_tensors
         uniform = ctx.grad1 is not None and gE.numel() > 1 and all(s == 0 for s in gE.stride())
         if _world(ctx.group)[1] > 1:
@@ -100,10 +136,11 @@ class _ShardedD3(torch.autograd.Function):
             uniform = bool(int(flag))
         if uniform:
             return (None, ctx.grad1 * gE.reshape(-1)[0]) + (None,) * 8
-        plan = SystemPlan(numbers, positions, rcov, r4r2, ctx.par.kcn, *ctx.tables)
-        runner = SystemRunner(plan, refcn, refc6, ctx.par, gE, _world(ctx.group)[1], ctx.rvdw)
-        run_sharded(runner, True, ctx.group)
-        return None, plan.scatter(runner.grad), None, None, None, None, None, None, None, None
+        eng = engine_for(numbers, positions, rcov, r4r2, refcn, refc6, ctx.par, tables=ctx.tables, rvdw=ctx.rvdw,
+                         group=ctx.group, want_grad=True, general_g=True)
+        eng.set_cotangent(gE)
+        _, gr = eng.step(positions)
+        return None, gr.clone(), None, None, None, None, None, None, None, None
 
 
 def dftd3_sharded(numbers: Tensor, positions: Tensor, param: dict, *, ref=None, rcov=None,

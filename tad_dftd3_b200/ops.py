@@ -217,29 +217,32 @@ def _tiled(c: "_Call", order: int) -> bool:
 
 
 def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None, want_p: bool = False):
-    from .system import SystemPlan, SystemRunner
-
     if c.par.s9 != 0.0 and c.st.rvdw_mode != 1:
         raise NotImplementedError(
             "the tiled path evaluates the ATM term from the [104,104] element-pair "
             "rvdw table only (pass rvdw=None); a dense per-pair rvdw is limited to "
             "structures that fit the fused kernel"
         )
+    from .engine import engine_for
+
     es, gs, ps = [], [], []
     for b in range(c.nflat):
         z = numbers if (c.nflat == 1 and numbers.dim() == 1 and numbers.dtype == torch.int64) else c.z[b]
         rcov = c.rcov if c.st.rcov_per_element else c.rcov[b]
         r4r2 = c.r4r2 if c.st.r4r2_per_element else c.r4r2[b]
-        plan = SystemPlan(z, c.x[b], rcov, r4r2, c.st.kcn, c.st.rcov_per_element, c.st.r4r2_per_element)
-        run = SystemRunner(plan, c.refcn, c.refc6, c.par, None if g is None else g[b], 1, c.rvdw)
+        # plan, work arrays and the CUDA graph of the sweep sequence live in a cached engine while
+        # the same numbers tensor keeps coming back (MD / optimisation loops)
+        eng = engine_for(z, c.x[b], rcov, r4r2, c.refcn, c.refc6, c.par,
+                         tables=(c.st.rcov_per_element, c.st.r4r2_per_element), rvdw=c.rvdw,
+                         want_grad=want_grad, general_g=g is not None)
+        if g is not None:
+            eng.set_cotangent(g[b])
+        e, gr = eng.step(c.x[b])
+        es.append(e.clone())
         if want_grad:
-            e, gr = run.run_vjp()
-            gs.append(gr)
-        else:
-            e = run.run_energy()
+            gs.append(gr.clone())
         if want_p:
-            ps.append(run.param_gradient())
-        es.append(e)
+            ps.append(eng.runner.param_gradient())
     if want_p:
         return torch.stack(es), (torch.stack(gs) if want_grad else None), torch.stack(ps)
     return torch.stack(es), (torch.stack(gs) if want_grad else None)

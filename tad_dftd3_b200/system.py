@@ -59,12 +59,13 @@ class _Static:
     `ORDER_MAX_AGE` calls while the same `numbers` tensor keeps coming back
     (MD / optimisation loops)."""
 
-    def __init__(self, numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table):
+    def __init__(self, numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table, pad_tiles=1):
         dev, dt = positions.device, positions.dtype
         idx = torch.nonzero(numbers != 0).reshape(-1)
         n = int(idx.numel())
         self.n = n
-        self.npad = npad = max(TILE, -(-n // TILE) * TILE)
+        unit = TILE * max(1, int(pad_tiles))          # equal tile counts per rank: pad to world * 128
+        self.npad = npad = max(unit, -(-n // unit) * unit)
         z = numbers[idx]
         if n:
             o1 = morton_order(positions.detach()[idx])
@@ -105,20 +106,20 @@ class _Static:
         self.age = 0
 
 
-def _static_for(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table) -> _Static:
+def _static_for(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table, pad_tiles=1) -> _Static:
     import weakref
 
     def tkey(t, table):
         return ("table" if table else "atom", id(t), t._version)
 
     key = (id(numbers), numbers._version, positions.dtype, str(positions.device), float(kcn),
-           tkey(rcov, rcov_table), tkey(r4r2, r4r2_table))
+           tkey(rcov, rcov_table), tkey(r4r2, r4r2_table), int(pad_tiles))
     hit = _static_cache.get(key)
     if hit is not None and hit[0]() is numbers and hit[1]() is rcov and hit[2]() is r4r2 \
             and hit[3].age < ORDER_MAX_AGE:
         hit[3].age += 1
         return hit[3]
-    st = _Static(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table)
+    st = _Static(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table, pad_tiles)
     if len(_static_cache) > 32:
         _static_cache.clear()
     try:
@@ -135,28 +136,19 @@ class SystemPlan:
     with `*_table=True`, per-element tables indexed by Z."""
 
     def __init__(self, numbers: Tensor, positions: Tensor, rcov: Tensor, r4r2: Tensor, kcn: float,
-                 rcov_table: bool = False, r4r2_table: bool = False):
+                 rcov_table: bool = False, r4r2_table: bool = False, pad_tiles: int = 1):
         dev, dt = positions.device, positions.dtype
         self.natoms_in = numbers.shape[0]
-        st = _static_for(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table)
+        st = _static_for(numbers, positions, rcov, r4r2, kcn, rcov_table, r4r2_table, pad_tiles)
         self.static = st
         self.n, self.npad, self.perm, self.z, self.sqrtq = st.n, st.npad, st.perm, st.z, st.sqrtq
         n, npad = st.n, st.npad
         self.dtype, self.device = dt, dev
         if dev.type == "cuda" and os.environ.get("TAD_DFTD3_B200_TORCH_PACK") != "1":
             # one launch: gather + AoS packing + sub-tile boxes (d3b200_system_pack_*)
-            x = positions.detach()
-            x = x if x.is_contiguous() else x.contiguous()
             self.atoms = torch.empty(npad, 4, dtype=dt, device=dev)
             self.box = torch.empty(npad // SUB, 6, dtype=dt, device=dev)
-            fn = getattr(_lib.lib(), "d3b200_system_pack_" + ("f64" if dt == torch.float64 else "f32"))
-            _lib.launch_count += 1
-            with torch.cuda.device(dev):
-                _lib.check(fn(npad, n, C.c_void_p(st.perm.data_ptr()), C.c_void_p(x.data_ptr()),
-                              C.c_void_p(st.template.data_ptr()), C.c_void_p(st.z.data_ptr()),
-                              C.c_void_p(self.atoms.data_ptr()), C.c_void_p(self.box.data_ptr()),
-                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-            self._keep = x
+            self.repack(positions)
             return
         # host tensors (the CPU tests of the sharding logic): the same arrays with tensor operations
         atoms = st.template.clone()
@@ -170,6 +162,23 @@ class SystemPlan:
         lo = torch.where(st.empty, xyz[:, 0, :], lo)
         hi = torch.where(st.empty, xyz[:, 0, :], hi)
         self.box = torch.cat([lo, hi], 1).contiguous()
+
+    def repack(self, positions: Tensor) -> None:
+        """Refresh `atoms` / `box` IN PLACE from new positions of the same structure (same
+        sorted order; the boxes are recomputed, so the order only matters for efficiency).
+        One launch of `d3b200_system_pack_*`; the arrays keep their addresses, which is what
+        lets a captured CUDA graph of the sweeps be replayed for every step."""
+        st, dev, dt = self.static, self.device, self.dtype
+        x = positions.detach()
+        x = x if x.is_contiguous() else x.contiguous()
+        fn = getattr(_lib.lib(), "d3b200_system_pack_" + ("f64" if dt == torch.float64 else "f32"))
+        _lib.launch_count += 1
+        with torch.cuda.device(dev):
+            _lib.check(fn(self.npad, self.n, C.c_void_p(st.perm.data_ptr()), C.c_void_p(x.data_ptr()),
+                          C.c_void_p(st.template.data_ptr()), C.c_void_p(st.z.data_ptr()),
+                          C.c_void_p(self.atoms.data_ptr()), C.c_void_p(self.box.data_ptr()),
+                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        self._keep = x
 
     def elements(self):
         """(zlist int32 [E], eidx int8 [npad]) -- distinct elements and each atom's index (-1 = padding)."""
@@ -205,6 +214,7 @@ class SystemRunner:
         self.sfx = "f64" if dt == torch.float64 else "f32"
         self.auxt = plan.aux(g)
         buf = torch.zeros(22 * npad, dtype=dt, device=dev)      # one allocation, one fill
+        self.buf = buf
         self.cn, self.decn, self.energy = buf[:npad], buf[npad:2 * npad], buf[2 * npad:3 * npad]
         self.grad = buf[3 * npad:6 * npad].view(npad, 3)
         self.w, self.dw = buf[6 * npad:14 * npad].view(npad, 8), buf[14 * npad:22 * npad].view(npad, 8)

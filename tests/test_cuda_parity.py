@@ -530,3 +530,87 @@ def test_denormal_weight_norm_regression():
     assert_close(out["energy"], e.detach(), RTOL, ATOL, "energy")
     assert_close(out["grad"], grads[0], RTOL, ATOL, "grad")
     assert_close(out["pgrad"], [float(x) for x in grads[1:]], RTOL, ATOL, "pgrad")
+
+
+# ---------------------------------------------------------------------------
+# Persistent engine of the tiled path (tad_dftd3_b200/engine.py): cached plan + work arrays +
+# CUDA graph of the sweep sequence must give what the blocked oracle gives, step after step.
+# ---------------------------------------------------------------------------
+def _blocked(numbers, positions, param, cutoff, g=None):
+    from d3_blocked import dftd3_blocked
+
+    refcn, refc6, rcov, r4r2, rvdw = tables(torch.double)
+    z = numbers.cpu()
+    return dftd3_blocked(z, positions.cpu(), param, refcn=refcn, refc6=refc6, rcov=rcov[z], r4r2=r4r2[z],
+                         rvdw_table=rvdw, g=None if g is None else g.cpu(), cutoff=cutoff)
+
+
+@pytest.mark.parametrize("atm", [False, True])
+def test_engine_steps_eager_and_graph_against_blocked_oracle(atm):
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import _lib, synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2
+    from tad_dftd3_b200.engine import SystemEngine
+
+    dt = torch.double
+    numbers, positions = syn.water_cluster(400, seed=11)                    # 1200 atoms: beyond the fused limit
+    numbers = numbers.clone()
+    numbers[[7, 400]] = 0                                                  # ghost atoms
+    numbers, positions = numbers.to(DEV), positions.to(DEV)
+    refcn, refc6, _, _, rvdw = tables(dt, DEV)
+    param = {"s6": 1.0, "s8": 0.78981345, "a1": 0.49484001, "a2": 5.73083694}
+    cutoff = 50.0
+    par = _lib.Params()
+    par.s6, par.s8, par.a1, par.a2 = param["s6"], param["s8"], param["a1"], param["a2"]
+    par.s9, par.rs9, par.alp, par.cutoff, par.cn_cutoff, par.kcn = 0.0, 1.3333333730697632, 14.0, cutoff, 25.0, 16.0
+    if atm:
+        cutoff = par.cutoff = 14.0
+        par.s9 = param["s9"] = 1.0
+    eng = SystemEngine(numbers, positions, COV_D3(dt, DEV), R4R2(dt, DEV), refcn, refc6, par, tables=(True, True),
+                       rvdw=rvdw if atm else None)
+    for step in range(5):                                                   # steps 0, 1 eager; 2.. graph replays
+        x = positions + 0.02 * step * torch.cos(positions * (1 + step))
+        e, g = eng.step(x)
+        out = _blocked(numbers, x, param, cutoff)
+        assert_close(e.cpu(), out["energy"], RTOL, ATOL, f"engine step {step} energy")
+        assert_close(g.cpu(), out["grad"], RTOL, ATOL, f"engine step {step} grad")
+        assert (e[[7, 400]] == 0).all() and (g[[7, 400]] == 0).all()
+    assert eng._graph is not None, "the sweep sequence was not captured"
+    # general cotangent
+    gen = torch.Generator().manual_seed(2)
+    w = (torch.rand(numbers.shape, dtype=dt, generator=gen) + 0.5).to(DEV)
+    eng2 = SystemEngine(numbers, positions, COV_D3(dt, DEV), R4R2(dt, DEV), refcn, refc6, par, tables=(True, True),
+                        rvdw=rvdw if atm else None, general_g=True)
+    for step in range(4):
+        x = positions + 0.02 * step * torch.cos(positions * (1 + step))
+        ws = w * (1.0 + 0.1 * step)
+        eng2.set_cotangent(ws)
+        _, g = eng2.step(x)
+        out = _blocked(numbers, x, param, cutoff, g=ws)
+        assert_close(g.cpu(), out["grad"], RTOL, ATOL, f"engine step {step} grad, random cotangent")
+
+
+def test_dftd3_large_structure_reuses_engine_and_tracks_positions():
+    """`dftd3()` on a structure beyond the fused limit goes through the cached engine: repeated calls
+    with the same numbers tensor and NEW positions must follow the positions."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.engine import _engines
+
+    dt = torch.double
+    numbers, positions = syn.water_cluster(380, seed=12)
+    numbers, positions = numbers.to(DEV), positions.to(DEV)
+    refcn, refc6, *_ = tables(dt, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    param = {"s6": 1.0, "s8": 0.78981345, "a1": 0.49484001, "a2": 5.73083694}
+    par = {k: torch.tensor(v, dtype=dt) for k, v in param.items()}
+    n0 = len(_engines)
+    for step in range(4):
+        x = (positions + 0.03 * step).clone().requires_grad_(True)
+        x.data[:, 0] += 0.01 * step * torch.sin(positions[:, 1])
+        e = d3.dftd3(numbers, x, par, ref=ref)
+        (g,) = torch.autograd.grad(e.sum(), x)
+        out = _blocked(numbers, x.detach(), param, 50.0)
+        assert_close(e.detach().cpu(), out["energy"], RTOL, ATOL, f"call {step} energy")
+        assert_close(g.cpu(), out["grad"], RTOL, ATOL, f"call {step} grad")
+    assert len(_engines) <= n0 + 1
