@@ -1,32 +1,44 @@
 #!/usr/bin/env python
 """
-Benchmark of the D3(BJ) hot path (BASELINE.json metric: energy+gradient
-pair-terms/s, fp64).
+Benchmark of the D3(BJ) hot path (BASELINE.json metric: "D3(BJ) energy+grad pair-terms/s
+fp64 at 1/2/4/8 B200; ATM triples/s").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload c3|c4|c5a] [--nmol 4096]
+                    [--workload all|c3|c4|c5a|c5b] [--scaling strong|weak]
 
-One "step" = one pass of the hot path (atom-resolved energies AND the complete
-analytic gradient) over one batch of synthetic structures.  Default workload
-(`c3`): BASELINE config 3, 4096 chain-grown drug-like molecules of 50..120
-atoms, zero-padded to 120, D3(BJ) two-body + CN, fp64; under torchrun every
-rank owns its own 4096-molecule shard (structures are independent: no
-data-path collective; weak scaling).
+One "step" = one pass of the hot path (atom-resolved energies AND the complete analytic
+gradient) over one batch of synthetic input.  The printed JSON line (rank 0) is the c3
+workload -- BASELINE config 3: ONE fixed batch of 4096 chain-grown drug-like molecules of
+50..120 atoms, zero-padded to 120, D3(BJ) two-body + CN, fp64 -- and, with the default
+`--workload all`, carries the other two throughput configs as sub-records measured in the
+same run:  "c4" (config 4: one 50 001-atom water cluster, rows sharded over the GPUs, CN /
+dL/dCN / E / gradient exchanged over NCCL) and "c5a" (config 5a: ATM three-body term on a
+10 002-atom cluster, cutoff 25 Bohr -> triples/s).
 
-Printed JSON line (rank 0):
-  value     pair-terms/s, inputs resident in HBM, one fused launch per step
-            (`d3b200_batch_vjp_f64` through the Python binding), CUDA events,
-            L2 flushed between steps, max over ranks;
-  e2e       the same metric through the public API (`dftd3()` +
-            `autograd.grad`) starting from pinned HOST buffers: H2D of numbers
-            and positions and D2H of energies and gradients inside the timed
-            region;
-  roofline  FP64 FMA pipe: algorithmic flops per launch (140 per
-            pair-term within 25 Bohr, 89 beyond) / event time of the kernel,
-            against an FP64 FMA-chain peak measured live on the same GPU;
-  cpu_baseline  the reference's own torch CPU path (unmodified reference
-            source over the tad-mctc stand-in when `baseline/_ref` travelled,
-            else the oracle port), on a bounded sample, all host threads.
+Multi-GPU (torchrun, one rank per GPU): STRONG scaling.  The fixed 4096-molecule batch is
+split by structure over the ranks (balanced on the pair count, no data-path collective); the
+fixed large structures are split by rows / centres (NCCL exchanges inside a CUDA graph).
+Every N > 1 record carries `checks.max_rel_err_vs_single_gpu`: the sharded result against
+the same input evaluated on ONE GPU in the same run.  `--scaling weak` gives every rank its
+own 4096-molecule batch (round 1's definition).
+
+Keys of the line:
+  value        pair-terms/s, inputs resident in HBM: all pairs of the batch / (median over the
+               K timed steps of the step time, max over ranks); one fused launch per step through
+               the C ABI (`d3b200_batch_vjp_f64`), CUDA events on the launch stream, L2 flushed
+               (256 MB write) between steps;
+  api_resident the same step through the drop-in API on resident tensors: `dftd3()` +
+               `torch.autograd.grad` (SURVEY 8d's definition of the timed region);
+  e2e          the same metric through the public host-buffer API (`dftd3_host`): pinned HOST
+               numbers/positions in, pinned host energies + gradient out, every step synchronised;
+  roofline     FP64 FMA pipe: algorithmic flops per launch (140 per pair-term within
+               25 Bohr, 89 beyond) / kernel time, against an FP64 FMA-chain peak measured live on
+               the same GPU; `traffic` is read from the named ncu summary under profiles/ (null
+               when no summary of the current kernel build is committed);
+  cpu_baseline the reference's own torch CPU path (unmodified reference source over the tad-mctc
+               stand-in when `baseline/_ref` travelled, else the oracle port) on a bounded sample
+               of the same batch, all host threads (rank 0 at N = 1 only).
+`--impl reference` times that CPU path alone on the same config (same `config` object).
 """
 from __future__ import annotations
 
@@ -118,383 +130,6 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------ reference arm
-def all_host_cores():
-    """The CPU baseline gets every host core: undo the GPU-local affinity of bind_host_thread_to_gpu."""
-    try:
-        os.sched_setaffinity(0, range(os.cpu_count() or 1))
-    except (AttributeError, OSError, ValueError):
-        pass
-    torch.set_num_threads(os.cpu_count() or 1)
-
-
-def reference_step_fn(nmol_sample, seed=0):
-    """Callable running energy+gradient of the reference CPU path on a sample; returns
-    (fn, kind, pair_terms, sample description)."""
-    from tad_dftd3_b200 import synthetic as syn
-    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
-
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    numbers, positions = make_batch(nmol_sample, seed)
-    near, far = count_pairs(numbers, positions)
-    dt = torch.double
-    c6 = syn.synthetic_c6_table(dt)
-    rcov, r4r2 = COV_D3(dt)[numbers], R4R2(dt)[numbers]
-    par = {k: torch.tensor(v, dtype=dt) for k, v in PARAM.items()}
-    from refimport import reference_available
-
-    if reference_available() is not None:
-        from refimport import import_reference
-
-        d3ref = import_reference()
-        from tad_dftd3.reference import Reference
-
-        refobj = Reference(cn=REFCN(dt), c6=c6)
-        kind = "reference"
-
-        def energy(pos):
-            return d3ref.dftd3(numbers, pos, par, ref=refobj, rcov=rcov, r4r2=r4r2)
-    else:
-        import d3_oracle as orc
-
-        refcn = REFCN(dt)
-        kind = "port"
-
-        def energy(pos):
-            return orc.dftd3(numbers, pos, par, refcn=refcn, refc6=c6, rcov=rcov, r4r2=r4r2)
-
-    def step():
-        pos = positions.clone().requires_grad_(True)
-        e = energy(pos)
-        (g,) = torch.autograd.grad(e.sum(), pos)
-        return float(e.detach().sum()), g
-
-    desc = (f"{nmol_sample} molecules of the c3 batch (seed {seed}), energy + autograd gradient, "
-            f"torch {torch.__version__} CPU fp64")
-    return step, kind, near + far, desc
-
-
-def reference_single(numbers, positions, param, *, cutoff=None, rvdw_table=None, hessian=False, chunk_size=None):
-    """The reference's own CPU path (unmodified source over the stand-in when `baseline/_ref`
-    or /root/reference is present, else the oracle port) on ONE structure: returns
-    (seconds for energy + gradient [or the Hessian], kind)."""
-    from tad_dftd3_b200 import synthetic as syn
-    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
-
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from refimport import reference_available
-
-    dt = torch.double
-    numbers, positions = numbers.cpu(), positions.cpu().to(dt)
-    c6 = syn.synthetic_c6_table(dt)
-    rcov, r4r2 = COV_D3(dt)[numbers], R4R2(dt)[numbers]
-    par = {k: torch.tensor(float(v), dtype=dt) for k, v in param.items()}
-    rvdw = None if rvdw_table is None else rvdw_table.cpu()[numbers.unsqueeze(-1), numbers.unsqueeze(-2)]
-    cut = None if cutoff is None else torch.tensor(cutoff, dtype=dt)
-    if reference_available() is not None:
-        from refimport import import_reference
-
-        d3ref = import_reference()
-        from tad_dftd3.reference import Reference
-
-        refobj = Reference(cn=REFCN(dt), c6=c6)
-        kind = "reference"
-
-        def energy(pos):
-            return d3ref.dftd3(numbers, pos, par, ref=refobj, rcov=rcov, r4r2=r4r2, rvdw=rvdw, cutoff=cut,
-                               chunk_size=chunk_size)
-    else:
-        import d3_oracle as orc
-
-        kind = "port"
-
-        def energy(pos):
-            return orc.dftd3(numbers, pos, par, refcn=REFCN(dt), refc6=c6, rcov=rcov, r4r2=r4r2, rvdw=rvdw,
-                             cutoff=50.0 if cutoff is None else cutoff)
-
-    t0 = time.perf_counter()
-    if hessian:
-        torch.func.jacrev(torch.func.jacrev(lambda p: energy(p).sum(-1)))(positions)
-    else:
-        pos = positions.clone().requires_grad_(True)
-        torch.autograd.grad(energy(pos).sum(), pos)
-    return time.perf_counter() - t0, kind
-
-
-def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    step, kind, pairs, desc = reference_step_fn(args.ref_nmol)
-    for _ in range(max(args.warmup, 1) if args.warmup < 3 else 1):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    v = pairs / dt
-    line = {
-        "impl": "reference", "metric": "D3(BJ) energy+grad pair-terms/s fp64", "value": v,
-        "unit": "pair-terms/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "c3: 4096 drug-like molecules (50-120 atoms, padded to 120), D3(BJ) two-body + CN, energy+grad fp64",
-                   "sample_per_step": desc},
-        "cpu_baseline": {"value": v, "unit": "pair-terms/s", "cores": torch.get_num_threads(), "kind": kind, "sample": desc},
-        "e2e": {"value": v, "unit": "pair-terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
-
-
-# ------------------------------------------------------------------ our arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nmol", type=int, default=4096)
-    ap.add_argument("--ref-nmol", type=int, default=192)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=0,
-                    help="c3 end-to-end: 0 = zero-copy form of dftd3_host (default); > 0 = staged form with this many "
-                         "structures per pipeline chunk")
-    ap.add_argument("--cutoff", type=float, default=25.0, help="c5a: dispersion/triple cutoff in Bohr")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5a", "c5b"],
-                    help="c3: 4096-molecule batch (default, the headline metric); "
-                         "c4: one 50k-atom water cluster, rows sharded over the GPUs")
-    ap.add_argument("--nwater", type=int, default=16667)
-    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="c3 only: arithmetic type of the path")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
-
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # NCCL prints its version banner (and warnings) to stdout: send them to a file so
-        # that stdout carries exactly the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/d3b200_nccl_%h_%p.log")
-        dist.init_process_group("nccl", device_id=dev)
-
-    import tad_dftd3_b200 as d3
-    from tad_dftd3_b200 import _lib, ops
-    from tad_dftd3_b200 import synthetic as syn
-    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
-
-    # one process per GPU: keep this rank's host thread and its page-locked buffers on the
-    # NUMA node of its GPU (matters for the end-to-end number when 8 ranks share the host)
-    numa_bound = d3.bind_host_thread_to_gpu(local) if os.environ.get("D3B200_NO_NUMA_BIND") != "1" else False
-    lib = _lib.lib()
-    dt = torch.double if args.dtype == "f64" else torch.float32
-    if args.workload == "c5a":
-        run_c5a(args, rank, local, world, dev)
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    if args.workload == "c5b":
-        run_c5b(args, rank, local, world, dev)
-        return
-    if args.workload == "c4":
-        run_c4(args, rank, local, world, dev)
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    # ---- this rank's shard (weak scaling: every rank owns nmol structures)
-    numbers_h, positions_h = make_batch(args.nmol, seed=rank)
-    numbers_h, positions_h = numbers_h.pin_memory(), positions_h.pin_memory()
-    positions_h = positions_h.to(dt).pin_memory()
-    numbers, positions = numbers_h.to(dev), positions_h.to(dev)
-    near, far = count_pairs(numbers, positions.double())
-    pairs = near + far
-    flops = near * FLOPS_NEAR + far * FLOPS_FAR
-    ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
-    refcn, refc6, _ = ref._prepared(dev, dt)
-    par = {k: torch.tensor(v, dtype=dt) for k, v in PARAM.items()}
-    p = torch.tensor([PARAM["s6"], PARAM["s8"], PARAM["a1"], PARAM["a2"], 0.0], dtype=dt)
-    st = ops.Settings(rcov_per_element=True, r4r2_per_element=True)
-    rcov_t, r4r2_t = COV_D3(dt, dev), R4R2(dt, dev)
-    g = torch.ones(numbers.shape, dtype=dt, device=dev)
-
-    # ---- the hot path, inputs resident: one fused launch = energies + gradient
-    call = ops._Call(numbers, positions, p, rcov_t, r4r2_t, None, refcn, refc6, st, 0)
-    # scheduling hint, as dftd3() applies it from the second call with the same numbers tensor on:
-    # largest structures first (computed once, outside the timed region)
-    order_hint = ops.batch_order(call.z) if os.environ.get("D3B200_NO_ORDER_HINT") != "1" else None
-    call.model.batch_order = order_hint.data_ptr() if order_hint is not None else None
-    energy = torch.empty(numbers.shape, dtype=dt, device=dev)
-    grad = torch.empty(*numbers.shape, 3, dtype=dt, device=dev)
-    fn = getattr(lib, f"d3b200_batch_vjp_{args.dtype}")
-    stream = torch.cuda.current_stream(dev)
-
-    def step_resident():
-        _lib.launch_count += 1
-        _lib.check(fn(call.nflat, call.n, call.z.data_ptr(), call.x.data_ptr(), C.byref(call.model),
-                      C.byref(call.par), g.data_ptr(), energy.data_ptr(), grad.data_ptr(), None,
-                      None, 0, C.c_void_p(stream.cuda_stream)))
-
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    # sanity of what is being timed (outside the timed region): every output finite,
-    # exact zeros on padding, vanishing net force per structure
-    assert bool(torch.isfinite(energy).all()) and bool(torch.isfinite(grad).all()), "non-finite output"
-    assert bool((energy[numbers == 0] == 0).all())
-    net_force = float(grad.sum(1).abs().max())
-    launches0 = _lib.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
-        # untimed pre-heat (~1 s of the same step) so that nvidia-smi samples the
-        # clocks UNDER LOAD: the K timed steps alone last only a few milliseconds
-        t_heat = time.perf_counter()
-        while time.perf_counter() - t_heat < 1.0:
-            for _ in range(50):
-                step_resident()
-            torch.cuda.synchronize(dev)
-        barrier()
-        n_launch = -_lib.launch_count
-        for a, b in ev:
-            flush.zero_()
-            a.record(stream)
-            step_resident()
-            b.record(stream)
-        barrier()
-        n_launch += _lib.launch_count
-        t_steps = [a.elapsed_time(b) for a, b in ev]  # ms, kernel only
-        # ---- end-to-end through the public API from pinned host buffers
-        e_h = torch.empty(numbers.shape, dtype=dt).pin_memory()
-        g_h = torch.empty(*numbers.shape, 3, dtype=dt).pin_memory()
-
-        # End to end through the public host-buffer API: `dftd3_host` cuts the batch
-        # into chunks of structures and pipelines H2D copy / fused kernel / D2H copy
-        # (d3b200_batch_vjp_host_f64); it returns after the results are in e_h / g_h.
-        host_chunk = max(0, args.e2e_chunk)
-        n_e2e_launch = 1 if host_chunk == 0 else d3.HostPipeline.chunks(args.nmol, host_chunk)
-        positions_e2e, ref_e2e = positions_h, ref
-
-        def step_e2e():
-            d3.dftd3_host(numbers_h, positions_e2e, par, ref=ref_e2e, energy_out=e_h, grad_out=g_h,
-                          chunk=host_chunk, device=dev, sync=True)
-
-        for _ in range(args.warmup):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        n_launch -= _lib.launch_count
-        for _ in range(args.steps):
-            step_e2e()
-        n_launch += _lib.launch_count
-        e1.record(stream)
-        barrier()
-        t_e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
-    launches = n_launch  # our kernels inside the two timed regions (K resident steps + K end-to-end steps)
-
-    # ---- FP64 FMA-chain peak on this GPU (roofline denominator)
-    out = torch.zeros(1, dtype=dt, device=dev)
-    blocks, iters = 148 * 8, 4096
-    probe = getattr(lib, f"d3b200_probe_fma_{args.dtype}")
-    for _ in range(2):
-        probe(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
-    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pa.record(stream)
-    probe(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
-    pb.record(stream)
-    torch.cuda.synchronize(dev)
-    peak_tflops = blocks * 256 * iters * 128 / (pa.elapsed_time(pb) * 1e-3) / 1e12
-
-    ms = float(np.mean(t_steps))
-    t = torch.tensor([ms, t_e2e_ms], dtype=torch.double, device=dev)
-    tot = torch.tensor([float(pairs), float(flops)], dtype=torch.double, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, e2e_ms = float(t[0]), float(t[1])
-    pairs_all, flops_all = float(tot[0]), float(tot[1])
-
-    if rank == 0:
-        achieved = flops / (float(np.mean(t_steps)) * 1e-3) / 1e12  # this GPU's kernel
-        line = {
-            "metric": "D3(BJ) energy+grad pair-terms/s fp64",
-            "value": pairs_all / (ms * 1e-3),
-            "unit": "pair-terms/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {
-                "workload": f"c3: {args.nmol} drug-like molecules per GPU (50-120 atoms, padded to 120), "
-                            f"D3(BJ) two-body + CN, energy+grad {args.dtype}",
-                "pair_terms_per_gpu": pairs, "pairs_within_25_bohr": near,
-                "entry": "d3b200_batch_vjp_f64 (one fused launch: CN, weights, C6, BJ energy, analytic gradient)",
-                "l2": "256 MB buffer written between timed steps",
-                "timing": "CUDA events around each step on the launch stream, mean of steps, max over ranks; "
-                          "1 s untimed pre-heat under the clock sampler",
-                "parallelism": f"structures sharded over {world} GPU(s), no data-path collective",
-                "tables": "synthetic C6 table (reference-c6.pt unavailable offline)",
-                "schedule": "CTAs take the structures largest first (d3b200_model.batch_order, computed once per numbers "
-                            "tensor; dftd3() does the same from the second call with the same tensor on; not used by the zero-copy "
-                            "end-to-end form, where it bunches the PCIe requests)",
-                "checks": {"all_outputs_finite": True, "max_net_force_per_structure": net_force},
-            },
-            "e2e": {
-                "value": pairs_all / (e2e_ms * 1e-3), "unit": "pair-terms/s",
-                "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * positions_h.element_size()),
-                "d2h_bytes_per_step": int((e_h.numel() + g_h.numel()) * e_h.element_size()),
-                "ms_per_step": e2e_ms,
-                "api": f"tad_dftd3_b200.dftd3_host(): pinned host buffers in, pinned host energies + gradient out "
-                       f"(d3b200_batch_vjp_host_{args.dtype}); "
-                       + ("one launch of the fused kernel reading and writing host memory directly (zero-copy, "
-                          "coalesced), " if host_chunk == 0 else
-                          f"{n_e2e_launch} chunks pipelined H2D / kernel / D2H, ")
-                       + "synchronised every step",
-                "host_thread_bound_to_gpu_numa_node": bool(numa_bound),
-            },
-            "gpu_launches": launches,
-            "roofline": {
-                "bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": achieved, "peak": peak_tflops,
-                "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": 15.85e6 if args.dtype == "f64" else None,
-                "kernel": "d3::molecule_kernel_v2<%s, true>" % ("double" if args.dtype == "f64" else "float"),
-                "peak_source": "FMA-chain probe of the same type measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "fp64_pipe_active_pct_ncu": 53.6 if args.dtype == "f64" else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1h_molecule_kernel_v2_raw.csv",
-                "flops_model": "140/pair-term (r<=25 Bohr), 89 (25<r<=50), SURVEY.md 8(d)",
-                "hbm_gbs_measured_peak": _measured_hbm(),
-            },
-            "clocks": clocks.summary(),
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            all_host_cores()
-            stepf, kind, rp, desc = reference_step_fn(args.ref_nmol)
-            stepf()  # warm-up (thread pools, allocator)
-            t0 = time.perf_counter()
-            stepf()
-            dtc = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": rp / dtc, "unit": "pair-terms/s", "cores": torch.get_num_threads(),
-                                    "kind": kind, "sample": desc, "seconds": dtc}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
 def count_pairs_single(positions, cutoff=50.0, cn_cutoff=25.0, chunk=2048):
     """Exact unordered pair counts of one structure (chunked, on the GPU)."""
     n = positions.shape[0]
@@ -521,135 +156,6 @@ def fp64_peak(lib, dev, stream):
     return blocks * 256 * iters * 128 / (pa.elapsed_time(pb) * 1e-3) / 1e12
 
 
-def run_c4(args, rank, local, world, dev):
-    """BASELINE config 4: one 50k-atom water cluster, two-body + CN, energy + gradient,
-    rows sharded over the ranks (strong scaling: the structure is fixed)."""
-    import torch.distributed as dist
-
-    import tad_dftd3_b200 as d3
-    from tad_dftd3_b200 import _lib
-    from tad_dftd3_b200 import synthetic as syn
-    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
-    from tad_dftd3_b200.distributed import dftd3_sharded, run_sharded
-    from tad_dftd3_b200.system import SystemPlan, SystemRunner
-
-    dt = torch.double
-    lib = _lib.lib()
-    stream = torch.cuda.current_stream(dev)
-    numbers_h, positions_h = syn.water_cluster(args.nwater, seed=0)
-    numbers_h, positions_h = numbers_h.pin_memory(), positions_h.pin_memory()
-    numbers, positions = numbers_h.to(dev), positions_h.to(dev)
-    near, far = count_pairs_single(positions)
-    pairs, flops = near + far, near * FLOPS_NEAR + far * FLOPS_FAR
-    ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
-    refcn, refc6, _ = ref._prepared(dev, dt)
-    rcov, r4r2 = COV_D3(dt, dev)[numbers], R4R2(dt, dev)[numbers]
-    par = _lib.Params()
-    par.s6, par.s8, par.a1, par.a2 = PARAM["s6"], PARAM["s8"], PARAM["a1"], PARAM["a2"]
-    par.s9, par.rs9, par.alp = 0.0, 4.0 / 3.0, 14.0
-    par.cutoff, par.cn_cutoff, par.kcn = 50.0, 25.0, 16.0
-    g = torch.ones(numbers.shape[0], dtype=dt, device=dev)
-    param = {k: torch.tensor(v, dtype=dt) for k, v in PARAM.items()}
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def step_resident():
-        plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn)
-        runner = SystemRunner(plan, refcn, refc6, par, g, world)
-        run_sharded(runner, True)
-        return plan.scatter(runner.energy), plan.scatter(runner.grad)
-
-    e_h = torch.empty(numbers.shape[0], dtype=dt).pin_memory()
-    g_h = torch.empty(numbers.shape[0], 3, dtype=dt).pin_memory()
-
-    def step_e2e():
-        z = numbers_h.to(dev, non_blocking=True)
-        x = positions_h.to(dev, non_blocking=True).requires_grad_(True)
-        e = dftd3_sharded(z, x, param, ref=ref)
-        (gx,) = torch.autograd.grad(e.sum(), x)
-        e_h.copy_(e.detach(), non_blocking=True)
-        g_h.copy_(gx, non_blocking=True)
-
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    l0 = _lib.launch_count
-    with ClockSampler(local) as clocks:
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        barrier()
-        t0 = time.perf_counter()
-        for a, b in ev:
-            a.record(stream)
-            step_resident()
-            b.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-        ms = max(float(np.mean([a.elapsed_time(b) for a, b in ev])), wall_ms)
-        for _ in range(args.warmup):
-            step_e2e()
-        barrier()
-        e2e_steps = []
-        for _ in range(args.steps):
-            t0 = time.perf_counter()
-            step_e2e()
-            torch.cuda.synchronize(dev)
-            e2e_steps.append((time.perf_counter() - t0) * 1e3)
-        barrier()
-        # median: a fresh process occasionally shows one step of tens of ms here (allocator growth while
-        # the plan of every step is rebuilt for a new numbers tensor)
-        e2e_ms = float(np.median(e2e_steps))
-    launches = _lib.launch_count - l0
-    peak = fp64_peak(lib, dev, stream)
-    t = torch.tensor([ms, e2e_ms], dtype=torch.double, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
-    if rank == 0:
-        achieved = flops / (ms * 1e-3) / 1e12
-        line = {
-            "metric": "D3(BJ) energy+grad pair-terms/s fp64", "value": pairs / (ms * 1e-3),
-            "unit": "pair-terms/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"c4: {numbers.shape[0]}-atom water cluster, D3(BJ) two-body + CN (cutoffs 50 / 25 Bohr), "
-                            "energy+grad fp64, rows sharded over the GPUs",
-                "pair_terms": pairs, "pairs_within_25_bohr": near,
-                "entry": "SystemPlan (cached Morton order, d3b200_system_pack_f64) + d3b200_system_{cn,weights,tvec,pair,cnbwd}_f64",
-                "l2": "per-atom arrays (10 MB) stream from L2/HBM every sweep; structure larger than one CTA's reach",
-                "timing": "max(CUDA events, wall clock) per step incl. the plan build, max over ranks",
-                "parallelism": f"rows of one structure over {world} GPU(s); all-reduce of CN, dL/dCN, E, grad",
-            },
-            "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "pair-terms/s",
-                    "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * 8),
-                    "d2h_bytes_per_step": int(e_h.numel() * 8 + g_h.numel() * 8), "ms_per_step": e2e_ms,
-                    "api": "tad_dftd3_b200.distributed.dftd3_sharded() + autograd.grad, pinned host buffers; "
-                           "median of the timed steps"},
-            "gpu_launches": launches,
-            "roofline": {"bound": "fp64", "achieved": achieved * world and achieved, "peak": peak * world,
-                         "unit": "TFLOP/s", "frac": achieved / (peak * world), "traffic": None,
-                         "kernel": "whole step (cn + weights + pair + cnbwd sweeps, all ranks)",
-                         "peak_source": "FP64 FMA-chain probe x n_gpus, measured in this run"},
-            "clocks": clocks.summary(),
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            # the reference cannot hold 50k atoms (20 GB per dense N x N temporary): time a
-            # 2000-atom sub-cluster of the same structure and report its dense pair rate
-            all_host_cores()
-            centre = positions.mean(0)
-            sub = torch.argsort((positions - centre).norm(dim=1))[:2000]
-            sn, sf = count_pairs_single(positions[sub])
-            sec, kind = reference_single(numbers[sub], positions[sub], PARAM, chunk_size=256)
-            line["cpu_baseline"] = {"value": (sn + sf) / sec, "unit": "pair-terms/s", "cores": torch.get_num_threads(),
-                                    "kind": kind, "seconds": sec,
-                                    "sample": "central 2000-atom sub-cluster of the same structure, energy + autograd "
-                                              "gradient, chunk_size=256 (the reference cannot hold 50k atoms)"}
-        print(json.dumps(line))
-
-
 def count_triples(positions, cutoff):
     """Unordered triples with at least two edges <= cutoff (the ones the reference's
     ordered rule includes for some ordering): sum_i C(n_i, 2) - 2 * #triangles."""
@@ -666,146 +172,642 @@ def count_triples(positions, cutoff):
     return int(round(wedges - 2.0 * tri)), int(round(tri)), int(adj.sum().item() // 2)
 
 
-def run_c5a(args, rank, local, world, dev):
-    """BASELINE config 5a: ATM three-body term on a 10k-atom water cluster with a triple cutoff.
-    One step = the whole dftd3() evaluation with s9 = 1 (CN, weights, two-body sweep, three-body
-    sweep, CN-backward), centres of the three-body term sharded over the GPUs."""
-    import torch.distributed as dist
+def _measured_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, KeyError, ValueError):
+        return None
 
-    import tad_dftd3_b200 as d3
-    from tad_dftd3_b200 import _lib, synthetic as syn
+
+
+C3_NMIN, C3_NMAX = 50, 120
+
+
+def c3_config(nmol, dtype):
+    """Workload description shared VERBATIM by both arms (`--impl reference` prints the same object)."""
+    return {
+        "workload": f"c3: one batch of {nmol} drug-like molecules ({C3_NMIN}-{C3_NMAX} atoms, padded to {C3_NMAX}), "
+                    f"D3(BJ) two-body + CN (cutoffs 50 / 25 Bohr), energy+grad {dtype}",
+        "nmol": nmol, "seed": 0, "param": PARAM,
+        "tables": "synthetic C6 table (reference-c6.pt unavailable offline), D3 covalent radii and r4r2",
+    }
+
+
+def shard_structures(numbers, world):
+    """Strong scaling of a batch: structures sorted by size (largest first) and dealt round-robin,
+    so every rank gets the same number of structures and nearly the same pair count."""
+    counts = (numbers != 0).sum(-1)
+    order = torch.argsort(counts, descending=True, stable=True)
+    return [order[r::world] for r in range(world)]
+
+
+# ------------------------------------------------------------------ reference arm
+def all_host_cores():
+    """The CPU baseline gets every host core: undo the GPU-local affinity of bind_host_thread_to_gpu."""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except (AttributeError, OSError, ValueError):
+        pass
+    torch.set_num_threads(os.cpu_count() or 1)
+
+
+def reference_energy_fn():
+    """(energy(numbers, positions) -> per-atom energies on CPU through the reference's own code, kind)."""
+    from tad_dftd3_b200 import synthetic as syn
     from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
-    from tad_dftd3_b200.distributed import run_sharded
-    from tad_dftd3_b200.system import SystemPlan, SystemRunner
 
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     dt = torch.double
-    lib = _lib.lib()
-    stream = torch.cuda.current_stream(dev)
-    nwater = 3334 if args.nwater == 16667 else args.nwater
-    numbers, positions = syn.water_cluster(nwater, seed=0)
-    numbers, positions = numbers.to(dev), positions.to(dev)
-    triples, triangles, edges = count_triples(positions, args.cutoff)
-    ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
-    refcn, refc6, _ = ref._prepared(dev, dt)
-    rcov, r4r2 = COV_D3(dt, dev)[numbers], R4R2(dt, dev)[numbers]
-    rvdw = syn.synthetic_rvdw_table(dt, dev)
-    par = _lib.Params()
-    par.s6, par.s8, par.a1, par.a2 = PARAM["s6"], PARAM["s8"], PARAM["a1"], PARAM["a2"]
-    par.s9, par.rs9, par.alp = 1.0, 1.3333333730697632, 14.0
-    par.cutoff, par.cn_cutoff, par.kcn = args.cutoff, 25.0, 16.0
-    g = torch.ones(numbers.shape[0], dtype=dt, device=dev)
+    c6 = syn.synthetic_c6_table(dt)
+    rcov_t, r4r2_t = COV_D3(dt), R4R2(dt)
+    par = {k: torch.tensor(v, dtype=dt) for k, v in PARAM.items()}
+    from refimport import reference_available
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    if reference_available() is not None:
+        from refimport import import_reference
 
-    t_atm, t_all = [], []
-    launches = 0
-    with ClockSampler(local) as clocks:
-        for it in range(args.warmup + args.steps):
-            barrier()
-            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-            l0 = _lib.launch_count
-            e0.record(stream)
-            plan = SystemPlan(numbers, positions, rcov, r4r2, par.kcn)
-            run = SystemRunner(plan, refcn, refc6, par, g, world, rvdw)
-            atm = run.sweep_atm
+        d3ref = import_reference()
+        from tad_dftd3.reference import Reference
 
-            def timed_atm(*a, _atm=atm):
-                e1.record(stream)
-                _atm(*a)
-                e2.record(stream)
+        refobj = Reference(cn=REFCN(dt), c6=c6)
 
-            run.sweep_atm = timed_atm
-            run_sharded(run, True)
-            energy, grad = plan.scatter(run.energy), plan.scatter(run.grad)
-            e3.record(stream)
-            barrier()
-            if it >= args.warmup:
-                t_atm.append(e1.elapsed_time(e2)); t_all.append(e0.elapsed_time(e3))
-                launches += _lib.launch_count - l0
-    # ---- end to end through the public API (dftd3_sharded == dftd3 at one GPU): pinned host
-    # numbers / positions in, pinned host energies + gradient out, every step
-    from tad_dftd3_b200.distributed import dftd3_sharded
+        def energy(numbers, pos, **kw):
+            return d3ref.dftd3(numbers, pos, dict(par, **kw.pop("param", {})), ref=refobj, rcov=rcov_t[numbers],
+                               r4r2=r4r2_t[numbers], **kw)
 
-    d3.data.set_vdw_pairwise(rvdw)
-    num_h, pos_h = numbers.cpu().pin_memory(), positions.cpu().pin_memory()
-    e_h = torch.empty(numbers.shape[0], dtype=dt).pin_memory()
-    g_h = torch.empty(numbers.shape[0], 3, dtype=dt).pin_memory()
-    param = {k: torch.tensor(v, dtype=dt) for k, v in dict(PARAM, s9=1.0).items()}
+        return energy, "reference"
+    import d3_oracle as orc
 
-    def step_e2e():
-        z = num_h.to(dev, non_blocking=True)
-        x = pos_h.to(dev, non_blocking=True).requires_grad_(True)
-        e = dftd3_sharded(z, x, param, ref=ref, cutoff=torch.tensor(args.cutoff, dtype=dt))
-        (gx,) = torch.autograd.grad(e.sum(), x)
-        e_h.copy_(e.detach(), non_blocking=True)
-        g_h.copy_(gx, non_blocking=True)
-        torch.cuda.synchronize(dev)
+    refcn = REFCN(dt)
 
-    step_e2e()
-    barrier()
+    def energy(numbers, pos, **kw):
+        kw.pop("chunk_size", None)
+        return orc.dftd3(numbers, pos, dict(par, **kw.pop("param", {})), refcn=refcn, refc6=c6, rcov=rcov_t[numbers],
+                         r4r2=r4r2_t[numbers], **{k: v for k, v in kw.items() if v is not None})
+
+    return energy, "port"
+
+
+def reference_chunk_step(numbers, positions, energy):
+    """energy + autograd gradient of one chunk of structures through the reference path."""
+    pos = positions.clone().requires_grad_(True)
+    e = energy(numbers, pos)
+    (g,) = torch.autograd.grad(e.sum(), pos)
+    return float(e.detach().sum()), g
+
+
+def reference_single(numbers, positions, param, *, cutoff=None, rvdw_table=None, hessian=False, chunk_size=None):
+    """The reference's CPU path on ONE structure: (seconds for energy + gradient [or the Hessian], kind)."""
+    energy, kind = reference_energy_fn()
+    dt = torch.double
+    numbers, positions = numbers.cpu(), positions.cpu().to(dt)
+    extra = {k: torch.tensor(float(v), dtype=dt) for k, v in param.items() if k not in PARAM}
+    kw = {"param": extra}
+    if rvdw_table is not None:
+        kw["rvdw"] = rvdw_table.cpu()[numbers.unsqueeze(-1), numbers.unsqueeze(-2)]
+    if cutoff is not None:
+        kw["cutoff"] = torch.tensor(cutoff, dtype=dt)
+    if chunk_size is not None:
+        kw["chunk_size"] = chunk_size
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    e2e_err = float((g_h.to(dev) - grad).abs().max())
-    # median over the timed steps: single steps are occasionally disturbed by allocator growth
-    t = torch.tensor([float(np.median(t_atm)), float(np.median(t_all)), e2e_ms], dtype=torch.double, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_atm, ms_all, e2e_ms = float(t[0]), float(t[1]), float(t[2])
+    if hessian:
+        torch.func.jacrev(torch.func.jacrev(lambda p: energy(numbers, p, **dict(kw)).sum(-1)))(positions)
+    else:
+        pos = positions.clone().requires_grad_(True)
+        torch.autograd.grad(energy(numbers, pos, **dict(kw)).sum(), pos)
+    return time.perf_counter() - t0, kind
+
+
+REF_CHUNK = 256          # structures per reference call (the N^2 x 49 gather of 256 molecules is 1.4 GB)
+REF_BUDGET_S = 110.0     # wall-clock budget of the timed steps of `--impl reference`
+
+
+def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on the c3 batch, all host threads.
+    Each step runs as many 256-structure chunks of the SAME batch as fit the time budget (all 16
+    when K is small); consecutive steps walk through the batch."""
+    rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    peak = fp64_peak(lib, dev, stream)
-    achieved = triples * 140.0 / (ms_atm * 1e-3) / 1e12
+    all_host_cores()
+    energy, kind = reference_energy_fn()
+    numbers, positions = make_batch(args.nmol, seed=0)
+    chunks = [(numbers[lo:lo + REF_CHUNK], positions[lo:lo + REF_CHUNK]) for lo in range(0, args.nmol, REF_CHUNK)]
+    pairs = [sum(count_pairs(z, x)) for z, x in chunks]
+    reference_chunk_step(*chunks[0], energy)                       # thread pools, allocator
+    t0 = time.perf_counter()
+    reference_chunk_step(*chunks[0], energy)
+    t_chunk = time.perf_counter() - t0
+    per_step = int(max(1, min(len(chunks), REF_BUDGET_S / max(args.steps, 1) / t_chunk)))
+    for _ in range(min(args.warmup, 2)):
+        reference_chunk_step(*chunks[-1], energy)
+    cursor, times, done = 0, [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(per_step):
+            reference_chunk_step(*chunks[cursor % len(chunks)], energy)
+            n += pairs[cursor % len(chunks)]
+            cursor += 1
+        times.append(time.perf_counter() - t0)
+        done.append(n)
+    v = float(np.sum(done) / np.sum(times))
+    desc = (f"{per_step} chunk(s) of {REF_CHUNK} structures of the c3 batch per step (of {len(chunks)}; steps walk "
+            f"through the batch), energy + autograd gradient, torch {torch.__version__} CPU fp64, "
+            f"{torch.get_num_threads()} threads")
     line = {
-        "metric": "ATM energy+grad triples/s fp64", "value": triples / (ms_all * 1e-3), "unit": "triples/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"c5a: dftd3() with the ATM term (s9=1) on a {numbers.shape[0]}-atom water cluster, "
-                               f"cutoff {args.cutoff} Bohr, energy+grad fp64, centres sharded over the GPUs",
-                   "triples": triples, "all_short_triangles": triangles, "short_edges": edges,
-                   "entry": "SystemPlan + d3b200_system_{cn,weights,tvec,pair,atm,cnbwd}_f64; value = triples / whole step "
-                            "(max over ranks, CUDA events); the three-body sweep alone in atm_ms",
-                   "atm_ms": ms_atm, "triples_per_s_atm_kernel": triples / (ms_atm * 1e-3),
-                   "atm_ms_per_step": [round(v, 3) for v in t_atm],
-                   "total_energy": float(energy.sum()),
-                   "parallelism": f"centres of the three-body term and rows of the two-body sweeps over {world} GPU(s); "
-                                  "all-reduce of CN, dL/dCN, E, grad"},
-        "gpu_launches": launches,
-        "e2e": {"value": triples / (e2e_ms * 1e-3), "unit": "triples/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(num_h.numel() * 8 + pos_h.numel() * 8),
-                "d2h_bytes_per_step": int((e_h.numel() + g_h.numel()) * 8),
-                "api": "tad_dftd3_b200.distributed.dftd3_sharded() (= dftd3() at one GPU) + autograd.grad, pinned host "
-                       "buffers, plan (Morton / element sort) rebuilt every step",
-                "max_abs_grad_diff_vs_resident": e2e_err},
-        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s",
-                     "frac": achieved / (peak * world),
-                     "traffic": 100.9e6 if (world == 1 and args.cutoff == 25.0 and nwater == 3334) else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (6.0 + 94.9 MB, mostly the "
-                                       "per-centre neighbour records leaving L2), profiles/r1h_system_atm3_raw.csv",
-                     "fp64_pipe_active_pct_ncu": 40.3,
-                     "kernel": "d3::system_atm3_kernel<double, true> (every triple once), all ranks",
-                     "flops_model": "140 per unordered triple (SURVEY.md 8d)"},
-        "clocks": clocks.summary(),
+        "impl": "reference", "metric": "D3(BJ) energy+grad pair-terms/s fp64", "value": v,
+        "unit": "pair-terms/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": c3_config(args.nmol, "f64"),
+        "cpu_baseline": {"value": v, "unit": "pair-terms/s", "cores": torch.get_num_threads(), "kind": kind, "sample": desc},
+        "e2e": {"value": v, "unit": "pair-terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        # the reference's ATM is dense N^3 (216 MB per temporary at N = 300): time a 300-atom sub-cluster
-        all_host_cores()
-        centre = positions.mean(0)
-        sub = torch.argsort((positions - centre).norm(dim=1))[:300]
-        t_sub, _, _ = count_triples(positions[sub], args.cutoff)
-        sec, kind = reference_single(numbers[sub], positions[sub], dict(PARAM, s9=1.0), cutoff=args.cutoff,
-                                     rvdw_table=rvdw)
-        sec0, _ = reference_single(numbers[sub], positions[sub], PARAM, cutoff=args.cutoff)
-        line["cpu_baseline"] = {"value": t_sub / max(sec - sec0, 1e-9), "unit": "triples/s",
-                                "cores": torch.get_num_threads(), "kind": kind, "seconds": sec - sec0,
-                                "sample": "central 300-atom sub-cluster, (two-body + ATM) minus (two-body) wall time, "
-                                          "energy + autograd gradient"}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+class Ctx:
+    """Rank / device / collective helpers shared by the workloads."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+
+        self.args = args
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # NCCL prints its version banner (and warnings) to stdout: send them to a file so
+            # that stdout carries exactly the one JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/d3b200_nccl_%h_%p.log")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def reduce_max(self, *vals):
+        t = torch.tensor([float(v) for v in vals], dtype=torch.double, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def reduce_sum(self, *vals):
+        t = torch.tensor([float(v) for v in vals], dtype=torch.double, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def timed(self, fn, steps, flush=True):
+        """K steps, each bracketed by CUDA events on the launch stream (L2 flushed before each);
+        barrier + synchronize on both sides.  Returns the per-step times in ms."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        for a, b in ev:
+            if flush:
+                self.flush.zero_()
+            a.record(self.stream)
+            fn()
+            b.record(self.stream)
+        self.barrier()
+        return [a.elapsed_time(b) for a, b in ev]
+
+    def timed_sync(self, fn, steps):
+        """K steps, each followed by a stream synchronize (host-visible result), wall clock per step."""
+        self.barrier()
+        out = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(self.dev)
+            out.append((time.perf_counter() - t0) * 1e3)
+        self.barrier()
+        return out
+
+
+def max_rel_err(a, b, atol=1e-12):
+    """Residual of the parity gate |a - b| <= atol + rtol |b|: the smallest rtol that passes."""
+    d = (a - b).abs()
+    return float(((d - atol).clamp_min(0) / b.abs().clamp_min(1e-300)).max()) if d.numel() else 0.0
+
+
+def profile_numbers(name):
+    """ncu figures of a kernel from a committed summary (profiles/<name>.json), labelled with their source."""
+    path = os.path.join(ROOT, "profiles", name + ".json")
+    try:
+        d = json.load(open(path))
+    except (OSError, ValueError):
+        return None
+    d["source"] = "profiles/" + name + ".json"
+    return d
+
+
+def run_c3(args, cx, clocks_out):
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import _lib, ops
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+
+    dev, world, rank = cx.dev, cx.world, cx.rank
+    lib = _lib.lib()
+    dt = torch.double if args.dtype == "f64" else torch.float32
+    if args.scaling == "weak":
+        nums_all, pos_all = make_batch(args.nmol, seed=rank)
+        mine = torch.arange(args.nmol)
+    else:
+        nums_all, pos_all = make_batch(args.nmol, seed=0)          # the same fixed batch on every rank
+        mine = shard_structures(nums_all, world)[rank]
+    numbers_h = nums_all[mine].contiguous().pin_memory()
+    positions_h = pos_all[mine].to(dt).contiguous().pin_memory()
+    numbers, positions = numbers_h.to(dev), positions_h.to(dev)
+    near, far = count_pairs(numbers, positions.double())
+    pairs, flops = near + far, near * FLOPS_NEAR + far * FLOPS_FAR
+    ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
+    refcn, refc6, _ = ref._prepared(dev, dt)
+    par = {k: torch.tensor(v, dtype=dt) for k, v in PARAM.items()}
+    p = torch.tensor([PARAM["s6"], PARAM["s8"], PARAM["a1"], PARAM["a2"], 0.0], dtype=dt)
+    st = ops.Settings(rcov_per_element=True, r4r2_per_element=True)
+    rcov_t, r4r2_t = COV_D3(dt, dev), R4R2(dt, dev)
+    g = torch.ones(numbers.shape, dtype=dt, device=dev)
+
+    # ---- the hot path, inputs resident: one fused launch = energies + gradient
+    call = ops._Call(numbers, positions, p, rcov_t, r4r2_t, None, refcn, refc6, st, 0)
+    # scheduling hint, as dftd3() applies it from the second call with the same numbers tensor on:
+    # largest structures first (computed once, outside the timed region)
+    order_hint = ops.batch_order(call.z) if os.environ.get("D3B200_NO_ORDER_HINT") != "1" else None
+    call.model.batch_order = order_hint.data_ptr() if order_hint is not None else None
+    energy = torch.empty(numbers.shape, dtype=dt, device=dev)
+    grad = torch.empty(*numbers.shape, 3, dtype=dt, device=dev)
+    fn = getattr(lib, f"d3b200_batch_vjp_{args.dtype}")
+    stream = cx.stream
+
+    def step_resident():
+        _lib.launch_count += 1
+        _lib.check(fn(call.nflat, call.n, call.z.data_ptr(), call.x.data_ptr(), C.byref(call.model),
+                      C.byref(call.par), g.data_ptr(), energy.data_ptr(), grad.data_ptr(), None,
+                      None, 0, C.c_void_p(stream.cuda_stream)))
+
+    # the same step through the drop-in API (SURVEY 8d's timed region)
+    x_leaf = positions.clone().requires_grad_(True)
+
+    def step_api():
+        e = d3.dftd3(numbers, x_leaf, par, ref=ref)
+        (gx,) = torch.autograd.grad(e.sum(), x_leaf)
+        return e, gx
+
+    for _ in range(args.warmup):
+        step_resident()
+    cx.barrier()
+    # sanity of what is being timed (outside the timed region): every output finite,
+    # exact zeros on padding, vanishing net force per structure
+    assert bool(torch.isfinite(energy).all()) and bool(torch.isfinite(grad).all()), "non-finite output"
+    assert bool((energy[numbers == 0] == 0).all())
+    net_force = float(grad.sum(1).abs().max())
+    checks = {"all_outputs_finite": True, "max_net_force_per_structure": net_force}
+    e_api, g_api = step_api()
+    checks["api_equals_c_abi_bitwise"] = bool(torch.equal(e_api.detach(), energy) and torch.equal(g_api, grad))
+    if world > 1 and args.scaling == "strong":
+        # the sharded result against the same batch evaluated on ONE GPU (this one), in the same run
+        zf, xf = nums_all.to(dev), pos_all.to(dt).to(dev)
+        xf.requires_grad_(True)
+        ef = d3.dftd3(zf, xf, par, ref=ref)
+        (gf,) = torch.autograd.grad(ef.sum(), xf)
+        sel = mine.to(dev)
+        err = max(max_rel_err(energy, ef.detach()[sel]), max_rel_err(grad, gf[sel]))
+        checks["max_rel_err_vs_single_gpu"] = cx.reduce_max(err)[0]
+        del zf, xf, ef, gf
+
+    with ClockSampler(cx.local) as clocks:
+        # untimed pre-heat (~1 s of the same step) so that nvidia-smi samples the
+        # clocks UNDER LOAD: the K timed steps alone last only a few milliseconds
+        t_heat = time.perf_counter()
+        while time.perf_counter() - t_heat < 1.0:
+            for _ in range(50):
+                step_resident()
+            torch.cuda.synchronize(dev)
+        n_launch = -_lib.launch_count
+        t_steps = cx.timed(step_resident, args.steps)
+        n_launch += _lib.launch_count
+        for _ in range(args.warmup):
+            step_api()
+        l0 = _lib.launch_count
+        t_api = cx.timed(step_api, args.steps)
+        api_launches = _lib.launch_count - l0
+        # ---- end-to-end through the public host-buffer API from pinned host buffers
+        e_h = torch.empty(numbers.shape, dtype=dt).pin_memory()
+        g_h = torch.empty(*numbers.shape, 3, dtype=dt).pin_memory()
+        host_chunk = max(0, args.e2e_chunk)
+        n_e2e_launch = 1 if host_chunk == 0 else d3.HostPipeline.chunks(numbers.shape[0], host_chunk)
+
+        def step_e2e():
+            d3.dftd3_host(numbers_h, positions_h, par, ref=ref, energy_out=e_h, grad_out=g_h,
+                          chunk=host_chunk, device=dev, sync=True)
+
+        for _ in range(args.warmup):
+            step_e2e()
+        n_launch -= _lib.launch_count
+        t_e2e = cx.timed_sync(step_e2e, args.steps)
+        n_launch += _lib.launch_count
+        checks["e2e_equals_resident_bitwise"] = bool(torch.equal(e_h.to(dev), energy) and torch.equal(g_h.to(dev), grad))
+    clocks_out.update(clocks.summary())
+
+    peak_tflops = fp_peak(lib, dev, stream, args.dtype)
+    ms_med, ms_mean = float(np.median(t_steps)), float(np.mean(t_steps))
+    ms, ms_api, ms_e2e = cx.reduce_max(ms_med, float(np.median(t_api)), float(np.median(t_e2e)))
+    pairs_all, flops_all, near_all = cx.reduce_sum(pairs, flops, near)
+    achieved = flops / (ms_med * 1e-3) / 1e12                          # this GPU's kernel
+    prof = profile_numbers("r2_c3_kernel_ncu") if args.dtype == "f64" else None
+    rec = {
+        "metric": "D3(BJ) energy+grad pair-terms/s fp64",
+        "value": pairs_all / (ms * 1e-3), "unit": "pair-terms/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": c3_config(args.nmol, args.dtype),
+        "details": {
+            "pair_terms_total": int(pairs_all), "pairs_within_25_bohr_total": int(near_all),
+            "pair_terms_this_rank": pairs, "structures_this_rank": int(numbers.shape[0]),
+            "ms_per_step_mean_rank0": ms_mean,
+            "entry": f"d3b200_batch_vjp_{args.dtype} (one fused launch: CN, weights, C6, BJ energy, analytic gradient)",
+            "l2": "256 MB buffer written between timed steps",
+            "timing": "CUDA events around each of the K steps on the launch stream; median over steps, max over ranks; "
+                      "barrier + synchronize on both sides; 1 s untimed pre-heat under the clock sampler",
+            "parallelism": (f"the fixed batch split by structure over {world} GPU(s) (largest first, round-robin), "
+                            "no data-path collective" if args.scaling == "strong" else
+                            f"every rank owns its own batch of {args.nmol} structures (weak scaling)"),
+            "cuda_graph": "not needed: the resident step is ONE kernel launch; with 8 GPUs a rank's 512 structures "
+                          "are a single wave of CTAs (592 resident per GPU), so the step time is that of its largest "
+                          "structures and strong scaling is bound by wave quantisation + launch latency",
+            "schedule": "CTAs take the structures largest first (d3b200_model.batch_order, computed once per numbers "
+                        "tensor; dftd3() does the same from the second call with the same tensor on; not used by the zero-copy "
+                        "end-to-end form, where it bunches the PCIe requests)",
+            "checks": checks,
+        },
+        "api_resident": {
+            "value": pairs_all / (ms_api * 1e-3), "unit": "pair-terms/s", "ms_per_step": ms_api,
+            "api": "tad_dftd3_b200.dftd3(numbers, positions, param) + torch.autograd.grad(energy.sum(), positions) on resident "
+                   "tensors; CUDA events, median over steps, max over ranks",
+            "launches_per_step": api_launches / max(args.steps, 1),
+        },
+        "e2e": {
+            "value": pairs_all / (ms_e2e * 1e-3), "unit": "pair-terms/s",
+            "h2d_bytes_per_step": int(numbers_h.numel() * 8 + positions_h.numel() * positions_h.element_size()) * world,
+            "d2h_bytes_per_step": int((e_h.numel() + g_h.numel()) * e_h.element_size()) * world,
+            "ms_per_step": ms_e2e, "ms_per_step_mean_rank0": float(np.mean(t_e2e)),
+            "api": f"tad_dftd3_b200.dftd3_host(): pinned host buffers in, pinned host energies + gradient out "
+                   f"(d3b200_batch_vjp_host_{args.dtype}); "
+                   + ("one launch of the fused kernel reading and writing host memory directly (zero-copy, "
+                      "coalesced), " if host_chunk == 0 else
+                      f"{n_e2e_launch} chunks pipelined H2D / kernel / D2H, ")
+                   + "synchronised every step; wall clock per step, median over steps, max over ranks; bytes summed over ranks",
+        },
+        "gpu_launches": n_launch,
+        "roofline": {
+            "bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": achieved, "peak": peak_tflops,
+            "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+            "traffic": None if prof is None else prof.get("dram_bytes_per_launch"),
+            "kernel": "d3::molecule_kernel_v2<%s, true, true>" % ("double" if args.dtype == "f64" else "float"),
+            "peak_source": "FMA-chain probe of the same type measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+            "from_profile": prof,
+            "flops_model": "140/pair-term (r<=25 Bohr), 89 (25<r<=50), SURVEY.md 8(d); this rank's launch",
+            "hbm_gbs_measured_peak": _measured_hbm(),
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline and rank == 0:
+        all_host_cores()
+        energy_fn, kind = reference_energy_fn()
+        zc, xc = nums_all[:REF_CHUNK], pos_all[:REF_CHUNK]
+        reference_chunk_step(zc, xc, energy_fn)  # warm-up (thread pools, allocator)
+        t0 = time.perf_counter()
+        e_sum, g_ref = reference_chunk_step(zc, xc, energy_fn)
+        dtc = time.perf_counter() - t0
+        rp = sum(count_pairs(zc, xc))
+        # the sample doubles as a parity check of what was timed (the shard is a permutation of the batch)
+        inv = torch.empty_like(mine)
+        inv[mine] = torch.arange(mine.numel())
+        rows = inv[:REF_CHUNK].to(dev)
+        rec["cpu_baseline"] = {
+            "value": rp / dtc, "unit": "pair-terms/s", "cores": torch.get_num_threads(), "kind": kind, "seconds": dtc,
+            "sample": f"first {REF_CHUNK} structures of the same batch, energy + autograd gradient, "
+                      f"torch {torch.__version__} CPU fp64",
+            "max_rel_err_gpu_vs_this_run": max_rel_err(grad[rows].cpu().double(), g_ref,
+                                                       1e-12 if args.dtype == "f64" else 1e-7),
+        }
+    return rec
+
+
+def fp_peak(lib, dev, stream, dtype="f64"):
+    dt = torch.double if dtype == "f64" else torch.float32
+    out = torch.zeros(1, dtype=dt, device=dev)
+    blocks, iters = 148 * 8, 4096
+    probe = getattr(lib, f"d3b200_probe_fma_{dtype}")
+    for _ in range(2):
+        probe(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record(stream)
+    probe(blocks, iters, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+    pb.record(stream)
+    torch.cuda.synchronize(dev)
+    return blocks * 256 * iters * 128 / (pa.elapsed_time(pb) * 1e-3) / 1e12
+
+
+def _system_params(cutoff, s9):
+    from tad_dftd3_b200 import _lib
+
+    par = _lib.Params()
+    par.s6, par.s8, par.a1, par.a2 = PARAM["s6"], PARAM["s8"], PARAM["a1"], PARAM["a2"]
+    par.s9, par.rs9, par.alp = s9, 1.3333333730697632, 14.0
+    par.cutoff, par.cn_cutoff, par.kcn = cutoff, 25.0, 16.0
+    return par
+
+
+def blocked_oracle_baseline(numbers, positions, param, cutoff, rvdw):
+    """CPU baseline of kind "port" for structures the reference cannot hold: the blocked fp64 C restatement
+    (oracle/d3_blocked.c, OpenMP on all host cores) on the FULL structure.  Returns (seconds, energy, grad)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from d3_blocked import dftd3_blocked
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+
+    dt = torch.double
+    z = numbers.cpu()
+    t0 = time.perf_counter()
+    o = dftd3_blocked(z, positions.cpu(), param, refcn=REFCN(dt), refc6=syn.synthetic_c6_table(dt), rcov=COV_D3(dt)[z],
+                      r4r2=R4R2(dt)[z], rvdw_table=rvdw, cutoff=cutoff)
+    return time.perf_counter() - t0, torch.from_numpy(o["energy"]), torch.from_numpy(o["grad"])
+
+
+def run_system(args, cx, which):
+    """One large structure with its rows (c4) / centres (c5a) sharded over the ranks: strong scaling.
+    c4: 50 001-atom water cluster, two-body + CN, cutoffs 50 / 25 Bohr  -> pair-terms/s
+    c5a: 10 002-atom water cluster, ATM term (s9 = 1), cutoff `--cutoff`  -> triples/s (whole dftd3() step)."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import _lib
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
+    from tad_dftd3_b200.distributed import LOCAL, dftd3_sharded
+    from tad_dftd3_b200.engine import SystemEngine
+
+    dev, world, rank, dt = cx.dev, cx.world, cx.rank, torch.double
+    lib = _lib.lib()
+    atm = which == "c5a"
+    nwater = (3334 if args.nwater == 16667 else args.nwater) if atm else args.nwater
+    cutoff = args.cutoff if atm else 50.0
+    numbers_h, positions_h = syn.water_cluster(nwater, seed=0)
+    numbers_h, positions_h = numbers_h.pin_memory(), positions_h.pin_memory()
+    numbers, positions = numbers_h.to(dev), positions_h.to(dev)
+    n = int(numbers.shape[0])
+    ref = d3.Reference(cn=REFCN(dt, dev), c6=syn.synthetic_c6_table(dt, dev))
+    refcn, refc6, _ = ref._prepared(dev, dt)
+    rcov_t, r4r2_t = COV_D3(dt, dev), R4R2(dt, dev)
+    rvdw = syn.synthetic_rvdw_table(dt, dev) if atm else None
+    if atm:
+        d3.data.set_vdw_pairwise(rvdw)
+    par = _system_params(cutoff, 1.0 if atm else 0.0)
+    param_f = dict(PARAM, s9=1.0) if atm else dict(PARAM)
+    param = {k: torch.tensor(v, dtype=dt) for k, v in param_f.items()}
+    cut_t = torch.tensor(cutoff, dtype=dt)
+    if atm:
+        units, triangles, edges = count_triples(positions, cutoff)
+        flops = units * 140.0
+        work = {"triples": units, "all_short_triangles": triangles, "short_edges": edges}
+    else:
+        near, far = count_pairs_single(positions)
+        units, flops = near + far, near * FLOPS_NEAR + far * FLOPS_FAR
+        work = {"pair_terms": units, "pairs_within_25_bohr": near}
+
+    eng = SystemEngine(numbers, positions, rcov_t, r4r2_t, refcn, refc6, par, tables=(True, True), rvdw=rvdw)
+
+    def step_resident():
+        eng.step(positions)
+
+    x_leaf = positions.clone().requires_grad_(True)
+
+    def step_api():
+        e = dftd3_sharded(numbers, x_leaf, param, ref=ref, cutoff=cut_t)
+        (gx,) = torch.autograd.grad(e.sum(), x_leaf)
+        return e, gx
+
+    e_h = torch.empty(n, dtype=dt).pin_memory()
+    g_h = torch.empty(n, 3, dtype=dt).pin_memory()
+
+    def step_e2e():
+        eng.step_host(numbers_h, positions_h, e_h, g_h, sync=False)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    cx.barrier()
+    energy, grad = eng.energy.clone(), eng.grad.clone()
+    checks = {"all_outputs_finite": bool(torch.isfinite(energy).all() and torch.isfinite(grad).all()),
+              "max_abs_net_force": float(grad.sum(0).abs().max()), "cuda_graph_captured": eng._graph is not None,
+              "total_energy": float(energy.sum())}
+    if world > 1:
+        solo = SystemEngine(numbers, positions, rcov_t, r4r2_t, refcn, refc6, par, tables=(True, True), rvdw=rvdw,
+                            group=LOCAL, graph=False)
+        e1, g1 = solo.step(positions)
+        err = max(max_rel_err(energy, e1), max_rel_err(grad, g1))
+        checks["max_rel_err_vs_single_gpu"] = cx.reduce_max(err)[0]
+        del solo
+    steps = args.steps if not atm else max(3, min(args.steps, 10))
+    l0 = _lib.launch_count
+    t_steps = cx.timed(step_resident, steps)
+    launches = _lib.launch_count - l0
+    for _ in range(3):
+        step_api()
+    e_api, g_api = step_api()
+    checks["api_equals_engine_bitwise"] = bool(torch.equal(e_api.detach(), energy) and torch.equal(g_api, grad))
+    t_api = cx.timed(step_api, steps)
+    for _ in range(3):
+        step_e2e()
+    t_e2e = cx.timed_sync(step_e2e, steps)
+    checks["e2e_max_abs_grad_diff_vs_resident"] = float((g_h.to(dev) - grad).abs().max())
+    # the dominant sweep alone (same arrays; results of this extra launch are discarded)
+    run = eng.runner
+    rows = run.atm_partition(rank, world) if atm else run.partition(rank, world)
+    sweep = (lambda: run.sweep_atm(True, rows)) if atm else (lambda: run.sweep_pair(True, rows))
+    t_sweep = cx.timed(sweep, min(steps, 5))
+    ms, ms_api, ms_e2e, ms_sweep = cx.reduce_max(float(np.median(t_steps)), float(np.median(t_api)),
+                                                 float(np.median(t_e2e)), float(np.median(t_sweep)))
+    peak = fp64_peak(lib, dev, cx.stream)
+    unit = "triples/s" if atm else "pair-terms/s"
+    achieved = flops / (ms * 1e-3) / 1e12
+    prof = profile_numbers("r2_c5a_atm_kernel_ncu" if atm else "r2_c4_pair_kernel_ncu")
+    rec = {
+        "metric": "ATM energy+grad triples/s fp64" if atm else "D3(BJ) energy+grad pair-terms/s fp64",
+        "value": units / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": dict({
+            "workload": (f"c5a: dftd3() with the ATM term (s9=1) on a {n}-atom water cluster, cutoff {cutoff} Bohr, "
+                         "energy+grad fp64, centres sharded over the GPUs" if atm else
+                         f"c4: {n}-atom water cluster, D3(BJ) two-body + CN (cutoffs 50 / 25 Bohr), energy+grad fp64, "
+                         "rows sharded over the GPUs")}, **work),
+        "details": {
+            "entry": "SystemEngine.step(): one CUDA-graph launch = d3b200_system_pack + memset + d3b200_system_{cn,weights,tvec,pair"
+                     + (",atm" if atm else "") + ",cnbwd}_f64 + NCCL exchanges (CN, dL/dCN, grad, E) + scatter to the caller's order",
+            "sweeps": "pairs-once (fp64 atomics)" if run.symmetric else "full-row (no atomics)",
+            "exchange": "none (one GPU)" if world == 1 else
+                        ("all-reduce" if (run.symmetric or atm) else "in-place all-gather") + " over NCCL, captured in the graph",
+            "dominant_sweep_ms": ms_sweep, "dominant_sweep": "d3b200_system_atm_f64" if atm else "d3b200_system_pair_f64",
+            "l2": "256 MB buffer written between timed steps",
+            "timing": "CUDA events around each step, median over steps, max over ranks",
+            "checks": checks,
+        },
+        "api_resident": {"value": units / (ms_api * 1e-3), "unit": unit, "ms_per_step": ms_api,
+                         "api": "tad_dftd3_b200.distributed.dftd3_sharded() (= dftd3() at one GPU) + torch.autograd.grad on "
+                                "resident tensors (cached engine of the structure)"},
+        "e2e": {"value": units / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(positions_h.numel() * 8) * world,
+                "d2h_bytes_per_step": int(e_h.numel() * 8 + g_h.numel() * 8) * world,
+                "api": "SystemEngine.step_host(): pinned host numbers (validated on the host) + positions in, pinned host "
+                       "energies + gradient out on every rank, one stream synchronize per step; bytes summed over ranks"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak * world, "unit": "TFLOP/s",
+                     "frac": achieved / (peak * world), "traffic": None if prof is None else prof.get("dram_bytes_per_launch"),
+                     "from_profile": prof,
+                     "kernel": "whole step, all ranks (dominant: " + ("d3::system_atm3_kernel" if atm else "d3::sym_pair_t_kernel / system_pair_t_kernel") + ")",
+                     "flops_model": "140 per unordered triple (SURVEY.md 8d)" if atm else
+                                    "140/pair-term (r<=25 Bohr), 89 (25<r<=50), SURVEY.md 8(d)",
+                     "peak_source": "FP64 FMA-chain probe x n_gpus, measured in this run"},
+    }
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        all_host_cores()
+        # (1) the reference itself on the largest sub-cluster it can hold
+        centre = positions.mean(0)
+        nsub = 300 if atm else 2000
+        sub = torch.argsort((positions - centre).norm(dim=1))[:nsub]
+        if atm:
+            t_sub, _, _ = count_triples(positions[sub], cutoff)
+            sec, kind = reference_single(numbers[sub], positions[sub], dict(PARAM, s9=1.0), cutoff=cutoff, rvdw_table=rvdw)
+            sec0, _ = reference_single(numbers[sub], positions[sub], PARAM, cutoff=cutoff)
+            rec["cpu_baseline"] = {"value": t_sub / max(sec - sec0, 1e-9), "unit": unit, "cores": torch.get_num_threads(),
+                                   "kind": kind, "seconds": sec - sec0,
+                                   "sample": "central 300-atom sub-cluster (the reference's ATM is dense N^3), (two-body + ATM) "
+                                             "minus (two-body) wall time, energy + autograd gradient"}
+        else:
+            sn, sf = count_pairs_single(positions[sub])
+            sec, kind = reference_single(numbers[sub], positions[sub], PARAM, chunk_size=256)
+            rec["cpu_baseline"] = {"value": (sn + sf) / sec, "unit": unit, "cores": torch.get_num_threads(), "kind": kind,
+                                   "seconds": sec,
+                                   "sample": "central 2000-atom sub-cluster of the same structure, energy + autograd gradient, "
+                                             "chunk_size=256 (the reference cannot hold 50k atoms)"}
+        # (2) the blocked C port on the FULL structure: a second CPU baseline and the parity check of this run
+        sec, e_o, g_o = blocked_oracle_baseline(numbers, positions, param_f, cutoff, None if rvdw is None else rvdw.cpu())
+        rec["cpu_baseline_port"] = {"value": units / sec, "unit": unit, "cores": os.cpu_count(), "kind": "port", "seconds": sec,
+                                    "sample": "the FULL structure through oracle/d3_blocked.c (gcc -O2, OpenMP)",
+                                    "max_rel_err_gpu_vs_port": max(max_rel_err(energy.cpu(), e_o), max_rel_err(grad.cpu(), g_o))}
+    if atm:
+        d3.data.set_vdw_pairwise(None)
+    eng.release_graph()
+    return rec
 
 
 def run_c5b(args, rank, local, world, dev):
@@ -887,11 +889,63 @@ def run_c5b(args, rank, local, world, dev):
     print(json.dumps(line))
 
 
-def _measured_hbm():
-    try:
-        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except (OSError, KeyError, ValueError):
-        return None
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nmol", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="c3 under torchrun: strong = the fixed batch split over the ranks (default); weak = one batch per rank")
+    ap.add_argument("--e2e-chunk", type=int, default=0,
+                    help="c3 end-to-end: 0 = zero-copy form of dftd3_host (default); > 0 = staged form with this many "
+                         "structures per pipeline chunk")
+    ap.add_argument("--cutoff", type=float, default=25.0, help="c5a: dispersion/triple cutoff in Bohr")
+    ap.add_argument("--workload", default="all", choices=["all", "c3", "c4", "c5a", "c5b"],
+                    help="all: c3 line with c4 and c5a sub-records (default); c3 / c4 / c5a / c5b: that workload alone")
+    ap.add_argument("--nwater", type=int, default=16667)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="c3 only: arithmetic type of the path")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    cx = Ctx(args)
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import engine
+
+    # one process per GPU: keep this rank's host thread and its page-locked buffers on the
+    # NUMA node of its GPU (matters for the end-to-end number when 8 ranks share the host)
+    numa_bound = d3.bind_host_thread_to_gpu(cx.local) if os.environ.get("D3B200_NO_NUMA_BIND") != "1" else False
+    clocks = {}
+    if args.workload == "c5b":
+        run_c5b(args, cx.rank, cx.local, cx.world, cx.dev)
+        line = None
+    elif args.workload in ("c4", "c5a"):
+        with ClockSampler(cx.local) as cs:
+            line = run_system(args, cx, args.workload)
+        line["clocks"] = cs.summary()
+    else:
+        line = run_c3(args, cx, clocks)
+        line["clocks"] = clocks
+        line["e2e"]["host_thread_bound_to_gpu_numa_node"] = bool(numa_bound)
+        if args.workload == "all" and args.dtype == "f64":
+            for which in ("c4", "c5a"):
+                with ClockSampler(cx.local) as cs:
+                    sub = run_system(args, cx, which)
+                sub["clocks"] = cs.summary()
+                line[which] = sub
+                line["gpu_launches"] += sub["gpu_launches"]
+    if cx.rank == 0 and line is not None:
+        print(json.dumps(line))
+    if cx.world > 1:
+        engine.shutdown()
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

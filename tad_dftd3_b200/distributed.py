@@ -37,8 +37,11 @@ from .system import TILE, SystemPlan, SystemRunner, row_partition
 __all__ = ["run_sharded", "dftd3_sharded"]
 
 
+LOCAL = False   # `group=LOCAL`: this process alone, even inside an initialised process group
+
+
 def _world(group):
-    if not dist.is_available() or not dist.is_initialized():
+    if group is LOCAL or not dist.is_available() or not dist.is_initialized():
         return 0, 1
     return dist.get_rank(group), dist.get_world_size(group)
 
@@ -55,7 +58,7 @@ def _exchange(t: Tensor, rows, group, mode: str) -> None:
     mode "sum": contributions to any row may come from any rank (pairs-once sweeps, the
     three-body term, ragged row ranges): all-reduce over arrays that are zero where a rank
     did not contribute."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+    if _world(group)[1] <= 1:
         return
     if mode == "gather":
         flat = t.reshape(-1)

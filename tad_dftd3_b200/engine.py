@@ -41,7 +41,7 @@ from . import _lib
 from .distributed import _world, run_sharded
 from .system import SystemPlan, SystemRunner
 
-__all__ = ["SystemEngine", "engine_for"]
+__all__ = ["SystemEngine", "engine_for", "shutdown"]
 
 
 class SystemEngine:
@@ -155,7 +155,29 @@ class SystemEngine:
         return energy_out, grad_out
 
 
+    def release_graph(self) -> None:
+        """Drop the captured CUDA graph (the next steps run eagerly and re-capture).  A graph that
+        holds captured NCCL work must be destroyed BEFORE its communicator:
+        `dist.destroy_process_group()` otherwise waits forever (observed with NCCL 2.28)."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph = None
+        self._eager_steps = 0
+
+
 _engines: dict = {}
+
+
+def shutdown() -> None:
+    """Release every cached engine (graphs first).  Call before `dist.destroy_process_group()`."""
+    import gc
+
+    for _, eng in list(_engines.values()):
+        eng.release_graph()
+    _engines.clear()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
 
 
 def engine_for(numbers: Tensor, positions: Tensor, rcov: Tensor, r4r2: Tensor, refcn: Tensor, refc6: Tensor,

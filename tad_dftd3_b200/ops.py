@@ -223,6 +223,7 @@ def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None, want_p: bool = Fals
             "rvdw table only (pass rvdw=None); a dense per-pair rvdw is limited to "
             "structures that fit the fused kernel"
         )
+    from .distributed import LOCAL
     from .engine import engine_for
 
     es, gs, ps = [], [], []
@@ -234,7 +235,7 @@ def _tiled_run(c: "_Call", g, want_grad: bool, numbers=None, want_p: bool = Fals
         # the same numbers tensor keeps coming back (MD / optimisation loops)
         eng = engine_for(z, c.x[b], rcov, r4r2, c.refcn, c.refc6, c.par,
                          tables=(c.st.rcov_per_element, c.st.r4r2_per_element), rvdw=c.rvdw,
-                         want_grad=want_grad, general_g=g is not None)
+                         group=LOCAL, want_grad=want_grad, general_g=g is not None)
         if g is not None:
             eng.set_cotangent(g[b])
         e, gr = eng.step(c.x[b])

@@ -35,6 +35,9 @@ def rel(a, b, atol=1e-12):
 
 
 def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(int(os.environ.get("D3B200_HANG_DUMP_S", "120")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--nwater", type=int, default=700)
     ap.add_argument("--atm", action="store_true")
@@ -105,7 +108,10 @@ def main():
         out["max_rel_err_vs_oracle"] = max(er_, gr_)
     dist.barrier()
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    from tad_dftd3_b200.engine import shutdown
+
+    shutdown()          # graphs with captured NCCL work go before the communicator
     dist.destroy_process_group()
 
 
