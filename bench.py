@@ -394,9 +394,11 @@ class Ctx:
 
 
 def max_rel_err(a, b, atol=1e-12):
-    """Residual of the parity gate |a - b| <= atol + rtol |b|: the smallest rtol that passes."""
-    d = (a - b).abs()
-    return float(((d - atol).clamp_min(0) / b.abs().clamp_min(1e-300)).max()) if d.numel() else 0.0
+    """Residual of the parity gate |a - b| <= atol + rtol |b|: the smallest rtol that passes
+    (entries where the comparison value `b` is not finite are skipped; see `reference_nan_structures`)."""
+    ok = torch.isfinite(b)
+    d = (a - b).abs()[ok]
+    return float(((d - atol).clamp_min(0) / b[ok].abs().clamp_min(1e-300)).max()) if d.numel() else 0.0
 
 
 def profile_numbers(name):
@@ -600,6 +602,10 @@ def run_c3(args, cx, clocks_out):
                       f"torch {torch.__version__} CPU fp64",
             "max_rel_err_gpu_vs_this_run": max_rel_err(grad[rows].cpu().double(), g_ref,
                                                        1e-12 if args.dtype == "f64" else 1e-7),
+            # The reference's autograd gradient is NaN for a structure in which every Gaussian weight of an atom
+            # underflows (crowded sulfur atoms of the chain-growth generator, CN > 15: the all-zero fallback of
+            # model/weights.py:162-174 divides 0 by 0 in backward); the kernels return the finite limit (dw = 0).
+            "reference_nan_structures": int((~torch.isfinite(g_ref)).any(-1).any(-1).sum()),
         }
     return rec
 
@@ -723,7 +729,8 @@ def run_system(args, cx, which):
     for _ in range(3):
         step_api()
     e_api, g_api = step_api()
-    checks["api_equals_engine_bitwise"] = bool(torch.equal(e_api.detach(), energy) and torch.equal(g_api, grad))
+    # (pairs-once sweeps add with fp64 atomics: equal to rounding, not bitwise)
+    checks["max_rel_err_api_vs_engine"] = max(max_rel_err(e_api.detach(), energy), max_rel_err(g_api, grad))
     t_api = cx.timed(step_api, steps)
     for _ in range(3):
         step_e2e()
@@ -736,6 +743,8 @@ def run_system(args, cx, which):
     t_sweep = cx.timed(sweep, min(steps, 5))
     ms, ms_api, ms_e2e, ms_sweep = cx.reduce_max(float(np.median(t_steps)), float(np.median(t_api)),
                                                  float(np.median(t_e2e)), float(np.median(t_sweep)))
+    eng.profile_step(positions)
+    phases = eng.profile_step(positions)           # eager launches with events at the phase boundaries (this rank)
     peak = fp64_peak(lib, dev, cx.stream)
     unit = "triples/s" if atm else "pair-terms/s"
     achieved = flops / (ms * 1e-3) / 1e12
@@ -756,7 +765,7 @@ def run_system(args, cx, which):
             "sweeps": "pairs-once (fp64 atomics)" if run.symmetric else "full-row (no atomics)",
             "exchange": "none (one GPU)" if world == 1 else
                         ("all-reduce" if (run.symmetric or atm) else "in-place all-gather") + " over NCCL, captured in the graph",
-            "dominant_sweep_ms": ms_sweep, "dominant_sweep": "d3b200_system_atm_f64" if atm else "d3b200_system_pair_f64",
+            "dominant_sweep_ms": ms_sweep, "phases_ms_eager_rank0": {k: round(v, 4) for k, v in phases.items()}, "dominant_sweep": "d3b200_system_atm_f64" if atm else "d3b200_system_pair_f64",
             "l2": "256 MB buffer written between timed steps",
             "timing": "CUDA events around each step, median over steps, max over ranks",
             "checks": checks,

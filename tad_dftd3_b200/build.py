@@ -50,6 +50,17 @@ def nvcc() -> str:
     return exe
 
 
+def build_variant(out: str, extra_flags) -> str:
+    """Kernel experiments: another build of the same library with extra nvcc flags (e.g. -DD3_V2_TMEM=0),
+    selected at run time through $TAD_DFTD3_B200_LIB."""
+    cus = [f for f in sources() if f.endswith(".cu")]
+    res = subprocess.run([nvcc(), *NVCC_FLAGS, *extra_flags, "-o", out, *cus], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building " + out)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     digest = _digest()
     if not force and os.path.isfile(LIB) and os.path.isfile(STAMP):
@@ -70,4 +81,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:            # python -m tad_dftd3_b200.build --variant out.so -DFLAG=0 ...
+        k = sys.argv.index("--variant")
+        print(build_variant(sys.argv[k + 1], sys.argv[k + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -68,7 +68,7 @@ def _exchange(t: Tensor, rows, group, mode: str) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
-def run_sharded(runner, want_grad: bool, group=None, zero: bool = True):
+def run_sharded(runner, want_grad: bool, group=None, zero: bool = True, mark=None):
     """Drive the sweeps of `runner` on this rank's rows and exchange the
     per-atom arrays.  Returns the rank's row range; afterwards `runner.energy`
     (and `runner.grad`) are complete on every rank.
@@ -85,23 +85,33 @@ def run_sharded(runner, want_grad: bool, group=None, zero: bool = True):
     atm_on = getattr(runner, "sweep_atm", None) is not None and getattr(runner.par, "s9", 0.0) != 0.0
     mode_cn = "gather" if contiguous else "sum"
     mode_out = "gather" if (contiguous and not atm_on) else "sum"
+    mark = mark or (lambda name: None)          # phase boundaries (SystemEngine.profile_step)
     if zero:
         for t in (runner.cn, runner.decn, runner.energy, runner.grad):
             t.zero_()
+    mark("zero")
     runner.sweep_cn(rows)
+    mark("sweep_cn")
     _exchange(runner.cn, rows, group, mode_cn)
+    mark("exchange_cn")
     runner.weights()
+    mark("weights")
     runner.sweep_pair(want_grad, rows)
+    mark("sweep_pair")
     atm = getattr(runner, "sweep_atm", None)
     if atm is not None:
         apart = getattr(runner, "atm_partition", None)
         # adds to energy / grad / dL/dCN of every atom of a triple (no-op when s9 == 0)
         atm(want_grad, apart(rank, world) if apart is not None else rows)
+        mark("sweep_atm")
     if want_grad:
         _exchange(runner.decn, rows, group, mode_out)
+        mark("exchange_decn")
         runner.sweep_cnbwd(rows)
+        mark("sweep_cnbwd")
         _exchange(runner.grad, rows, group, mode_out)
     _exchange(runner.energy, rows, group, mode_out)
+    mark("exchange_out")
     return rows
 
 

@@ -80,16 +80,41 @@ class SystemEngine:
         self.steps = 0
 
     # ------------------------------------------------------------------
-    def _sequence(self):
+    def _sequence(self, mark=None):
         plan, run = self.plan, self.runner
         plan.repack(self.x_in)
         if not self._unit_g:
             run.auxt[: plan.n, 1] = self.g_in[plan.perm]
         run.buf[: 6 * plan.npad].zero_()            # cn, decn, energy, grad
-        run_sharded(run, self.want_grad, self.group, zero=False)
+        if mark:
+            mark("pack")
+        run_sharded(run, self.want_grad, self.group, zero=False, mark=mark)
         self.energy.index_copy_(0, plan.perm, run.energy[: plan.n])
         if self.want_grad:
             self.grad.index_copy_(0, plan.perm, run.grad[: plan.n])
+        if mark:
+            mark("scatter")
+
+    def profile_step(self, positions: Tensor) -> dict:
+        """One EAGER step with CUDA events at the phase boundaries: {phase: ms} (diagnostics for bench.py;
+        collectives included, so every rank of the group must call it)."""
+        self.x_in.copy_(positions.detach())
+        stream = torch.cuda.current_stream(self.device)
+        names, events = [], [torch.cuda.Event(enable_timing=True)]
+        events[0].record(stream)
+
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            names.append(name)
+            events.append(ev)
+
+        with torch.cuda.device(self.device):
+            self._sequence(mark)
+        torch.cuda.synchronize(self.device)
+        out = {n: events[k].elapsed_time(events[k + 1]) for k, n in enumerate(names)}
+        out["total"] = events[0].elapsed_time(events[-1])
+        return out
 
     def _capture(self):
         stream = torch.cuda.current_stream(self.device)
