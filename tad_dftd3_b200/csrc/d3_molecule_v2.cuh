@@ -110,6 +110,19 @@ template <int V> __device__ __forceinline__ int red_row(int lane) {
   return lane / Q;
 }
 
+// -(1/r) d f / d r = kcn rc r^-3 f (1 - f) of the counting function for one pair (0 when the pair does not
+// count): what the CN sweep stores in TMEM, recomputed for the pairs that did not fit.
+template <typename S>
+__device__ __noinline__ S cn_df_recompute(S dx, S dy, S dz, S rk, bool pj, S cn_cutoff2, S kcn) {
+  const S r2 = dx * dx + dy * dy + dz * dz;
+  const bool ok = pj & (r2 <= cn_cutoff2) & (r2 >= eps_of<S>());
+  const S rinv = frsq(r2 + tiny_of<S>());
+  const S e = fex(fmx(kcn - rk * rinv, S(-700)));
+  const S f = frcp(S(1) + e);
+  const S dfv = (rk * (rinv * rinv * rinv)) * (f * (e * f));
+  return ok ? dfv : S(0);
+}
+
 // QE: r4r2 comes from the per-element table (the default `r4r2=None` of dftd3()), so
 // R0 = a1 sqrt(3 q_i q_j) + a2, R0^6, R0^8 and s8 * 3 q_i q_j depend on (row, partner
 // ELEMENT) only and are hoisted out of the partner loop next to the U contraction.
@@ -353,7 +366,10 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
   // ---------------------------------------------------------------- phase 3
   constexpr int PB = D3_V2_PB;              // partners per iteration and half-warp
   constexpr int PV = WANT_G ? 5 : 1;        // j-side values per partner
-  D3_PIECES_BEGIN(18)
+#ifndef D3_V2_OVH3
+#define D3_V2_OVH3 18
+#endif
+  D3_PIECES_BEGIN(D3_V2_OVH3)
   {
     const Atom4<S> ai = sA[ic];
     const Pair2<S> bi = sB[ic];
@@ -481,8 +497,11 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
         }
       };
       const int nrg = gnref[grp];
+#ifndef D3_V2_NR3
+#define D3_V2_NR3 1
+#endif
       if (nrg <= 2) sweep(std::integral_constant<int, 2>{});
-      else if (nrg == 3) sweep(std::integral_constant<int, 3>{});
+      else if (D3_V2_NR3 && nrg == 3) sweep(std::integral_constant<int, 3>{});
       else if (nrg <= 5) sweep(std::integral_constant<int, 5>{});
       else sweep(std::integral_constant<int, kNRef>{});
     }
@@ -538,15 +557,10 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
           if (cached) {
             df = dfc[GB * h + s];
           } else {
-            S r2 = dx * dx + dy * dy + dz * dz;
+            // structure too large for the TMEM slots of this lane: recompute (kept out of line so that the
+            // common loop body stays small)
             const bool pj = irow & ((unsigned)(j - i - 1) < jspan);
-            const bool ok = pj & (r2 <= A.cn_cutoff2) & (r2 >= eps);
-            S rinv = frsq(r2 + tiny);
-            S rk = ai.rk + aj.rk;
-            S e = fex(fmx(A.kcn - rk * rinv, S(-700)));
-            S f = frcp(S(1) + e);
-            S dfv = (rk * (rinv * rinv * rinv)) * (f * (e * f));
-            df = ok ? dfv : S(0);
+            df = cn_df_recompute<S>(dx, dy, dz, ai.rk + aj.rk, pj, A.cn_cutoff2, A.kcn);
           }
           S c = (dci + sdecn[jc]) * df;                 // = -(dL/dCN_i + dL/dCN_j) f'(r) / r
           S cx = c * dx, cy = c * dy, cz = c * dz;
