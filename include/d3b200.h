@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define D3B200_ABI_VERSION 1
+#define D3B200_ABI_VERSION 2
 #define D3B200_MAX_ELEMENT 104 /* reference defaults.py:72 */
 #define D3B200_NREF 7          /* reference systems per element, reference.py:32-161 */
 
@@ -56,6 +56,14 @@ typedef struct d3b200_params {
   double s6, s8, a1, a2;
   double s9, rs9, alp;
   double cutoff, cn_cutoff, kcn;
+  /* Model functions behind the reference's callable hooks (disp.py:89-91); 0 = the defaults.
+   *  counting: 0 exp_count  1 / (1 + exp(-kcn (rc/r - 1)))            (tad-mctc ncoord/count.py)
+   *            1 erf_count  (1 + erf(-kcn (r/rc - 1))) / 2
+   *  damping:  0 rational_damping  1 / (r^n + (a1 sqrt(qq) + a2)^n)      (damping/rational.py:68)
+   *            1 zero_damping      1 / (r^n (1 + 6 (rs_n sqrt(qq) / r)^alp_n)), rs_6 = a1, rs_8 = a2 of this
+   *              struct, alp_6 = alp, alp_8 = alp + 2 (D3(0)-style damping on the radius sqrt(C8/C6))
+   * Non-default functions run in the general fused kernel (structures up to d3b200_batch_max_atoms_*(1)). */
+  int32_t counting, damping;
 } d3b200_params;
 
 /* Model data and per-atom inputs shared by all batch entry points.

@@ -13,14 +13,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # TAD_DFTD3_B200_LIB points at another build of the same library (kernel experiments)
 LIB_PATH = os.environ.get("TAD_DFTD3_B200_LIB") or os.path.join(HERE, "libd3b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Params(C.Structure):
     """`d3b200_params` (host memory)."""
 
     _fields_ = [(k, C.c_double) for k in
-                ("s6", "s8", "a1", "a2", "s9", "rs9", "alp", "cutoff", "cn_cutoff", "kcn")]
+                ("s6", "s8", "a1", "a2", "s9", "rs9", "alp", "cutoff", "cn_cutoff", "kcn")] + [
+        ("counting", C.c_int32), ("damping", C.c_int32)]   # model functions, 0 = defaults (see d3b200.h)
 
 
 class Model(C.Structure):

@@ -118,8 +118,15 @@ int fill_common(d3::MolArgs<S>& a, int nbatch, int natoms, const int64_t* number
   a.cutoff2 = cut * cut;
   a.cn_cutoff2 = cncut * cncut;
   a.kcn = (B)par->kcn;
+  if (par->counting < 0 || par->counting > 1 || par->damping < 0 || par->damping > 1)
+    return fail(D3B200_EINVAL, "unknown counting / damping function id%s");
+  a.counting = par->counting;
+  a.damping = par->damping;
   return D3B200_OK;
 }
+
+// the pairs-once kernel (molecule_kernel_v2) implements the default model functions only
+inline bool default_model(const d3b200_params* par) { return par->counting == 0 && par->damping == 0; }
 
 template <typename S>
 size_t workspace_bytes(int nbatch, int natoms, int atm) {
@@ -151,7 +158,7 @@ int energy_impl(int nbatch, int natoms, const int64_t* numbers, const B* positio
   if ((rc = set_workspace(a, par, workspace, wbytes))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (par->s9 != 0.0) return launch<B, d3::kWantE | d3::kAtm>(a, s);
-  if (v2_fits<B>(natoms)) return launch_v2<B, false>(a, s);
+  if (v2_fits<B>(natoms) && default_model(par)) return launch_v2<B, false>(a, s);
   return launch<B, d3::kWantE>(a, s);
 }
 
@@ -179,11 +186,11 @@ int vjp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
   }
   if (energy) {
     if (atm) return launch<B, kWantE | kWantG | kAtm>(a, s);
-    if (v2_fits<B>(natoms)) return launch_v2<B, true>(a, s);
+    if (v2_fits<B>(natoms) && default_model(par)) return launch_v2<B, true>(a, s);
     return launch<B, kWantE | kWantG>(a, s);
   }
   if (atm) return launch<B, kWantG | kAtm>(a, s);
-  if (v2_fits<B>(natoms)) return launch_v2<B, true>(a, s);
+  if (v2_fits<B>(natoms) && default_model(par)) return launch_v2<B, true>(a, s);
   return launch<B, kWantG>(a, s);
 }
 

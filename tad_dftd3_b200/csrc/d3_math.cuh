@@ -109,6 +109,12 @@ template <typename T> D3_HD Dual<T> ex(Dual<T> a) {
   return Dual<T>(e, e * a.d);
 }
 
+D3_HD float er(float a) { return erff(a); }
+D3_HD double er(double a) { return erf(a); }
+template <typename T> D3_HD Dual<T> er(Dual<T> a) {
+  return Dual<T>(er(a.v), T(1.1283791670955126) * ex(-(a.v * a.v)) * a.d);   // 2 / sqrt(pi)
+}
+
 D3_HD float lg(float a) { return logf(a); }
 D3_HD double lg(double a) { return log(a); }
 template <typename T> D3_HD Dual<T> lg(Dual<T> a) { return Dual<T>(lg(a.v), a.d / a.v); }

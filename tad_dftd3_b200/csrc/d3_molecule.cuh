@@ -56,6 +56,7 @@ struct MolArgs {
   B* dpgrad;
   S* work;                  // ATM scratch: sqrt|C6| per structure, [nbatch][N][N]
   const int* order;         // optional: CTA k works on structure order[k] (scheduling hint)
+  int counting, damping;    // model functions (d3b200_params.counting / .damping); molecule_kernel only
   int host_io;              // molecule_kernel_v2: numbers / positions / energy / grad may live in mapped HOST
                             // memory -> every global access of these arrays fully coalesced
 };
@@ -136,6 +137,77 @@ __device__ __forceinline__ void reference_weights(
     w[a] = narrow<S>(wa[a]);
     dw[a] = narrow<S>(d);
   }
+}
+
+// ---- model functions behind the reference's callable hooks (disp.py:89-91) ---------------------------
+enum : int { kCountExp = 0, kCountErf = 1 };
+enum : int { kDampRational = 0, kDampZero = 1 };
+
+// Counting function f(r) and df = f'(r) / r of one pair (r2 = r^2 > 0, rc = rcov_i + rcov_j).
+//   exp (D3, tad-mctc exp_count):  f = 1 / (1 + exp(-kcn (rc / r - 1)))
+//   erf (tad-mctc erf_count):      f = (1 + erf(-kcn (r / rc - 1))) / 2
+template <typename S, typename B>
+__device__ __forceinline__ void counting_pair(int kind, S r2, S rc, B kcn, S& f, S& df) {
+  S rinv = frsq(r2);
+  if (kind == kCountErf) {
+    S x = r2 * rinv * rcp(rc);                    // r / rc
+    S y = kcn * (B(1) - x);
+    f = B(0.5) * (B(1) + er(y));
+    // f' = -kcn / (rc sqrt(pi)) exp(-y^2)
+    df = (B(-0.5641895835477563) * kcn) * (rcp(rc) * rinv) * ex(-(y * y));
+    return;
+  }
+  S arg = kcn * (rc * rinv - B(1));
+  S e = fex(fmx(-arg, B(-700)));
+  f = frcp(B(1) + e);
+  df = (-kcn) * (rc * (rinv * rinv * rinv)) * (f * (e * f));   // f (1 - f) = e f^2
+}
+
+// Two-body radial factors t6, t8 (E_ij = -C6 (s6 t6 + s8 qq t8)), their derivatives with respect to r^2
+// and with respect to the two damping parameters (p1, p2) = (a1, a2) or (rs6, rs8).
+//   rational (BJ, damping/rational.py:68):  t_n = 1 / (r^n + R0^n),  R0 = a1 sqrt(qq) + a2
+//   zero (D3(0)-style on R0 = sqrt(qq)):     t_n = r^-n / (1 + 6 (rs_n R0 / r)^alp_n)
+template <typename S, typename B>
+__device__ __forceinline__ void damping_pair(int kind, S r2, S sqq, S p1, S p2, B alp6,
+                                             S& t6, S& t8, S& dt6, S& dt8,     // dt_n = -d t_n / d(r^2)
+                                             S& t6p1, S& t6p2, S& t8p1, S& t8p2) {
+  if (kind == kDampZero) {
+    const B alp8 = alp6 + B(2);
+    S rinv = frsq(r2);
+    S ir2 = rinv * rinv;
+    S ir6 = ir2 * ir2 * ir2;
+    S u6 = pw(p1 * (sqq * rinv), alp6), u8 = pw(p2 * (sqq * rinv), alp8);
+    S f6 = frcp(B(1) + B(6) * u6), f8 = frcp(B(1) + B(6) * u8);
+    t6 = ir6 * f6;
+    t8 = (ir6 * ir2) * f8;
+    // d t_n / d r^2 = t_n / r^2 (-n/2 + 3 alp_n u_n f_n)
+    dt6 = (t6 * ir2) * (B(3) - (B(3) * alp6) * (u6 * f6));
+    dt8 = (t8 * ir2) * (B(4) - (B(3) * alp8) * (u8 * f8));
+    // d t_n / d rs_n = -6 alp_n t_n f_n u_n / rs_n
+    t6p1 = (B(-6) * alp6) * ((t6 * f6) * (u6 * rcp(p1)));
+    t8p2 = (B(-6) * alp8) * ((t8 * f8) * (u8 * rcp(p2)));
+    t6p2 = S(B(0));
+    t8p1 = S(B(0));
+    return;
+  }
+  S r0 = p1 * sqq + p2;
+  S r02 = r0 * r0;
+  S r06 = r02 * r02 * r02;
+  S r08 = r06 * r02;
+  S r4 = r2 * r2;
+  S r6 = r4 * r2;
+  S r8 = r4 * r4;
+  t6 = frcp(r6 + r06);
+  t8 = frcp(r8 + r08);
+  S t62 = t6 * t6, t82 = t8 * t8;
+  dt6 = B(3) * (r4 * t62);
+  dt8 = B(4) * (r6 * t82);
+  // d t_n / d R0 = -n R0^(n-1) t_n^2;  dR0/da1 = sqrt(qq), dR0/da2 = 1
+  S r05 = r02 * r02 * r0;
+  t6p2 = B(-6) * (r05 * t62);
+  t8p2 = B(-8) * ((r05 * r02) * t82);
+  t6p1 = t6p2 * sqq;
+  t8p1 = t8p2 * sqq;
 }
 
 // One ATM term and its derivative with respect to a = r_ij^2
@@ -278,9 +350,15 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
       S r2 = dx * dx + dy * dy + dz * dz;
       if (val(r2) > A.cn_cutoff2) continue;
       if (val(r2) < eps) r2 = S(eps);
-      S rinv = frsq(r2);
-      S arg = A.kcn * ((rci + srcov[j]) * rinv - B(1));
-      cn += frcp(B(1) + fex(fmx(-arg, B(-700))));
+      if (A.counting == kCountExp) {
+        S rinv = frsq(r2);
+        S arg = A.kcn * ((rci + srcov[j]) * rinv - B(1));
+        cn += frcp(B(1) + fex(fmx(-arg, B(-700))));
+      } else {
+        S f, df;
+        counting_pair<S, B>(A.counting, r2, rci + srcov[j], A.kcn, f, df);
+        cn += f;
+      }
     }
     scn[i] = cn;
     S wi[kNRef], dwi[kNRef];
@@ -300,7 +378,7 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
     for (int a = 0; a < kNRef; ++a) { wi[a] = sw[8 * i + a]; dwi[a] = sdw[8 * i + a]; }
     S e_i = S(B(0)), gx = S(B(0)), gy = S(B(0)), gz = S(B(0)), decn = S(B(0));
     const B gi = sg[i];
-    const S sa_i = A.a1 * sqr(B(3) * qi);   // a1 sqrt(3 q_i);  R0 = sa_i sqrt(q_j) + a2
+    const S s3q_i = sqr(B(3) * qi);         // sqrt(3 q_i);  sqrt(qq) = s3q_i sqrt(q_j)
     const S q3_i = B(3) * qi;
     for (int grp = 0; grp < ng; ++grp) {
       const int Zj = gZ[grp];
@@ -334,15 +412,9 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
         }
         if (val(r2) < eps) r2 = S(eps);
         S qq = q3_i * sq[j];
-        S r0 = sa_i * ssq[j] + A.a2;
-        S r02 = r0 * r0;
-        S r06 = r02 * r02 * r02;
-        S r08 = r06 * r02;
-        S r4 = r2 * r2;
-        S r6 = r4 * r2;
-        S r8 = r4 * r4;
-        S t6 = frcp(r6 + r06);
-        S t8 = frcp(r8 + r08);
+        S sqq = s3q_i * ssq[j];                    // sqrt(qq) = sqrt(3 q_i q_j)
+        S t6, t8, dt6, dt8, t6p1, t6p2, t8p1, t8p2;
+        damping_pair<S, B>(A.damping, r2, sqq, A.a1, A.a2, val(A.alp), t6, t8, dt6, dt8, t6p1, t6p2, t8p1, t8p2);
         S s8q = A.s8 * qq;
         S P = A.s6 * t6 + s8q * t8;
         if (WANT_E) e_i += c6 * P;   // scaled by -1/2 at the end
@@ -353,9 +425,8 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
           B gam = B(0.5) * (gi + sg[j]);
           // dL/dC6_ij = -gam P ;  dL/dCN_i += that * dC6_ij/dCN_i
           decn -= (gam * P) * dc6;
-          // -dP/d(r^2) = 3 s6 r^4 t6^2 + 4 s8 qq r^6 t8^2
-          S t62 = t6 * t6, t82 = t8 * t8;
-          S dP = B(3) * (A.s6 * (r4 * t62)) + B(4) * (s8q * (r6 * t82));
+          // -dP/d(r^2) = s6 dt6 + s8 qq dt8
+          S dP = A.s6 * dt6 + s8q * dt8;
           // dL/dx_i = -gam C6 dP/dr2 * 2 d
           S f = (B(2) * gam) * (c6 * dP);
           gx += f * dx; gy += f * dy; gz += f * dz;
@@ -364,12 +435,9 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
             S hc = (B(-0.5) * gam) * c6;
             p_s6 += hc * t6;
             p_s8 += hc * (qq * t8);
-            // dP/dR0 = -(6 s6 R0^5 t6^2 + 8 s8 qq R0^7 t8^2)
-            S r05 = r02 * r02 * r0;
-            S dPr0 = B(-6) * (A.s6 * (r05 * t62)) - B(8) * (s8q * ((r05 * r02) * t82));
-            S h = hc * dPr0;
-            p_a2 += h;
-            p_a1 += h * sqr(qq);
+            // derivatives with respect to the two damping parameters (a1, a2) / (rs6, rs8)
+            p_a1 += hc * (A.s6 * t6p1 + s8q * t8p1);
+            p_a2 += hc * (A.s6 * t6p2 + s8q * t8p2);
           }
         }
       }
@@ -513,12 +581,8 @@ __global__ void __launch_bounds__(kMolThreads) molecule_kernel(MolArgs<S> A) {
         S r2 = dx * dx + dy * dy + dz * dz;
         if (val(r2) > A.cn_cutoff2) continue;
         if (val(r2) < eps) continue;  // clamped distance: no position dependence
-        S rinv = frsq(r2);
-        S rc = rci + srcov[j];
-        S arg = A.kcn * (rc * rinv - B(1));
-        S e = fex(fmx(-arg, B(-700)));
-        S f = frcp(B(1) + e);
-        S df = (-A.kcn) * (rc * (rinv * rinv * rinv)) * (f * (e * f));  // f(1-f) = e f^2
+        S f, df;
+        counting_pair<S, B>(A.counting, r2, rci + srcov[j], A.kcn, f, df);
         S c = (decn + sdecn[j]) * df;
         gx += c * dx; gy += c * dy; gz += c * dz;
       }

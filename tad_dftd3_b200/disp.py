@@ -91,14 +91,15 @@ def _scalar(v: Any) -> float:
     return float(v.detach()) if isinstance(v, Tensor) else float(v)
 
 
-def _param_vector(param: dict, dtype) -> Tensor:
-    """(s6, s8, a1, a2, s9) with the reference's defaults; keeps the autograd graph."""
-    keys = ("s6", "s8", "a1", "a2", "s9")
-    dflt = (defaults.S6, defaults.S8, defaults.A1, defaults.A2, 0.0)
+def _param_vector(param: dict, dtype, damping_id: int = 0) -> Tensor:
+    """(s6, s8, a1, a2, s9) with the reference's defaults -- (s6, s8, rs6, rs8, s9) for zero damping --;
+    keeps the autograd graph."""
+    keys = ("s6", "s8", "a1", "a2", "s9") if damping_id == 0 else ("s6", "s8", "rs6", "rs8", "s9")
+    dflt = (defaults.S6, defaults.S8, defaults.A1, defaults.A2, 0.0) if damping_id == 0 else (defaults.S6, defaults.S8, 1.0, 1.0, 0.0)
     vals = [param.get(k, d) for k, d in zip(keys, dflt)]
     live = [v for v in vals if isinstance(v, Tensor) and (v.requires_grad or _is_functorch(v))]
     if not live:
-        key = tuple(_scalar(v) for v in vals) + (dtype,)
+        key = tuple(_scalar(v) for v in vals) + (dtype, damping_id)
         t = _pvec_cache.get(key)
         if t is None:
             if len(_pvec_cache) > 64:
@@ -145,13 +146,19 @@ def dftd3(
 
     `chunk_size` is accepted and ignored: no `N x N x 7 x 7` tensor exists.
     """
-    if counting_function is not exp_count or weighting_function is not gaussian_weight \
-            or damping_function is not rational_damping:
+    from .damping import DAMPING_IDS
+    from .ncoord import COUNTING_IDS
+
+    if counting_function not in COUNTING_IDS or weighting_function is not gaussian_weight \
+            or damping_function not in DAMPING_IDS:
         raise NotImplementedError(
-            "tad_dftd3_b200 implements the default D3(BJ) model functions "
-            "(exp_count, gaussian_weight, rational_damping) as CUDA kernels; "
-            "custom callables are not supported."
+            "tad_dftd3_b200 implements these model functions as CUDA kernels: counting_function exp_count "
+            "(default) or erf_count, weighting_function gaussian_weight, damping_function rational_damping "
+            "(default) or zero_damping (the objects exported by tad_dftd3_b200.ncoord / .model / .damping); "
+            "arbitrary Python callables cannot run inside the kernels and are not supported."
         )
+    counting_id, kcn = COUNTING_IDS[counting_function]
+    damping_id = DAMPING_IDS[damping_function]
     if numbers.shape != positions.shape[:-1]:
         raise ValueError(
             f"Shape of positions ({tuple(positions.shape[:-1])}) is not consistent "
@@ -214,10 +221,10 @@ def dftd3(
     st = Settings(
         rcov_per_element=rcov_pe, r4r2_per_element=r4r2_pe, rvdw_mode=rvdw_mode,
         cutoff=defaults.D3_DISP_CUTOFF if cutoff is None else _scalar(cutoff),
-        cn_cutoff=defaults.D3_CN_CUTOFF, kcn=defaults.D3_KCN,
-        alp=_scalar(param.get("alp", defaults.ALP)),
+        cn_cutoff=defaults.D3_CN_CUTOFF, kcn=kcn,
+        alp=_scalar(param.get("alp", defaults.ALP)), counting=counting_id, damping=damping_id,
     )
-    p = _param_vector(param if atm else {k: v for k, v in param.items() if k != "s9"}, dtype)
+    p = _param_vector(param if atm else {k: v for k, v in param.items() if k != "s9"}, dtype, damping_id)
     if _raw:
         return p, rcov_t, r4r2_t, rvdw_t, refcn, refc6, st
     return d3_energy(numbers, positions, p, rcov_t, r4r2_t, rvdw_t, refcn, refc6, st)

@@ -109,8 +109,14 @@ def run_sharded(runner, want_grad: bool, group=None, zero: bool = True, mark=Non
         mark("exchange_decn")
         runner.sweep_cnbwd(rows)
         mark("sweep_cnbwd")
-        _exchange(runner.grad, rows, group, mode_out)
-    _exchange(runner.energy, rows, group, mode_out)
+    # E and dL/dx: one message when they sit next to each other in the runner's work buffer and are summed
+    both = getattr(runner, "energy_grad", None) if (want_grad and mode_out == "sum") else None
+    if both is not None:
+        _exchange(both, rows, group, "sum")
+    else:
+        if want_grad:
+            _exchange(runner.grad, rows, group, mode_out)
+        _exchange(runner.energy, rows, group, mode_out)
     mark("exchange_out")
     return rows
 

@@ -50,6 +50,8 @@ class Settings:
     kcn: float = 16.0
     rs9: float = 1.3333333730697632  # float32(4/3), reference disp.py:312
     alp: float = 14.0
+    counting: int = 0   # d3b200_params.counting: 0 exp_count, 1 erf_count
+    damping: int = 0    # d3b200_params.damping: 0 rational (p[2], p[3] = a1, a2), 1 zero (p[2], p[3] = rs6, rs8)
 
 
 def _sfx(dtype: torch.dtype) -> str:
@@ -69,6 +71,7 @@ def _params(vals, st: Settings) -> _lib.Params:
     p.s6, p.s8, p.a1, p.a2, p.s9 = (float(v) for v in vals)
     p.rs9, p.alp = st.rs9, st.alp
     p.cutoff, p.cn_cutoff, p.kcn = st.cutoff, st.cn_cutoff, st.kcn
+    p.counting, p.damping = int(st.counting), int(st.damping)
     return p
 
 
@@ -211,8 +214,14 @@ def _tiled(c: "_Call", order: int) -> bool:
     """Structures beyond the one-CTA limit go to the tiled `d3b200_system_*` sweeps."""
     if not (c.nflat and c.n):
         return False
-    if os.environ.get("TAD_DFTD3_B200_TILED") == "1":
+    default_model = c.st.counting == 0 and c.st.damping == 0
+    if os.environ.get("TAD_DFTD3_B200_TILED") == "1" and default_model:
         return True
+    if c.n > _fused_limit(c.sfx, order) and not default_model:
+        raise NotImplementedError(
+            "erf_count / zero_damping run in the general fused kernel, which takes structures of up to "
+            f"{_fused_limit(c.sfx, 1)} atoms; the tiled large-structure sweeps implement the default "
+            "D3(BJ) model functions (exp_count, rational_damping) only")
     return c.n > _fused_limit(c.sfx, order)
 
 

@@ -217,6 +217,7 @@ class SystemRunner:
         self.buf = buf
         self.cn, self.decn, self.energy = buf[:npad], buf[npad:2 * npad], buf[2 * npad:3 * npad]
         self.grad = buf[3 * npad:6 * npad].view(npad, 3)
+        self.energy_grad = buf[2 * npad:6 * npad]               # contiguous [E | dL/dx]: one message on several GPUs
         self.w, self.dw = buf[6 * npad:14 * npad].view(npad, 8), buf[14 * npad:22 * npad].view(npad, 8)
         self.refcn, self.refc6 = refcn, refc6
         s = _lib.System()
@@ -246,8 +247,11 @@ class SystemRunner:
         # measured on the 50k-atom cluster, 5.75 vs 6.47 ms at jsplit 5 (one GPU) but
         # 1.31 vs 1.14 ms per rank at jsplit 37 (eight GPUs).
         # TAD_DFTD3_B200_FULLROW=1 / =0 forces one or the other.
+        # Round 2, with the plan, the work arrays and the launch sequence cached in a CUDA graph (engine.py) the
+        # fixed costs are gone and the pairs-once sweeps win at every GPU count measured: 3.98 / 2.24 / 1.31 /
+        # 0.89 ms at 1 / 2 / 4 / 8 GPUs against 5.48 / 3.08 / - / 1.09 ms full-row (profiles/r2_summary.md).
         force = os.environ.get("TAD_DFTD3_B200_FULLROW")
-        self.symmetric = self.use_tvec and (force == "0" or (force != "1" and self.jsplit <= 8))
+        self.symmetric = self.use_tvec and force != "1"
         # experiment knob: pairs-once sweeps with a capped j-split (fewer, longer CTAs)
         cap = os.environ.get("TAD_DFTD3_B200_SYM_JSPLIT")
         if cap and self.use_tvec:

@@ -36,7 +36,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_limits(lib):
-    assert lib.d3b200_abi_version() == 1
+    assert lib.d3b200_abi_version() == 2
     assert lib.d3b200_batch_max_atoms_f64(0) >= 512
     assert lib.d3b200_batch_max_atoms_f64(1) >= 256
     assert lib.d3b200_batch_max_atoms_f32(0) >= lib.d3b200_batch_max_atoms_f64(0)
@@ -189,8 +189,12 @@ def test_model_struct_layout_matches_header():
     names = [n for decl in re.findall(r"([^;]+);", body) for n in re.findall(r"(\w+)\s*(?:,|$)", decl.strip())]
     assert names == [f[0] for f in _lib.System._fields_]
     body = re.search(r"typedef struct d3b200_params \{(.*?)\} d3b200_params;", text, flags=re.S).group(1)
-    names = [n for decl in re.findall(r"double ([^;]+);", body) for n in re.split(r"\s*,\s*", decl.strip())]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n for decl in re.findall(r"(?:double|int32_t) ([^;]+);", body) for n in re.split(r"\s*,\s*", decl.strip())]
     assert names == [f[0] for f in _lib.Params._fields_]
+    import ctypes as C
+
+    assert C.sizeof(_lib.Params) == 10 * 8 + 2 * 4
 
 
 def test_staged_host_entry_chunk_schedule(lib):

@@ -614,3 +614,59 @@ def test_dftd3_large_structure_reuses_engine_and_tracks_positions():
         assert_close(e.detach().cpu(), out["energy"], RTOL, ATOL, f"call {step} energy")
         assert_close(g.cpu(), out["grad"], RTOL, ATOL, f"call {step} grad")
     assert len(_engines) <= n0 + 1
+
+
+# ---------------------------------------------------------------------------
+# Non-default model functions behind the reference's callable hooks (disp.py:89-91): erf_count and
+# zero_damping run natively in the general fused kernel; compared with the UNMODIFIED reference driven
+# through the same hooks (tests/golden/reference_models.npz, oracle/make_golden_models.py).
+# ---------------------------------------------------------------------------
+def _model_cases():
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_models.npz"))
+    return sorted({k.split("/")[0] for k in z.files})
+
+
+@pytest.mark.parametrize("case", _model_cases())
+def test_model_function_hooks_match_reference(case):
+    import tad_dftd3_b200 as d3
+    from conftest import Golden
+    from tad_dftd3_b200.damping import rational_damping, zero_damping
+    from tad_dftd3_b200.ncoord import erf_count, exp_count
+
+    c = Golden("reference_models.npz").case(case)
+    dt = torch.double
+    refcn, refc6, rcov, r4r2, rvdw = tables(dt, DEV)
+    numbers = torch.from_numpy(c["numbers"]).to(DEV)
+    pos = torch.from_numpy(c["positions"]).to(DEV).requires_grad_(True)
+    pkeys = [str(k) for k in c["pgrad_keys"]]
+    par = {str(k): torch.tensor(float(v), dtype=dt, device=DEV, requires_grad=str(k) in pkeys)
+           for k, v in zip(c["param_keys"], c["param_vals"])}
+    kw = dict(ref=d3.Reference(cn=refcn, c6=refc6), cutoff=torch.tensor(float(c["cutoff"]), dtype=dt),
+              rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)],
+              counting_function={"exp": exp_count, "erf": erf_count}[str(c["counting"])],
+              damping_function={"rational": rational_damping, "zero": zero_damping}[str(c["damping"])])
+    e = d3.dftd3(numbers, pos, par, **kw)
+    g = torch.from_numpy(c["g"]).to(DEV)
+    grads = torch.autograd.grad((e * g).sum(), [pos] + [par[k] for k in pkeys])
+    assert_close(e.detach().cpu(), c["energy"], RTOL, ATOL, case + " energy")
+    assert_close(grads[0].cpu(), c["grad"], RTOL, ATOL, case + " grad")
+    assert_close(np.asarray([float(x) for x in grads[1:]]), c["pgrad"], 1e-9, 1e-12, case + " parameter gradients")
+    if "hessian" in c:
+        pd = {k: v.detach() for k, v in par.items()}
+        h = torch.func.jacrev(torch.func.jacrev(lambda p: d3.dftd3(numbers, p, pd, **kw).sum(-1)))(pos.detach())
+        assert_close(h.cpu(), c["hessian"], 1e-9, 1e-12, case + " hessian")
+
+
+def test_unknown_callables_still_raise():
+    import tad_dftd3_b200 as d3
+
+    numbers = torch.tensor([8, 1, 1], device=DEV)
+    pos = torch.rand(3, 3, dtype=torch.double, device=DEV) * 3
+    refcn, refc6, *_ = tables(torch.double, DEV)
+    par = {"s6": torch.tensor(1.0), "s8": torch.tensor(1.0)}
+    with pytest.raises(NotImplementedError):
+        d3.dftd3(numbers, pos, par, ref=d3.Reference(cn=refcn, c6=refc6), damping_function=lambda *a: None)
+    with pytest.raises(NotImplementedError):
+        d3.dftd3(numbers, pos, par, ref=d3.Reference(cn=refcn, c6=refc6), counting_function=lambda *a: None)
