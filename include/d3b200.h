@@ -388,6 +388,35 @@ int d3b200_stage_disp2_f64(int nbatch, int natoms, const int64_t* numbers, const
 int d3b200_stage_atm_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
                          const double* c6, const double* rvdw, const d3b200_params* par,
                          double* energy, void* stream);
+/* Vector-Jacobian products of the stage functions (what torch autograd derives for the reference's stage
+ * pipeline, README.rst:238-261 under `autograd.grad`).  Cotangents in, gradients out, first order:
+ *   _stage_cn_bwd       gx[B][N][3]   from gcn[B][N]              (positions; rcov is a constant)
+ *   _stage_weights_bwd  gcn[n]        from gw[n][7]
+ *   _stage_disp2_bwd    gx[B][N][3], gc6[B][N][N] (entries of the dense c6 are independent variables, as in the
+ *                       reference), gpar[B][N][4] = ge_i dE_i/d(s6, s8, a1, a2) (sum over atoms = parameter gradient)
+ *                       from ge[B][N]
+ *   _stage_atm_bwd      gx[B][N][3], gc6[B][N][N] from ge[B][N]; both outputs must be ZERO on entry (fp64 atomics);
+ *                       the ordered term (i; j, k) uses c6[i][j], c6[i][k], c6[j][k] as damping/atm.py:93-97 indexes them */
+int d3b200_stage_cn_bwd_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
+                            const double* rcov, double cutoff, double kcn, const double* gcn, double* gx, void* stream);
+int d3b200_stage_weights_bwd_f64(size_t n, const int64_t* numbers, const double* cn, const double* refcn,
+                                 const double* gw, double* gcn, void* stream);
+int d3b200_stage_disp2_bwd_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
+                               const double* c6, const double* r4r2, const d3b200_params* par, const double* ge,
+                               double* gx, double* gc6, double* gpar, void* stream);
+int d3b200_stage_atm_bwd_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
+                             const double* c6, const double* rvdw, const d3b200_params* par, const double* ge,
+                             double* gx, double* gc6, void* stream);
+int d3b200_stage_cn_bwd_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
+                            const float* rcov, double cutoff, double kcn, const float* gcn, float* gx, void* stream);
+int d3b200_stage_weights_bwd_f32(size_t n, const int64_t* numbers, const float* cn, const float* refcn,
+                                 const float* gw, float* gcn, void* stream);
+int d3b200_stage_disp2_bwd_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
+                               const float* c6, const float* r4r2, const d3b200_params* par, const float* ge,
+                               float* gx, float* gc6, float* gpar, void* stream);
+int d3b200_stage_atm_bwd_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
+                             const float* c6, const float* rvdw, const d3b200_params* par, const float* ge,
+                             float* gx, float* gc6, void* stream);
 int d3b200_stage_cn_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
                         const float* rcov, double cutoff, double kcn, float* cn, void* stream);
 int d3b200_stage_weights_f32(size_t n, const int64_t* numbers, const float* cn, const float* refcn,

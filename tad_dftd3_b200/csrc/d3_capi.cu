@@ -648,6 +648,46 @@ int stage_atm(int nb, int n, const int64_t* z, const B* x, const B* c6, const B*
   return launched("stage_atm_kernel");
 }
 
+template <typename B>
+int stage_cn_bwd(int nb, int n, const int64_t* z, const B* x, const B* rcov, double cutoff, double kcn, const B* gcn,
+                 B* gx, void* st) {
+  if (nb < 0 || n < 0 || !z || !x || !rcov || !gcn || !gx) return fail(D3B200_EINVAL, "bad stage_cn_bwd argument%s");
+  if (!nb || !n) return D3B200_OK;
+  B c = (B)cutoff;
+  d3::stage_cn_bwd_kernel<B><<<dim3((n + 127) / 128, nb), 128, 0, (cudaStream_t)st>>>(n, z, x, rcov, c * c, (B)kcn, gcn, gx);
+  return launched("stage_cn_bwd_kernel");
+}
+template <typename B>
+int stage_weights_bwd(size_t n, const int64_t* z, const B* cn, const B* refcn, const B* gw, B* gcn, void* st) {
+  if (!z || !cn || !refcn || !gw || !gcn) return fail(D3B200_EINVAL, "bad stage_weights_bwd argument%s");
+  if (!n) return D3B200_OK;
+  d3::stage_weights_bwd_kernel<B><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)st>>>(n, z, cn, refcn, gw, gcn);
+  return launched("stage_weights_bwd_kernel");
+}
+template <typename B>
+int stage_disp2_bwd(int nb, int n, const int64_t* z, const B* x, const B* c6, const B* q, const d3b200_params* p,
+                    const B* ge, B* gx, B* gc6, B* gpar, void* st) {
+  if (nb < 0 || n < 0 || !z || !x || !c6 || !q || !p || !ge || !gx || !gc6 || !gpar)
+    return fail(D3B200_EINVAL, "bad stage_disp2_bwd argument%s");
+  if (!nb || !n) return D3B200_OK;
+  B c = (B)p->cutoff;
+  d3::stage_disp2_bwd_kernel<B><<<dim3((n + 127) / 128, nb), 128, 0, (cudaStream_t)st>>>(
+      n, z, x, c6, q, (B)p->s6, (B)p->s8, (B)p->a1, (B)p->a2, c * c, ge, gx, gc6, gpar);
+  return launched("stage_disp2_bwd_kernel");
+}
+template <typename B>
+int stage_atm_bwd(int nb, int n, const int64_t* z, const B* x, const B* c6, const B* rvdw, const d3b200_params* p,
+                  const B* ge, B* gx, B* gc6, void* st) {
+  if (nb < 0 || n < 0 || !z || !x || !c6 || !rvdw || !p || !ge || !gx || !gc6)
+    return fail(D3B200_EINVAL, "bad stage_atm_bwd argument%s");
+  if (!nb || !n) return D3B200_OK;
+  if (nb > 65535 || n > 65535) return fail(D3B200_ESIZE, "stage_atm_bwd: batch or structure too large%s");
+  B c = (B)p->cutoff;
+  d3::stage_atm_bwd_kernel<B><<<dim3((n + 63) / 64, n, nb), 64, 0, (cudaStream_t)st>>>(
+      n, z, x, c6, rvdw, c * c, (B)p->s9, (B)p->rs9, (B)((p->alp + 2.0) / 3.0), ge, gx, gc6);
+  return launched("stage_atm_bwd_kernel");
+}
+
 }  // namespace
 
 extern "C" {
@@ -666,7 +706,18 @@ extern "C" {
   int d3b200_stage_disp2_##SFX(int nb, int n, const int64_t* z, const T* x, const T* c6, const T* q,         \
                                const d3b200_params* p, T* e, void* st) { return stage_disp2<T>(nb, n, z, x, c6, q, p, e, st); } \
   int d3b200_stage_atm_##SFX(int nb, int n, const int64_t* z, const T* x, const T* c6, const T* rvdw,        \
-                             const d3b200_params* p, T* e, void* st) { return stage_atm<T>(nb, n, z, x, c6, rvdw, p, e, st); }
+                             const d3b200_params* p, T* e, void* st) { return stage_atm<T>(nb, n, z, x, c6, rvdw, p, e, st); } \
+  int d3b200_stage_cn_bwd_##SFX(int nb, int n, const int64_t* z, const T* x, const T* rcov, double cutoff,   \
+                                double kcn, const T* gcn, T* gx, void* st) {                                 \
+    return stage_cn_bwd<T>(nb, n, z, x, rcov, cutoff, kcn, gcn, gx, st); }                                    \
+  int d3b200_stage_weights_bwd_##SFX(size_t n, const int64_t* z, const T* cn, const T* refcn, const T* gw,   \
+                                     T* gcn, void* st) { return stage_weights_bwd<T>(n, z, cn, refcn, gw, gcn, st); } \
+  int d3b200_stage_disp2_bwd_##SFX(int nb, int n, const int64_t* z, const T* x, const T* c6, const T* q,     \
+                                   const d3b200_params* p, const T* ge, T* gx, T* gc6, T* gpar, void* st) {  \
+    return stage_disp2_bwd<T>(nb, n, z, x, c6, q, p, ge, gx, gc6, gpar, st); }                                \
+  int d3b200_stage_atm_bwd_##SFX(int nb, int n, const int64_t* z, const T* x, const T* c6, const T* rvdw,    \
+                                 const d3b200_params* p, const T* ge, T* gx, T* gc6, void* st) {             \
+    return stage_atm_bwd<T>(nb, n, z, x, c6, rvdw, p, ge, gx, gc6, st); }
 D3_STAGE_API(f64, double)
 D3_STAGE_API(f32, float)
 #undef D3_STAGE_API

@@ -42,8 +42,8 @@ def _no_grad(*tensors):
     for t in tensors:
         if isinstance(t, Tensor) and t.requires_grad and torch.is_grad_enabled():
             raise NotImplementedError(
-                "the stage-level functions of tad_dftd3_b200 are forward only; "
-                "use dftd3() for derivatives (or wrap the call in torch.no_grad())"
+                "this argument of the stage-level function is treated as a constant (derivatives exist for "
+                "positions, cn, weights, c6 and s6, s8, a1, a2); use dftd3() or wrap the call in torch.no_grad()"
             )
 
 
@@ -72,13 +72,64 @@ def _check_z(numbers: Tensor):
     _check_numbers(numbers)
 
 
+def _wants_grad(*tensors) -> bool:
+    f = torch._C._functorch
+    return any(isinstance(t, Tensor) and ((t.requires_grad and torch.is_grad_enabled()) or f.is_gradtrackingtensor(t))
+               for t in tensors)
+
+
+_SECOND_ORDER = ("the stage-level functions provide first derivatives (vector-Jacobian products on the CUDA "
+                 "kernels); for second derivatives use dftd3(), whose backward is differentiable again")
+
+
+class _CnD3(torch.autograd.Function):
+    """cn_d3 with its VJP with respect to the positions (`d3b200_stage_cn_bwd_*`)."""
+
+    @staticmethod
+    def forward(ctx, numbers, positions, rcov, cutoff, kcn):
+        ctx.save_for_backward(numbers, positions, rcov)
+        ctx.cutoff, ctx.kcn = cutoff, kcn
+        return _cn_forward(numbers, positions, rcov, cutoff, kcn)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gcn):
+        numbers, positions, rcov = ctx.saved_tensors
+        dt, dev = positions.dtype, positions.device
+        n = numbers.shape[-1]
+        z = _z(numbers).reshape(-1, n)
+        x = positions.detach().reshape(-1, n, 3).contiguous()
+        rc = rcov.detach().to(dt).reshape(-1, n).contiguous()
+        g = gcn.detach().to(dt).expand(numbers.shape).reshape(-1, n).contiguous()
+        gx = torch.empty_like(x)
+        fn = getattr(_lib.lib(), f"d3b200_stage_cn_bwd_{_sfx(dt)}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(rc), ctx.cutoff, ctx.kcn, _p(g), _p(gx), _stream(dev)))
+        return None, gx.reshape(positions.shape), None, None, None
+
+
+def _cn_forward(numbers, positions, rcov, cutoff, kcn):
+    dt, dev = positions.dtype, positions.device
+    n = numbers.shape[-1]
+    z = _z(numbers).reshape(-1, n)
+    x = positions.detach().reshape(-1, n, 3).contiguous()
+    rc = rcov.detach().to(dt).reshape(-1, n).contiguous()
+    out = torch.empty(z.shape, dtype=dt, device=dev)
+    fn = getattr(_lib.lib(), f"d3b200_stage_cn_{_sfx(dt)}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(rc), cutoff, kcn, _p(out), _stream(dev)))
+    return out.reshape(numbers.shape)
+
+
 def cn_d3(numbers, positions, *, counting_function=None, rcov=None, cutoff=None, **kwargs):
+    """D3 coordination number (tad-mctc `cn_d3`, call site disp.py:150-152); differentiable with respect to
+    the positions (first order) on the CUDA kernels."""
     from .ncoord import exp_count
 
     if counting_function is not None and counting_function is not exp_count:
-        raise NotImplementedError("only the default exp_count counting function is implemented")
+        raise NotImplementedError("the stage-level cn_d3 implements exp_count; erf_count is available through dftd3()")
     _cuda(positions, "positions")
-    _no_grad(positions, rcov)
+    _no_grad(rcov)
     dt, dev = positions.dtype, positions.device
     if rcov is None:
         rcov = data.COV_D3(dt, dev)[numbers]
@@ -88,27 +139,37 @@ def cn_d3(numbers, positions, *, counting_function=None, rcov=None, cutoff=None,
         raise ValueError(
             f"Shape of positions ({tuple(positions.shape[:-1])}) is not consistent with atomic numbers ({tuple(numbers.shape)})."
         )
-    n = numbers.shape[-1]
-    z = _z(numbers).reshape(-1, n)
-    x = positions.detach().reshape(-1, n, 3).contiguous()
-    rc = rcov.detach().to(dt).reshape(-1, n).contiguous()
-    out = torch.empty(z.shape, dtype=dt, device=dev)
-    fn = getattr(_lib.lib(), f"d3b200_stage_cn_{_sfx(dt)}")
-    with torch.cuda.device(dev):
-        _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(rc), _scalar(cutoff, defaults.D3_CN_CUTOFF),
-                      float(kwargs.get("kcn", defaults.D3_KCN)), _p(out), _stream(dev)))
-    return out.reshape(numbers.shape)
+    cut, kcn = _scalar(cutoff, defaults.D3_CN_CUTOFF), float(kwargs.get("kcn", defaults.D3_KCN))
+    if _wants_grad(positions):
+        return _CnD3.apply(numbers, positions, rcov, cut, kcn)
+    return _cn_forward(numbers, positions, rcov, cut, kcn)
 
 
-def weight_references(numbers, cn, reference, weighting_function=None, **kwargs):
-    from .model import gaussian_weight
+class _Weights(torch.autograd.Function):
+    """weight_references with its VJP with respect to the coordination numbers (`d3b200_stage_weights_bwd_*`)."""
 
-    if weighting_function is not None and weighting_function is not gaussian_weight or kwargs:
-        raise NotImplementedError("only the default gaussian_weight (factor 4) is implemented")
-    _cuda(cn, "cn")
-    _no_grad(cn)
+    @staticmethod
+    def forward(ctx, numbers, cn, refcn):
+        ctx.save_for_backward(numbers, cn, refcn)
+        return _weights_forward(numbers, cn, refcn)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gw):
+        numbers, cn, refcn = ctx.saved_tensors
+        dt, dev = cn.dtype, cn.device
+        z = _z(numbers).reshape(-1)
+        c = cn.detach().reshape(-1).contiguous()
+        g = gw.detach().to(dt).expand(*numbers.shape, 7).reshape(-1, 7).contiguous()
+        out = torch.empty_like(c)
+        fn = getattr(_lib.lib(), f"d3b200_stage_weights_bwd_{_sfx(dt)}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(C.c_size_t(z.shape[0]), _p(z), _p(c), _p(refcn), _p(g), _p(out), _stream(dev)))
+        return None, out.reshape(cn.shape), None
+
+
+def _weights_forward(numbers, cn, refcn):
     dt, dev = cn.dtype, cn.device
-    refcn, _, _ = reference._prepared(dev, dt)
     z = _z(numbers).reshape(-1)
     c = cn.detach().reshape(-1).contiguous()
     out = torch.empty(z.shape[0], 7, dtype=dt, device=dev)
@@ -116,6 +177,19 @@ def weight_references(numbers, cn, reference, weighting_function=None, **kwargs)
     with torch.cuda.device(dev):
         _lib.check(fn(C.c_size_t(z.shape[0]), _p(z), _p(c), _p(refcn), _p(out), _stream(dev)))
     return out.reshape(*numbers.shape, 7)
+
+
+def weight_references(numbers, cn, reference, weighting_function=None, **kwargs):
+    """Gaussian reference weights (model/weights.py:78-176); differentiable with respect to `cn` (first order)."""
+    from .model import gaussian_weight
+
+    if weighting_function is not None and weighting_function is not gaussian_weight or kwargs:
+        raise NotImplementedError("only the default gaussian_weight (factor 4) is implemented")
+    _cuda(cn, "cn")
+    refcn, _, _ = reference._prepared(cn.device, cn.dtype)
+    if _wants_grad(cn):
+        return _Weights.apply(numbers, cn, refcn)
+    return _weights_forward(numbers, cn, refcn)
 
 
 def _c6_launch(name, numbers, a, b, refc6, out_shape):
@@ -246,15 +320,45 @@ def _prep(numbers, positions, c6):
     return dt, dev, n, z, x, c
 
 
-def dispersion2(numbers, positions, param, c6, r4r2, damping_function=None, cutoff=None, **kwargs):
-    from .damping import rational_damping
+_PKEYS2 = (("s6", defaults.S6), ("s8", defaults.S8), ("a1", defaults.A1), ("a2", defaults.A2))
 
-    if damping_function is not None and damping_function is not rational_damping or kwargs:
-        raise NotImplementedError("only the default rational (Becke-Johnson) damping is implemented")
-    _no_grad(positions, c6, *param.values())
+
+class _Disp2(torch.autograd.Function):
+    """dispersion2 with its VJP with respect to positions, the dense c6 and (s6, s8, a1, a2)
+    (`d3b200_stage_disp2_bwd_*`)."""
+
+    @staticmethod
+    def forward(ctx, numbers, positions, c6, r4r2, pvec, cutoff):
+        ctx.save_for_backward(numbers, positions, c6, r4r2, pvec)
+        ctx.cutoff = cutoff
+        return _disp2_forward(numbers, positions, c6, r4r2, pvec.detach().tolist(), cutoff)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, ge):
+        numbers, positions, c6, r4r2, pvec = ctx.saved_tensors
+        dt, dev, n, z, x, c = _prep(numbers, positions, c6)
+        q = r4r2.detach().to(dt).reshape(-1, n).contiguous()
+        par = _lib.Params()
+        par.s6, par.s8, par.a1, par.a2 = pvec.detach().tolist()
+        par.cutoff = ctx.cutoff
+        g = ge.detach().to(dt).expand(numbers.shape).reshape(-1, n).contiguous()
+        gx, gc6 = torch.empty_like(x), torch.empty_like(c)
+        gpar = torch.empty(z.shape[0], n, 4, dtype=dt, device=dev)
+        fn = getattr(_lib.lib(), f"d3b200_stage_disp2_bwd_{_sfx(dt)}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(c), _p(q), C.byref(par), _p(g), _p(gx), _p(gc6), _p(gpar),
+                          _stream(dev)))
+        gp = gpar.sum((0, 1)).to(device=pvec.device, dtype=pvec.dtype) if ctx.needs_input_grad[4] else None
+        return None, gx.reshape(positions.shape), gc6.reshape(c6.shape).to(c6.dtype), None, gp, None
+
+
+def _disp2_forward(numbers, positions, c6, r4r2, pvals, cutoff):
     dt, dev, n, z, x, c = _prep(numbers, positions, c6)
     q = r4r2.detach().to(dt).reshape(-1, n).contiguous()
-    par = _params(param, cutoff, dt)
+    par = _lib.Params()
+    par.s6, par.s8, par.a1, par.a2 = pvals
+    par.cutoff = cutoff
     out = torch.empty(z.shape, dtype=dt, device=dev)
     fn = getattr(_lib.lib(), f"d3b200_stage_disp2_{_sfx(dt)}")
     with torch.cuda.device(dev):
@@ -262,21 +366,81 @@ def dispersion2(numbers, positions, param, c6, r4r2, damping_function=None, cuto
     return out.reshape(numbers.shape)
 
 
-def dispersion_atm(numbers, positions, c6, rvdw, cutoff, s9=None, rs9=None, alp=None):
-    _no_grad(positions, c6)
+def dispersion2(numbers, positions, param, c6, r4r2, damping_function=None, cutoff=None, **kwargs):
+    """Becke-Johnson two-body energy from a dense c6 (disp.py:245-302); differentiable (first order) with respect
+    to positions, c6 and the parameters s6, s8, a1, a2."""
+    from .damping import rational_damping
+
+    if damping_function is not None and damping_function is not rational_damping or kwargs:
+        raise NotImplementedError("the stage-level dispersion2 implements rational_damping; zero_damping is available through dftd3()")
+    _no_grad(r4r2)
+    _cuda(positions, "positions")
+    cut = _scalar(cutoff, defaults.D3_DISP_CUTOFF)
+    vals = [param.get(k, d) for k, d in _PKEYS2]
+    if _wants_grad(positions, c6, *vals):
+        dt = positions.dtype
+        live = [v for v in vals if isinstance(v, Tensor) and v.requires_grad]
+        pdev = live[0].device if live else torch.device("cpu")
+        pvec = torch.stack([(v.to(device=pdev, dtype=dt) if isinstance(v, Tensor)
+                             else torch.tensor(float(v), dtype=dt, device=pdev)).reshape(()) for v in vals])
+        return _Disp2.apply(numbers, positions, c6, r4r2, pvec, cut)
+    return _disp2_forward(numbers, positions, c6, r4r2, [_scalar(v) for v in vals], cut)
+
+
+class _Atm(torch.autograd.Function):
+    """dispersion_atm with its VJP with respect to positions and the dense c6 (`d3b200_stage_atm_bwd_*`)."""
+
+    @staticmethod
+    def forward(ctx, numbers, positions, c6, rvdw, scalars):
+        ctx.save_for_backward(numbers, positions, c6, rvdw)
+        ctx.scalars = scalars
+        return _atm_forward(numbers, positions, c6, rvdw, scalars)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, ge):
+        numbers, positions, c6, rvdw = ctx.saved_tensors
+        dt, dev, n, z, x, c = _prep(numbers, positions, c6)
+        rv = rvdw.detach().to(dt).reshape(-1, n, n).contiguous()
+        par = _atm_params(ctx.scalars)
+        g = ge.detach().to(dt).expand(numbers.shape).reshape(-1, n).contiguous()
+        gx, gc6 = torch.zeros_like(x), torch.zeros_like(c)
+        fn = getattr(_lib.lib(), f"d3b200_stage_atm_bwd_{_sfx(dt)}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(c), _p(rv), C.byref(par), _p(g), _p(gx), _p(gc6), _stream(dev)))
+        return None, gx.reshape(positions.shape), gc6.reshape(c6.shape).to(c6.dtype), None, None
+
+
+def _atm_params(scalars) -> _lib.Params:
+    par = _lib.Params()
+    par.s9, par.alp, par.rs9, par.cutoff = scalars
+    return par
+
+
+def _atm_forward(numbers, positions, c6, rvdw, scalars):
     dt, dev, n, z, x, c = _prep(numbers, positions, c6)
     rv = rvdw.detach().to(dt).reshape(-1, n, n).contiguous()
-    par = _lib.Params()
-    par.s9 = _scalar(s9, defaults.S9)
-    par.alp = _scalar(alp, defaults.ALP)
-    # the reference's default rs9 tensor is float32(4/3) (damping/atm.py:50)
-    par.rs9 = float(torch.tensor(defaults.RS9)) if rs9 is None else float(rs9.detach().to(dt))
-    par.cutoff = _scalar(cutoff, defaults.D3_DISP_CUTOFF)
+    par = _atm_params(scalars)
     out = torch.empty(z.shape, dtype=dt, device=dev)
     fn = getattr(_lib.lib(), f"d3b200_stage_atm_{_sfx(dt)}")
     with torch.cuda.device(dev):
         _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(c), _p(rv), C.byref(par), _p(out), _stream(dev)))
     return out.reshape(numbers.shape)
+
+
+def dispersion_atm(numbers, positions, c6, rvdw, cutoff, s9=None, rs9=None, alp=None):
+    """Axilrod-Teller-Muto energy from dense c6 / rvdw (damping/atm.py:43-155); differentiable (first order) with
+    respect to positions and c6."""
+    _no_grad(rvdw, s9, rs9, alp)
+    _cuda(positions, "positions")
+    dt = positions.dtype
+    # the reference's default rs9 tensor is float32(4/3) (damping/atm.py:50)
+    scalars = (_scalar(s9, defaults.S9), _scalar(alp, defaults.ALP),
+               float(torch.tensor(defaults.RS9)) if rs9 is None else float(rs9.detach().to(dt)),
+               _scalar(cutoff, defaults.D3_DISP_CUTOFF))
+    if _wants_grad(positions, c6):
+        return _Atm.apply(numbers, positions, c6, rvdw, scalars)
+    return _atm_forward(numbers, positions, c6, rvdw, scalars)
 
 
 def dispersion3(numbers, positions, param, c6, rvdw, cutoff, rs9=None):

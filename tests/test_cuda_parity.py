@@ -431,16 +431,79 @@ def test_stage_pins_from_reference_tests(pins, name):
     assert_close(e.cpu(), c["disp2"], 1e-9 if loose else 1e-13, 2e-11 if loose else 1e-16, name + " disp2")
 
 
-def test_stage_functions_are_forward_only():
+def test_stage_pipeline_gradient_matches_reference(runs):
+    """README.rst:238-261 under autograd: cn_d3 -> weight_references -> atomic_c6 -> dispersion composed from the
+    stage functions, differentiated by torch through their CUDA vector-Jacobian products, gives the gradient
+    (and the parameter gradients) that the unmodified reference's dftd3() gives."""
     import tad_dftd3_b200 as d3
 
-    numbers = torch.tensor([8, 1, 1], device=DEV)
-    pos = torch.tensor([[0.0, 0.0, -0.7], [1.4, 0.0, 0.4], [-1.4, 0.0, 0.4]], device=DEV, dtype=torch.double,
-                       requires_grad=True)
-    with pytest.raises(NotImplementedError):
-        d3.ncoord.cn_d3(numbers, pos)
+    checked = 0
+    for case in ("c2_atm_f64", "heavy12_atm_f64", "c2_f64", "mols6_atm_cut12_f64", "c1_f64", "c2_atm_cut8_f64"):
+        if case not in runs.cases:
+            continue
+        c = runs.case(case)
+        dtype, numbers, positions, g, param, cutoff = case_inputs(c, DEV)
+        refcn, refc6, rcov, r4r2, rvdw = tables(dtype, DEV)
+        ref = d3.Reference(cn=refcn, c6=refc6)
+        pos = positions.clone().requires_grad_(True)
+        want_p = "pgrad" in c
+        par = {k: v.clone().requires_grad_(want_p and k in ("s6", "s8", "a1", "a2")) for k, v in param.items()}
+        cn = d3.ncoord.cn_d3(numbers, pos, rcov=rcov[numbers])
+        w = d3.model.weight_references(numbers, cn, ref)
+        c6 = d3.model.atomic_c6(numbers, w, ref)
+        e = d3.disp.dispersion(numbers, pos, par, c6, rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)],
+                               r4r2=r4r2[numbers], cutoff=torch.tensor(cutoff, dtype=dtype, device=DEV))
+        assert_close(e.detach().cpu(), c["energy"], RTOL, ATOL, case + " stage energy")
+        wrt = [pos] + ([par[k] for k in ("s6", "s8", "a1", "a2") if k in par] if want_p else [])
+        grads = torch.autograd.grad((e * g).sum(), wrt)
+        assert_close(grads[0].cpu(), c["grad"], RTOL, ATOL, case + " stage-pipeline gradient")
+        if want_p:
+            assert_close(np.asarray([float(v) for v in grads[1:]]), c["pgrad"], 1e-9, 1e-12, case + " stage pgrad")
+        checked += 1
+    assert checked >= 3
+
+
+def test_stage_vjps_gradcheck():
+    """Each stage VJP on its own against finite differences (fp64), including the entries of the dense c6."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+
+    dt = torch.double
+    numbers, positions = syn.water_cluster(3, seed=2)
+    numbers = torch.cat([numbers, torch.tensor([0])]).to(DEV)                       # one padding atom
+    positions = torch.cat([positions, torch.zeros(1, 3, dtype=dt)]).to(DEV)
+    refcn, refc6, rcov, r4r2, rvdw = tables(dt, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    gc = dict(eps=1e-6, atol=1e-8, rtol=1e-6, nondet_tol=1e-12)
+    x = positions.clone().requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda p: d3.ncoord.cn_d3(numbers, p), (x,), **gc)
+    cn = d3.ncoord.cn_d3(numbers, positions).clone().requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda c: d3.model.weight_references(numbers, c, ref), (cn,), **gc)
     with torch.no_grad():
-        assert d3.ncoord.cn_d3(numbers, pos).shape == (3,)
+        c6 = d3.model.atomic_c6(numbers, d3.model.weight_references(numbers, cn.detach(), ref), ref)
+    c6 = (c6 * (1.0 + 0.1 * torch.rand_like(c6))).requires_grad_(True)                 # unsymmetric: entries are independent
+    par = {k: torch.tensor(v, dtype=dt, device=DEV, requires_grad=True)
+           for k, v in (("s6", 1.0), ("s8", 0.79), ("a1", 0.49), ("a2", 5.7))}
+    q = r4r2[numbers]
+
+    def e2(p, c, s6, s8, a1, a2):
+        return d3.disp.dispersion2(numbers, p, {"s6": s6, "s8": s8, "a1": a1, "a2": a2}, c, q, None, None)
+
+    assert torch.autograd.gradcheck(e2, (x, c6, *par.values()), **gc)
+    rv = rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)]
+
+    def e3(p, c):
+        return d3.damping.dispersion_atm(numbers, p, c, rv, torch.tensor(7.0, dtype=dt), torch.tensor(1.0, dtype=dt))
+
+    assert torch.autograd.gradcheck(e3, (x, c6), **gc)
+    # second order is refused with a pointer to dftd3()
+    e = d3.ncoord.cn_d3(numbers, x).sum()
+    (g1,) = torch.autograd.grad(e, x, create_graph=True)
+    with pytest.raises(RuntimeError):
+        torch.autograd.grad(g1.sum(), x)
+    # constants stay constants: rcov / rvdw with requires_grad are refused
+    with pytest.raises(NotImplementedError):
+        d3.ncoord.cn_d3(numbers, positions, rcov=rcov[numbers].clone().requires_grad_(True))
 
 
 def test_atomic_c6_is_differentiable_like_the_reference_op(runs):
