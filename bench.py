@@ -506,7 +506,7 @@ def run_c3(args, cx, clocks_out):
         # ---- end-to-end through the public host-buffer API from pinned host buffers
         e_h = torch.empty(numbers.shape, dtype=dt).pin_memory()
         g_h = torch.empty(*numbers.shape, 3, dtype=dt).pin_memory()
-        host_chunk = max(0, args.e2e_chunk)
+        host_chunk = args.e2e_chunk
         n_e2e_launch = 1 if host_chunk == 0 else d3.HostPipeline.chunks(numbers.shape[0], host_chunk)
 
         def step_e2e():
@@ -568,7 +568,9 @@ def run_c3(args, cx, clocks_out):
                    f"(d3b200_batch_vjp_host_{args.dtype}); "
                    + ("one launch of the fused kernel reading and writing host memory directly (zero-copy, "
                       "coalesced), " if host_chunk == 0 else
-                      f"{n_e2e_launch} chunks pipelined H2D / kernel / D2H, ")
+                      (f"{n_e2e_launch} chunks pipelined H2D / kernel / D2H, " if host_chunk > 0 else
+                       f"hybrid: inputs staged by the copy engine in {n_e2e_launch} chunks, kernels write the results "
+                       "directly into host memory (no D2H copy), "))
                    + "synchronised every step; wall clock per step, median over steps, max over ranks; bytes summed over ranks",
         },
         "gpu_launches": n_launch,
@@ -911,7 +913,7 @@ def main():
                     help="c3 under torchrun: strong = the fixed batch split over the ranks (default); weak = one batch per rank")
     ap.add_argument("--e2e-chunk", type=int, default=0,
                     help="c3 end-to-end: 0 = zero-copy form of dftd3_host (default); > 0 = staged form with this many "
-                         "structures per pipeline chunk")
+                         "structures per pipeline chunk; < 0 = hybrid form (inputs staged, outputs written directly)")
     ap.add_argument("--cutoff", type=float, default=25.0, help="c5a: dispersion/triple cutoff in Bohr")
     ap.add_argument("--workload", default="all", choices=["all", "c3", "c4", "c5a", "c5b"],
                     help="all: c3 line with c4 and c5a sub-records (default); c3 / c4 / c5a / c5b: that workload alone")

@@ -173,7 +173,7 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
  * live in HOST memory (page-locked for the copies to be asynchronous), as a
  * caller of the reference's CPU `dftd3()` + autograd holds them.
  *
- * Two forms.  (1) Zero-copy, taken when chunk <= 0, par->s9 == 0 and every host
+ * Three forms.  (1) Zero-copy, taken when chunk == 0, par->s9 == 0 and every host
  * buffer is page-locked and mapped (cudaHostAlloc / cudaHostRegister under UVA):
  * ONE launch of the fused kernel on `stream` reads the inputs and writes the
  * results directly in host memory; all its global accesses are coalesced, and
@@ -186,6 +186,9 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
  * D2H of chunk k-1 run concurrently.  Work is ordered after everything already
  * queued on `stream`, and `stream` waits for the last D2H: synchronise `stream`
  * before reading h_energy / h_grad.  Nothing is synchronised inside.
+ * (3) Hybrid, chunk < 0 with page-locked mapped OUTPUT buffers (two-body + CN): the inputs are staged chunk by
+ * chunk (|chunk| structures) with the copy engine while the kernels of the earlier chunks run and write their
+ * results straight into host memory (posted PCIe writes of coalesced blocks): no device->host copy exists.
  *
  * A pipe owns 4 CUDA streams and a set of events on the current device; it is
  * the only object of this ABI that is created and destroyed, and one pipe must
@@ -197,8 +200,8 @@ int d3b200_batch_hvp_f32(int nbatch, int natoms, const int64_t* numbers,
  *   h_energy  : `[nbatch][natoms]` or NULL;  h_grad: `[nbatch][natoms][3]`
  *   workspace : DEVICE staging, `d3b200_batch_host_workspace_bytes_*` bytes
  *   chunk     : > 0: staged form with this many structures per chunk;
- *               <= 0: zero-copy when possible, else staged with about one wave of
- *               CTAs per chunk */
+ *               == 0: zero-copy when possible, else staged with about one wave of CTAs per chunk;
+ *               < 0: hybrid form with |chunk| structures per chunk when possible, else staged */
 typedef struct d3b200_pipe d3b200_pipe;
 int d3b200_pipe_create(d3b200_pipe** pipe);
 int d3b200_pipe_destroy(d3b200_pipe* pipe);

@@ -51,7 +51,7 @@ struct AtmArgs3 {
   AtmArgs2<S> a;
   int* list;       // [gridDim.x][natoms]          neighbour indices of the CTA's current centre
   S* rec;          // [gridDim.x][natoms][kAtm3Rec] neighbour records
-  int* counter;    // zero before the launch
+  int* counter;    // zero before the launch; counter[1] = largest neighbour count of any atom (system_atm_maxn_kernel)
   int tile_stride; // the launch owns the 32-atom sub-tiles row_begin/32 + k * tile_stride below row_end
   int parts;       // a centre is split into `parts` work units (every parts-th tile of its list): keeps
                    // the persistent CTAs busy when a launch owns few centres (several GPUs)
@@ -109,6 +109,38 @@ __device__ __forceinline__ S pow16_3_fast(S x) {
   return c8 * c8;
 }
 
+// Largest number of neighbours within the cutoff of any atom: sizes the per-CTA slots of the neighbour scratch
+// of `system_atm3_kernel` (slots of `natoms` entries, 1 MB apart, alias in the L2 sets and were written back
+// to DRAM at 50x the algorithmic bytes, profiles/r1h_system_atm3_raw.csv).  One warp per 32-atom sub-tile,
+// lane = atom, partner sub-tiles culled by their boxes; the result is an atomicMax into *out (zero before).
+template <typename S>
+__global__ void __launch_bounds__(128) system_atm_maxn_kernel(SysArgs<S> A, const signed char* eidx, int* out) {
+  const int lane = threadIdx.x & 31;
+  const int sub = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nsub = A.natoms / kSysSub;
+  if (sub >= nsub) return;
+  const int i = sub * kSysSub + lane;
+  const Atom4<S> ai = A.atoms[i];
+  const bool real_i = eidx[i] >= 0;
+  const S* ibox = A.box + (size_t)sub * 6;
+  int n = 0;
+  for (int js = 0; js < nsub; ++js) {
+    if (box_dist2(ibox, A.box + (size_t)js * 6) > A.cutoff2) continue;     // warp-uniform
+    const int j = js * kSysSub + lane;
+    const Atom4<S> aj = A.atoms[j];
+    const bool real_j = eidx[j] >= 0;
+    for (int l = 0; l < 32; ++l) {
+      const S x = __shfl_sync(0xffffffffu, aj.x, l), y = __shfl_sync(0xffffffffu, aj.y, l), z = __shfl_sync(0xffffffffu, aj.z, l);
+      const bool rj = __shfl_sync(0xffffffffu, (int)real_j, l) != 0;
+      const S dx = ai.x - x, dy = ai.y - y, dz = ai.z - z;
+      n += (rj && (js * kSysSub + l) != i && dx * dx + dy * dy + dz * dz <= A.cutoff2) ? 1 : 0;
+    }
+  }
+  n = real_i ? n : 0;
+  n = __reduce_max_sync(0xffffffffu, n);
+  if (lane == 0 && n > 0) atomicMax(out, n);
+}
+
 // record slots
 enum { kRx = 0, kRy, kRz, kRidx, kRh, kRr2, kRinv, kRci, kRcn, kRvdw, kRg, kRe };
 
@@ -135,8 +167,10 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
   const int tstride = Q.tile_stride > 0 ? Q.tile_stride : 1;
   const int nsub_own = ((A.row_end - A.row_begin) / kSysSub + tstride - 1) / tstride;
   const int nrows = nsub_own * kSysSub;
-  int* list = Q.list + (size_t)blockIdx.x * natoms;
-  S* rec = Q.rec + (size_t)blockIdx.x * natoms * kAtm3Rec;
+  // per-CTA slots sized by the largest neighbour count (rounded up to whole tiles), packed back to back
+  const int slot = min(natoms, ((Q.counter[1] + TK - 1) / TK) * TK);
+  int* list = Q.list + (size_t)blockIdx.x * slot;
+  S* rec = Q.rec + (size_t)blockIdx.x * slot * kAtm3Rec;
   S* redw = red + wid * 7 * kAtm3RedStride;
   const S* __restrict__ tvec = P.tvec;
   const unsigned tdoff = (unsigned)natoms * E * 8;  // Td vectors sit right behind the T vectors

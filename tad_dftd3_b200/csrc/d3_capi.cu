@@ -165,11 +165,14 @@ int energy_impl(int nbatch, int natoms, const int64_t* numbers, const B* positio
 template <typename B>
 int vjp_impl(int nbatch, int natoms, const int64_t* numbers, const B* positions,
              const typename ModelOf<B>::type* model, const d3b200_params* par, const B* g,
-             B* energy, B* grad, B* pgrad, void* workspace, size_t wbytes, void* stream, int host_io = 0) {
+             B* energy, B* grad, B* pgrad, void* workspace, size_t wbytes, void* stream, int host_io = 0,
+             const int* ready = nullptr, int ready_per = 1) {
   d3::MolArgs<B> a;
   int rc = fill_common<B, B>(a, nbatch, natoms, numbers, positions, model, par, nullptr);
   if (rc) return rc;
   a.host_io = host_io;
+  a.ready = ready;
+  a.ready_per = ready_per;
   if (!grad) return fail(D3B200_EINVAL, "null gradient output%s");  // g == NULL: unit cotangent
   if (nbatch == 0 || natoms == 0) return D3B200_OK;
   a.g = g;
@@ -228,6 +231,9 @@ struct d3b200_pipe {
   cudaStream_t in, out, comp[2];
   cudaEvent_t start, done, ev_in[kPipeMaxChunks], ev_k[kPipeMaxChunks];
   int device;
+  int* h_one;   // page-locked constant 1: the streamed form raises its per-chunk flags with 4-byte H2D COPIES
+                // (a small cudaMemsetAsync may be a kernel, which could not be scheduled next to the resident
+                // CTAs that are waiting for exactly that flag)
 };
 
 namespace {
@@ -256,7 +262,8 @@ size_t host_workspace_bytes(int nbatch, int natoms, int with_g, int atm) {
 // fused kernel, 148 SMs x 4), quarter- and half-size chunks at both ends so that the un-overlapped
 // first H2D copy and last D2H copy are short; at most kPipeMaxChunks chunks.  bounds[0..n], returns n.
 int pipe_schedule(int nbatch, int chunk, int* bounds) {
-  if (chunk <= 0) chunk = 592;
+  if (chunk < 0) chunk = -chunk;
+  if (chunk == 0) chunk = 592;
   if ((nbatch + chunk - 1) / chunk + 4 > kPipeMaxChunks) chunk = (nbatch + kPipeMaxChunks - 5) / (kPipeMaxChunks - 4);
   int nchunk = 0;
   const int q = chunk / 4, h = chunk / 2;
@@ -287,10 +294,20 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
   // fused kernel on the host pointers.  Every CTA reads its structure over PCIe at its start and writes
   // its results at its end -- all accesses of the kernel are coalesced for that purpose -- so the transfers
   // of the 592 resident CTAs overlap the arithmetic of the others without any staging or chunking.
-  if (chunk <= 0 && !atm && v2_fits<B>(natoms) && device_visible(h_numbers) && device_visible(h_positions) &&
-      device_visible(h_grad) && (!h_energy || device_visible(h_energy)) && (!h_g || device_visible(h_g)))
+  const bool out_mapped = device_visible(h_grad) && (!h_energy || device_visible(h_energy));
+  if (chunk == 0 && !atm && v2_fits<B>(natoms) && default_model(par) && device_visible(h_numbers) &&
+      device_visible(h_positions) && out_mapped && (!h_g || device_visible(h_g)))
     return vjp_impl<B>(nbatch, natoms, h_numbers, h_positions, model, par, h_g, h_energy, h_grad, nullptr,
                        nullptr, 0, stream, 1);
+  // Hybrid form (chunk < 0: |chunk| structures per chunk; outputs page-locked and mapped): the inputs are staged
+  // with the copy engine, chunk by chunk, while the kernels of the previous chunks run and WRITE THEIR RESULTS
+  // DIRECTLY INTO HOST MEMORY (posted PCIe writes, coalesced blocks) -- no device->host copies at all.
+  const bool hybrid = chunk < 0 && !atm && v2_fits<B>(natoms) && default_model(par) && out_mapped;
+  if (chunk < 0) chunk = -chunk;
+  // Streamed form (chunk in -15..-2: 2^|chunk| structures per chunk; outputs mapped): ONE launch of the fused kernel on
+  // `stream`; its CTAs wait for per-chunk flags that the copy stream sets behind each chunk of inputs, and write
+  // their results directly into host memory.  Copy engine and kernel overlap without any launch boundary.
+  const bool streamed = hybrid && chunk >= 2 && chunk <= 15;
   const size_t need = host_workspace_bytes<B>(nbatch, natoms, h_g != nullptr, atm);
   if (!workspace || wbytes < need)
     return fail(D3B200_EINVAL, "host-entry workspace too small%s: %ld < %ld bytes", "", (long)wbytes, (long)need);
@@ -312,6 +329,32 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
   chunk_model.batch_order = nullptr;                 // the hint refers to the whole batch, not to a chunk
   cudaError_t e;
 #define D3_CK(call, what) if ((e = (call)) != cudaSuccess) return cuda_fail(e, what)
+  if (streamed) {
+    const int per = 1 << chunk;
+    const int nflag = (nbatch + per - 1) / per;
+    // flags live in the (otherwise unused) device energy staging area
+    int* d_ready = reinterpret_cast<int*>(d_e);
+    if ((size_t)nflag * sizeof(int) > na * sizeof(B)) return fail(D3B200_EINVAL, "streamed host form: too many chunks%s");
+    D3_CK(cudaMemsetAsync(d_ready, 0, (size_t)nflag * sizeof(int), (cudaStream_t)stream), "cudaMemsetAsync");
+    D3_CK(cudaEventRecord(pipe->start, (cudaStream_t)stream), "cudaEventRecord");
+    D3_CK(cudaStreamWaitEvent(pipe->in, pipe->start, 0), "cudaStreamWaitEvent");
+    int rc = vjp_impl<B>(nbatch, natoms, d_z, d_x, &chunk_model, par, h_g ? d_g : nullptr, h_energy, h_grad, nullptr,
+                         nullptr, 0, stream, 1, d_ready, per);
+    if (rc) return rc;
+    for (int k = 0; k < nflag; ++k) {
+      const int lo = k * per, nb = (lo + per <= nbatch ? per : nbatch - lo);
+      const size_t o = (size_t)lo * natoms, cnt = (size_t)nb * natoms;
+      D3_CK(cudaMemcpyAsync(d_z + o, h_numbers + o, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, pipe->in), "H2D numbers");
+      D3_CK(cudaMemcpyAsync(d_x + 3 * o, h_positions + 3 * o, cnt * 3 * sizeof(B), cudaMemcpyHostToDevice, pipe->in), "H2D positions");
+      if (h_g) D3_CK(cudaMemcpyAsync(d_g + o, h_g + o, cnt * sizeof(B), cudaMemcpyHostToDevice, pipe->in), "H2D cotangent");
+      D3_CK(cudaMemcpyAsync(d_ready + k, pipe->h_one, sizeof(int), cudaMemcpyHostToDevice, pipe->in), "H2D flag");
+    }
+    // the next call may reuse the staging buffers: `stream` also waits for the copy stream (already implied by the
+    // kernel having consumed every flag, made explicit for the stream order)
+    D3_CK(cudaEventRecord(pipe->done, pipe->in), "cudaEventRecord");
+    D3_CK(cudaStreamWaitEvent((cudaStream_t)stream, pipe->done, 0), "cudaStreamWaitEvent");
+    return D3B200_OK;
+  }
   D3_CK(cudaEventRecord(pipe->start, (cudaStream_t)stream), "cudaEventRecord");
   D3_CK(cudaStreamWaitEvent(pipe->in, pipe->start, 0), "cudaStreamWaitEvent");
   for (int k = 0; k < nchunk; ++k) {
@@ -323,12 +366,18 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
     D3_CK(cudaEventRecord(pipe->ev_in[k], pipe->in), "cudaEventRecord");
     cudaStream_t cs = pipe->comp[k & 1];
     D3_CK(cudaStreamWaitEvent(cs, pipe->ev_in[k], 0), "cudaStreamWaitEvent");
-    int rc = vjp_impl<B>(nb, natoms, d_z + o, d_x + 3 * o, &chunk_model, par, h_g ? d_g + o : nullptr,
-                         h_energy ? d_e + o : nullptr, d_gr + 3 * o, nullptr,
-                         atm ? d_atm + (size_t)lo * atm_per : nullptr, (size_t)nb * atm_per, cs);
+    int rc;
+    if (hybrid)
+      rc = vjp_impl<B>(nb, natoms, d_z + o, d_x + 3 * o, &chunk_model, par, h_g ? d_g + o : nullptr,
+                       h_energy ? h_energy + o : nullptr, h_grad + 3 * o, nullptr, nullptr, 0, cs, 1);
+    else
+      rc = vjp_impl<B>(nb, natoms, d_z + o, d_x + 3 * o, &chunk_model, par, h_g ? d_g + o : nullptr,
+                       h_energy ? d_e + o : nullptr, d_gr + 3 * o, nullptr,
+                       atm ? d_atm + (size_t)lo * atm_per : nullptr, (size_t)nb * atm_per, cs);
     if (rc) return rc;
     D3_CK(cudaEventRecord(pipe->ev_k[k], cs), "cudaEventRecord");
     D3_CK(cudaStreamWaitEvent(pipe->out, pipe->ev_k[k], 0), "cudaStreamWaitEvent");
+    if (hybrid) continue;
     if (h_energy) D3_CK(cudaMemcpyAsync(h_energy + o, d_e + o, cnt * sizeof(B), cudaMemcpyDeviceToHost, pipe->out), "D2H energy");
     D3_CK(cudaMemcpyAsync(h_grad + 3 * o, d_gr + 3 * o, cnt * 3 * sizeof(B), cudaMemcpyDeviceToHost, pipe->out), "D2H gradient");
   }
@@ -564,8 +613,10 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       r.counter = reinterpret_cast<int*>(wsp);
       r.rec = reinterpret_cast<B*>(wsp + 256);
       r.list = reinterpret_cast<int*>(wsp + 256 + (size_t)grid * p.sys.natoms * d3::kAtm3Rec * sizeof(B));
-      cudaError_t e = cudaMemsetAsync(r.counter, 0, sizeof(int), st);
+      cudaError_t e = cudaMemsetAsync(r.counter, 0, 2 * sizeof(int), st);
       if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+      // largest neighbour count -> stride of the per-CTA neighbour slots (keeps the scratch L2-resident)
+      d3::system_atm_maxn_kernel<B><<<(p.sys.natoms / d3::kSysSub + 3) / 4, 128, 0, st>>>(p.sys, q.eidx, r.counter + 1);
       if (want_grad) d3::system_atm3_kernel<B, true><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
       else d3::system_atm3_kernel<B, false><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
       return launched("system_atm3_kernel");
@@ -822,6 +873,8 @@ int d3b200_pipe_create(d3b200_pipe** out) {
     e = cudaEventCreateWithFlags(&p->ev_in[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_k[k], cudaEventDisableTiming);
   }
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&p->h_one, sizeof(int), cudaHostAllocDefault);
+  if (e == cudaSuccess) *p->h_one = 1;
   if (e != cudaSuccess) { d3b200_pipe_destroy(p); return cuda_fail(e, "d3b200_pipe_create"); }
   *out = p;
   return D3B200_OK;
@@ -836,6 +889,7 @@ int d3b200_pipe_destroy(d3b200_pipe* p) {
     if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
     if (p->ev_k[k]) cudaEventDestroy(p->ev_k[k]);
   }
+  if (p->h_one) cudaFreeHost(p->h_one);
   free(p);
   return D3B200_OK;
 }

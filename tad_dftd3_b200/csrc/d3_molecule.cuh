@@ -57,6 +57,8 @@ struct MolArgs {
   S* work;                  // ATM scratch: sqrt|C6| per structure, [nbatch][N][N]
   const int* order;         // optional: CTA k works on structure order[k] (scheduling hint)
   int counting, damping;    // model functions (d3b200_params.counting / .damping); molecule_kernel only
+  const int* ready;         // molecule_kernel_v2, streamed host form: structure b may be read once ready[b / ready_per] != 0
+  int ready_per;            // (set by a stream-ordered memset behind the copy of each chunk of inputs)
   int host_io;              // molecule_kernel_v2: numbers / positions / energy / grad may live in mapped HOST
                             // memory -> every global access of these arrays fully coalesced
 };

@@ -157,6 +157,16 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
 
   const int64_t* numbers = A.numbers + (size_t)b * N;
   const S* pos = A.positions + (size_t)b * N * 3;
+  if (A.ready) {
+    // streamed host form: the inputs of this structure are still on their way over PCIe (copy engine, chunk by
+    // chunk, on another stream); wait for the flag that the copy stream sets behind the chunk
+    if (t == 0) {
+      const volatile int* flag = A.ready + b / A.ready_per;
+      while (*flag == 0) __nanosleep(256);
+      __threadfence();
+    }
+    __syncthreads();
+  }
 
   // tensor memory: kCols 32-bit columns for this CTA, a quarter of the lanes per warp
   constexpr bool kTmem = WANT_G && (D3_V2_TMEM != 0);

@@ -250,17 +250,26 @@ def hessian(numbers: Tensor, positions: Tensor, param: dict, **kwargs) -> Tensor
     dtype, device = positions.dtype, positions.device
     if n == 0:
         return torch.zeros(0, 3, 0, 3, dtype=dtype, device=device)
-    nb = 3 * n
-    vx = torch.eye(nb, dtype=dtype, device=device).reshape(nb, n, 3)
-    g = torch.ones(nb, n, dtype=dtype, device=device)
+    ntan = 3 * n
+    # With the three-body term every tangent of a launch needs its own dual-number sqrt|C6| matrix (16 N^2 bytes
+    # in fp64): the 3N unit tangents go in chunks that keep that workspace below 1 GiB.
+    per_tangent = 2 * positions.element_size() * n * n if float(p[4]) != 0.0 else 0
+    chunk = ntan if per_tangent == 0 else max(1, min(ntan, (1 << 30) // per_tangent))
+    eye = torch.eye(ntan, dtype=dtype, device=device).reshape(ntan, n, 3)
+    cols = []
+    for lo in range(0, ntan, chunk):
+        nb = min(chunk, ntan - lo)
+        g = torch.ones(nb, n, dtype=dtype, device=device)
 
-    def per_batch(t, per_element):
-        return t if (t is None or per_element) else t.unsqueeze(0).expand(nb, *t.shape)
+        def per_batch(t, per_element):
+            return t if (t is None or per_element) else t.unsqueeze(0).expand(nb, *t.shape)
 
-    _, dgrad, _ = _run_hvp(
-        numbers.unsqueeze(0).expand(nb, n), positions.detach().unsqueeze(0).expand(nb, n, 3), p.detach(), g, vx,
-        torch.zeros(5, dtype=dtype), per_batch(rcov_t, st.rcov_per_element), per_batch(r4r2_t, st.r4r2_per_element),
-        per_batch(rvdw_t, st.rvdw_mode != 2), refcn, refc6, st)
+        _, dgrad, _ = _run_hvp(
+            numbers.unsqueeze(0).expand(nb, n), positions.detach().unsqueeze(0).expand(nb, n, 3), p.detach(), g,
+            eye[lo:lo + nb], torch.zeros(5, dtype=dtype), per_batch(rcov_t, st.rcov_per_element),
+            per_batch(r4r2_t, st.r4r2_per_element), per_batch(rvdw_t, st.rvdw_mode != 2), refcn, refc6, st)
+        cols.append(dgrad)
+    dgrad = cols[0] if len(cols) == 1 else torch.cat(cols)
     # row k of dgrad is H e_k, i.e. column k of the (symmetric) Hessian
     return dgrad.reshape(n, 3, n, 3).permute(2, 3, 0, 1).contiguous()
 

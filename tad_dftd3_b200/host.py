@@ -186,14 +186,16 @@ class HostPipeline:
 
         if nb and n:
             fn = getattr(self._lib, f"d3b200_batch_vjp_host_{sfx}")
-            zero_copy = (chunk <= 0 and not atm and z.is_pinned() and x.is_pinned() and energy_out.is_pinned()
+            zero_copy = (chunk == 0 and not atm and z.is_pinned() and x.is_pinned() and energy_out.is_pinned()
                          and grad_out.is_pinned() and (g is None or g.is_pinned()))
             # (the zero-copy form does not touch the workspace; it is sized for the staged form the
             # library falls back to when a buffer turns out not to be mapped)
             wsfn = getattr(self._lib, f"d3b200_batch_host_workspace_bytes_{sfx}")
             work = self._workspace(int(wsfn(nb, n, int(g is not None), int(atm))))
-            _lib.launch_count += 1 if zero_copy else self.chunks(nb, chunk)
-            self.last_mode = "zero-copy" if zero_copy else "staged"
+            hybrid = chunk < 0 and not atm and energy_out.is_pinned() and grad_out.is_pinned()
+            streamed = hybrid and -15 <= chunk <= -2
+            _lib.launch_count += 1 if (zero_copy or streamed) else self.chunks(nb, chunk)
+            self.last_mode = "zero-copy" if zero_copy else ("streamed" if streamed else ("hybrid" if hybrid else "staged"))
             # (no `batch_order` hint here: with largest-first scheduling the CTAs of a wave finish
             # together and their PCIe requests arrive in bursts -- measured 0.65 ms against 0.61 ms)
             args = (self._pipe, nb, n, C.c_void_p(z.data_ptr()), C.c_void_p(x.data_ptr()),
@@ -217,7 +219,7 @@ class HostPipeline:
                 import weakref
 
                 self._fast = (fkey, tuple(weakref.ref(t) for t in (numbers, positions, energy_out, grad_out)),
-                              (fn, args, 1 if zero_copy else self.chunks(nb, chunk), outs), self._keep)
+                              (fn, args, 1 if (zero_copy or streamed) else self.chunks(nb, chunk), outs), self._keep)
             return outs
         return energy_out.reshape(*lead, n), grad_out.reshape(*lead, n, 3)
 

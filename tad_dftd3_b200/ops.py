@@ -293,6 +293,11 @@ def _run_vjp(numbers, positions, p, g, rcov, r4r2, rvdw, refcn, refc6, st, want_
 
 def _run_hvp(numbers, positions, p, g, vx, vp, rcov, r4r2, rvdw, refcn, refc6, st):
     c = _Call(numbers, positions, p, rcov, r4r2, rvdw, refcn, refc6, st, 1)
+    if c.nflat and c.n > _fused_limit(c.sfx, 1):
+        raise NotImplementedError(
+            f"second derivatives (gradgradcheck, nested jacrev, hessian()) are provided by the fused kernel on dual "
+            f"numbers, which takes structures of up to {_fused_limit(c.sfx, 1)} atoms ({c.n} given); the tiled "
+            "large-structure sweeps provide energies, gradients and parameter gradients")
     de = c.new(c.nflat, c.n, zero=True)
     dgrad = c.new(c.nflat, c.n, 3, zero=True)
     dpgrad = c.new(c.nflat, NPAR, zero=True)

@@ -35,10 +35,12 @@ def test_host_entry_matches_reference_runs(runs, case):
 
 
 @pytest.mark.parametrize("dtype", [torch.double, torch.float32])
-@pytest.mark.parametrize("chunk", [0, 5, 16])
+@pytest.mark.parametrize("chunk", [0, 5, 16, -16, -3])
 def test_host_entry_bitwise_equals_device_path(dtype, chunk):
     """Chunking must not change a single bit: structures are independent and the
-    kernel's summation order depends on the structure only."""
+    kernel's summation order depends on the structure only.  chunk 0: zero-copy; > 0: staged;
+    -16: hybrid (inputs staged, results written straight into host memory); -3: streamed (one
+    launch whose CTAs wait for per-chunk flags set behind the copies, 2^3 structures per chunk)."""
     import tad_dftd3_b200 as d3
     from tad_dftd3_b200 import synthetic as syn
 
