@@ -61,11 +61,39 @@ def build_variant(out: str, extra_flags) -> str:
     return out
 
 
+INFO = os.path.join(HERE, "build_info.json")
+
+
+def _record(mode: str, digest: str, seconds: float = 0.0) -> None:
+    """`build_info.json` next to the library: which build the loaded .so is (source digest, flags, nvcc) and whether
+    the last `build()` call compiled it ("compiled") or found it up to date ("reused: source digest unchanged")."""
+    import json
+    import time
+
+    try:
+        ver = subprocess.run([nvcc(), "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    except (OSError, RuntimeError, IndexError):
+        ver = "nvcc unavailable"
+    info = {"library": os.path.basename(LIB), "mode": mode, "source_digest": digest, "nvcc": ver,
+            "flags": NVCC_FLAGS, "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),
+            "compile_seconds": round(seconds, 1), "lib_bytes": os.path.getsize(LIB) if os.path.isfile(LIB) else 0}
+    try:
+        with open(INFO, "w") as fh:
+            json.dump(info, fh, indent=1)
+    except OSError:  # pragma: no cover
+        pass
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    import time
+
     digest = _digest()
+    force = force or os.environ.get("TAD_DFTD3_B200_FORCE_BUILD") == "1"
     if not force and os.path.isfile(LIB) and os.path.isfile(STAMP):
         if open(STAMP).read().strip() == digest:
+            _record("reused: source digest unchanged", digest)
             return LIB
+    t0 = time.time()
     cus = [f for f in sources() if f.endswith(".cu")]
     cmd = [nvcc(), *NVCC_FLAGS, "-o", LIB, *cus]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -77,6 +105,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         fh.write(res.stderr)
     with open(STAMP, "w") as fh:
         fh.write(digest)
+    _record("compiled", digest, time.time() - t0)
     return LIB
 
 
