@@ -348,8 +348,9 @@ int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* p
  * counter, compact the centre's neighbour list into the scratch and walk the
  * pairs of neighbours (see csrc/d3_atm3.cuh).  The launch owns the centres of
  * the 32-atom sub-tiles row_begin/32 + k*tile_stride below row_end (row range
- * aligned to 32; tile_stride <= 1: the whole range), which is how ranks shard
- * the term. */
+ * aligned to 32; tile_stride 0 or 1: the whole range), or, with tile_stride < 0, the
+ * single atoms row_begin + k*|tile_stride| below row_end (any row_begin), which is how
+ * ranks shard the term: dealt atom by atom the ranks' costs differ by well under 1 %. */
 size_t d3b200_system_atm_workspace_bytes_f64(int natoms);
 size_t d3b200_system_atm_workspace_bytes_f32(int natoms);
 int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par,

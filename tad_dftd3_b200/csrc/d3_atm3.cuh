@@ -52,7 +52,8 @@ struct AtmArgs3 {
   int* list;       // [gridDim.x][natoms]          neighbour indices of the CTA's current centre
   S* rec;          // [gridDim.x][natoms][kAtm3Rec] neighbour records
   int* counter;    // zero before the launch; counter[1] = largest neighbour count of any atom (system_atm_maxn_kernel)
-  int tile_stride; // the launch owns the 32-atom sub-tiles row_begin/32 + k * tile_stride below row_end
+  int tile_stride; // > 0: the launch owns the 32-atom sub-tiles row_begin/32 + k * tile_stride below row_end;
+                   // < 0: the atoms row_begin + k * |tile_stride| below row_end
   int parts;       // a centre is split into `parts` work units (every parts-th tile of its list): keeps
                    // the persistent CTAs busy when a launch owns few centres (several GPUs)
 };
@@ -164,9 +165,13 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
   const int E = P.nelem;
   const int natoms = A.natoms;
   const int nsub = natoms / kSysSub;
-  const int tstride = Q.tile_stride > 0 ? Q.tile_stride : 1;
+  // ownership of the centres: tile_stride > 0: the 32-atom sub-tiles row_begin/32 + k * tile_stride;
+  // tile_stride < 0: the atoms row_begin + k * |tile_stride| (atom by atom: neighbouring atoms of the sorted
+  // order cost about the same, so ranks that deal them round-robin finish together)
+  const bool atomwise = Q.tile_stride < 0;
+  const int tstride = atomwise ? -Q.tile_stride : (Q.tile_stride > 0 ? Q.tile_stride : 1);
   const int nsub_own = ((A.row_end - A.row_begin) / kSysSub + tstride - 1) / tstride;
-  const int nrows = nsub_own * kSysSub;
+  const int nrows = atomwise ? (A.row_end - A.row_begin + tstride - 1) / tstride : nsub_own * kSysSub;
   // per-CTA slots sized by the largest neighbour count (rounded up to whole tiles), packed back to back
   const int slot = min(natoms, ((Q.counter[1] + TK - 1) / TK) * TK);
   int* list = Q.list + (size_t)blockIdx.x * slot;
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
     const int part = s_center % parts;
     const int c = s_center / parts;
     if (c >= nrows) break;
-    const int i = A.row_begin + (c / kSysSub) * tstride * kSysSub + (c % kSysSub);
+    const int i = atomwise ? A.row_begin + c * tstride : A.row_begin + (c / kSysSub) * tstride * kSysSub + (c % kSysSub);
     const int ei = P.eidx[i];
     if (ei < 0) continue;                  // padding row (CTA-uniform)
     const Atom4<S> ai = A.atoms[i];

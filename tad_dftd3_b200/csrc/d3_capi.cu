@@ -577,7 +577,8 @@ int atm3_grid() {
 template <typename B>
 int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int want_grad, void* stream) {
   d3::AtmArgs<B> p;
-  int rc = sys_fill<B>(p.sys, s, par, d3::kSysSub);
+  // tile_stride < 0: centres dealt atom by atom (row_begin = first centre, any value), see d3b200.h
+  int rc = sys_fill<B>(p.sys, s, par, s && s->tile_stride < 0 ? 1 : d3::kSysSub);
   if (rc) return rc;
   if (!rvdw || !s->aux || !s->w || !s->dw || !s->refc6 || !s->energy) return fail(D3B200_EINVAL, "null ATM argument%s");
   if (want_grad && (!s->grad || !s->decn)) return fail(D3B200_EINVAL, "null ATM gradient output%s");
@@ -601,11 +602,12 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       // every triple once: persistent CTAs, centre atoms from a counter
       d3::AtmArgs3<B> r;
       r.a = q;
-      r.tile_stride = s->tile_stride > 0 ? s->tile_stride : 1;
+      r.tile_stride = s->tile_stride != 0 ? s->tile_stride : 1;
       const int grid = atm3_grid();
       {
         // about four work units per persistent CTA, at most 8 per centre
-        const int owned = (rows + r.tile_stride - 1) / r.tile_stride;
+        const int astride = r.tile_stride < 0 ? -r.tile_stride : r.tile_stride;
+        const int owned = (rows + astride - 1) / astride;
         int parts = owned > 0 ? (4 * grid + owned - 1) / owned : 1;
         r.parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
       }
@@ -621,7 +623,7 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       else d3::system_atm3_kernel<B, false><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
       return launched("system_atm3_kernel");
     }
-    if (s->tile_stride > 1) return fail(D3B200_EINVAL, "strided ATM ownership needs atm_work (the triples-once kernel)%s");
+    if (s->tile_stride > 1 || s->tile_stride < 0) return fail(D3B200_EINVAL, "strided ATM ownership needs atm_work (the triples-once kernel)%s");
     const size_t smem = d3::atm2_smem_bytes<B>(q.nelem);
     if (want_grad) {
       auto kern = d3::system_atm2_kernel<B, true>;
@@ -634,7 +636,7 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
     }
     return launched("system_atm2_kernel");
   }
-  if (s->tile_stride > 1) return fail(D3B200_EINVAL, "strided ATM ownership needs the T vectors and atm_work%s");
+  if (s->tile_stride > 1 || s->tile_stride < 0) return fail(D3B200_EINVAL, "strided ATM ownership needs the T vectors and atm_work%s");
   if (want_grad) d3::system_atm_kernel<B, true><<<rows, 32 * d3::kAtmWarps, 0, st>>>(p);
   else d3::system_atm_kernel<B, false><<<rows, 32 * d3::kAtmWarps, 0, st>>>(p);
   return launched("system_atm_kernel");

@@ -240,15 +240,16 @@ def test_plan_sorting_and_padding(monkeypatch):
     assert back[3] == 0 and torch.equal(back[plan.perm], vals[: plan.n])
 
 
-def test_three_body_centre_ownership_covers_every_sub_tile_once():
-    """`SystemRunner.atm_partition` + the kernel's index arithmetic (csrc/d3_atm3.cuh: a launch owns the
-    32-atom sub-tiles row_begin/32 + k*stride below row_end): over the ranks every sub-tile exactly once."""
+def test_three_body_centre_ownership_covers_every_atom_once():
+    """`SystemRunner.atm_partition` + the kernel's index arithmetic (csrc/d3_atm3.cuh): with a negative stride a
+    launch owns the atoms row_begin + k*|stride| below row_end, with a positive one the 32-atom sub-tiles
+    row_begin/32 + k*stride; over the ranks every centre exactly once."""
     from tad_dftd3_b200 import _lib, synthetic as syn
     from tad_dftd3_b200.data import COV_D3, R4R2, REFCN
     from tad_dftd3_b200.system import SUB, SystemPlan, SystemRunner
 
     dt = torch.double
-    numbers, positions = syn.water_cluster(150, seed=2)               # 450 atoms -> 512 padded, 16 sub-tiles
+    numbers, positions = syn.water_cluster(150, seed=2)               # 450 atoms -> 512 padded
     par = _lib.Params()
     par.s6, par.s8, par.a1, par.a2, par.s9 = 1.0, 0.79, 0.49, 5.73, 1.0
     par.cutoff, par.cn_cutoff, par.kcn = 20.0, 25.0, 16.0
@@ -259,8 +260,12 @@ def test_three_body_centre_ownership_covers_every_sub_tile_once():
             run = SystemRunner(plan, REFCN(dt), syn.synthetic_c6_table(dt), par, None, world, syn.synthetic_rvdw_table(dt))
             begin, end = run.atm_partition(rank, world)
             stride = run._atm_stride
-            assert begin % SUB == 0 and end % SUB == 0
-            nsub_own = ((end - begin) // SUB + stride - 1) // stride            # the kernel's count
-            owned += [begin // SUB + k * stride for k in range(nsub_own)]
-        owned = [s for s in owned if s < plan.npad // SUB]
-        assert sorted(owned) == list(range(plan.npad // SUB)), (world, sorted(owned))
+            if stride < 0:                                              # atom by atom (the kernel's arithmetic)
+                nown = (end - begin + (-stride) - 1) // (-stride)
+                owned += [begin + k * (-stride) for k in range(nown)]
+            else:                                                       # sub-tiles
+                assert begin % SUB == 0 and end % SUB == 0
+                nsub_own = ((end - begin) // SUB + stride - 1) // stride
+                owned += [s * SUB + a for s in (begin // SUB + k * stride for k in range(nsub_own)) for a in range(SUB)]
+        owned = [a for a in owned if a < plan.npad]
+        assert sorted(owned) == list(range(plan.npad)), (world, len(owned))
