@@ -114,18 +114,19 @@ __device__ __forceinline__ S pow16_3_fast(S x) {
 // of `system_atm3_kernel` (slots of `natoms` entries, 1 MB apart, alias in the L2 sets and were written back
 // to DRAM at 50x the algorithmic bytes, profiles/r1h_system_atm3_raw.csv).  One warp per 32-atom sub-tile,
 // lane = atom, partner sub-tiles culled by their boxes; the result is an atomicMax into *out (zero before).
+constexpr int kMaxnWarps = 8;
 template <typename S>
-__global__ void __launch_bounds__(128) system_atm_maxn_kernel(SysArgs<S> A, const signed char* eidx, int* out) {
-  const int lane = threadIdx.x & 31;
-  const int sub = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(32 * kMaxnWarps) system_atm_maxn_kernel(SysArgs<S> A, const signed char* eidx, int* out) {
+  // one CTA per 32-atom sub-tile (lane = atom), its warps deal the partner sub-tiles round-robin
+  __shared__ int cnt[kMaxnWarps][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sub = blockIdx.x;
   const int nsub = A.natoms / kSysSub;
-  if (sub >= nsub) return;
   const int i = sub * kSysSub + lane;
   const Atom4<S> ai = A.atoms[i];
-  const bool real_i = eidx[i] >= 0;
   const S* ibox = A.box + (size_t)sub * 6;
   int n = 0;
-  for (int js = 0; js < nsub; ++js) {
+  for (int js = w; js < nsub; js += kMaxnWarps) {
     if (box_dist2(ibox, A.box + (size_t)js * 6) > A.cutoff2) continue;     // warp-uniform
     const int j = js * kSysSub + lane;
     const Atom4<S> aj = A.atoms[j];
@@ -137,9 +138,16 @@ __global__ void __launch_bounds__(128) system_atm_maxn_kernel(SysArgs<S> A, cons
       n += (rj && (js * kSysSub + l) != i && dx * dx + dy * dy + dz * dz <= A.cutoff2) ? 1 : 0;
     }
   }
-  n = real_i ? n : 0;
-  n = __reduce_max_sync(0xffffffffu, n);
-  if (lane == 0 && n > 0) atomicMax(out, n);
+  cnt[w][lane] = n;
+  __syncthreads();
+  if (w == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxnWarps; ++k) tot += cnt[k][lane];
+    tot = eidx[i] >= 0 ? tot : 0;
+    tot = __reduce_max_sync(0xffffffffu, tot);
+    if (lane == 0 && tot > 0) atomicMax(out, tot);
+  }
 }
 
 // record slots

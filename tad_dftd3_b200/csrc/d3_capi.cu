@@ -338,7 +338,10 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
     D3_CK(cudaMemsetAsync(d_ready, 0, (size_t)nflag * sizeof(int), (cudaStream_t)stream), "cudaMemsetAsync");
     D3_CK(cudaEventRecord(pipe->start, (cudaStream_t)stream), "cudaEventRecord");
     D3_CK(cudaStreamWaitEvent(pipe->in, pipe->start, 0), "cudaStreamWaitEvent");
-    int rc = vjp_impl<B>(nbatch, natoms, d_z, d_x, &chunk_model, par, h_g ? d_g : nullptr, h_energy, h_grad, nullptr,
+    // (D3B200_STREAMED_DEVICE_OUT=1: timing experiment only -- results stay in the device staging area)
+    static const bool dev_out = getenv("D3B200_STREAMED_DEVICE_OUT") != nullptr;
+    int rc = vjp_impl<B>(nbatch, natoms, d_z, d_x, &chunk_model, par, h_g ? d_g : nullptr,
+                         dev_out ? nullptr : h_energy, dev_out ? d_gr : h_grad, nullptr,
                          nullptr, 0, stream, 1, d_ready, per);
     if (rc) return rc;
     for (int k = 0; k < nflag; ++k) {
@@ -605,10 +608,10 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       r.tile_stride = s->tile_stride != 0 ? s->tile_stride : 1;
       const int grid = atm3_grid();
       {
-        // about four work units per persistent CTA, at most 8 per centre
+        // about eight work units per persistent CTA (tail of the dynamic schedule), at most 8 per centre
         const int astride = r.tile_stride < 0 ? -r.tile_stride : r.tile_stride;
         const int owned = (rows + astride - 1) / astride;
-        int parts = owned > 0 ? (4 * grid + owned - 1) / owned : 1;
+        int parts = owned > 0 ? (8 * grid + owned - 1) / owned : 1;
         r.parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
       }
       char* wsp = reinterpret_cast<char*>(s->atm_work);
@@ -618,7 +621,7 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       cudaError_t e = cudaMemsetAsync(r.counter, 0, 2 * sizeof(int), st);
       if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
       // largest neighbour count -> stride of the per-CTA neighbour slots (keeps the scratch L2-resident)
-      d3::system_atm_maxn_kernel<B><<<(p.sys.natoms / d3::kSysSub + 3) / 4, 128, 0, st>>>(p.sys, q.eidx, r.counter + 1);
+      d3::system_atm_maxn_kernel<B><<<p.sys.natoms / d3::kSysSub, 32 * d3::kMaxnWarps, 0, st>>>(p.sys, q.eidx, r.counter + 1);
       if (want_grad) d3::system_atm3_kernel<B, true><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
       else d3::system_atm3_kernel<B, false><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
       return launched("system_atm3_kernel");

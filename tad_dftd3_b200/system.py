@@ -228,7 +228,11 @@ class SystemRunner:
         s.energy, s.grad = self.energy.data_ptr(), self.grad.data_ptr()
         ntiles = npad // TILE
         rows_tiles = max(1, ntiles // max(world, 1))
-        self.jsplit = int(max(1, min(ntiles, -(-self.TARGET_CTAS // rows_tiles))))
+        # with four or more ranks a rank's ~50-100 row tiles need a finer j-split to fill 148 SMs:
+        # 50k atoms on 8 GPUs 0.86 ms at 12 CTAs per SM, 0.79 ms at 24, 1.01 ms at 8 (profiles/r2_summary.md)
+        target = self.TARGET_CTAS * (2 if world >= 4 else 1)
+        target = int(os.environ.get("TAD_DFTD3_B200_TARGET_CTAS", target))             # experiment knob
+        self.jsplit = int(max(1, min(ntiles, -(-target // rows_tiles))))
         self.scratch = torch.empty(5 * self.jsplit * npad, dtype=dt, device=dev)
         s.jsplit, s.scratch = self.jsplit, self.scratch.data_ptr()
         # pre-contracted reference vectors (structures with <= 8 distinct elements)
