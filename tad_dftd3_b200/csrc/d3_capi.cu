@@ -344,12 +344,18 @@ int vjp_host_impl(d3b200_pipe* pipe, int nbatch, int natoms, const int64_t* h_nu
                          dev_out ? nullptr : h_energy, dev_out ? d_gr : h_grad, nullptr,
                          nullptr, 0, stream, 1, d_ready, per);
     if (rc) return rc;
+    // numbers (and the cotangent) travel on a second copy stream, next to the positions: every copy pays ~10 us of
+    // DMA set-up, which in ONE stream made a chunk's transfer slower than its arithmetic
+    D3_CK(cudaStreamWaitEvent(pipe->out, pipe->start, 0), "cudaStreamWaitEvent");
+    const int nev = nflag < kPipeMaxChunks ? nflag : kPipeMaxChunks;
     for (int k = 0; k < nflag; ++k) {
       const int lo = k * per, nb = (lo + per <= nbatch ? per : nbatch - lo);
       const size_t o = (size_t)lo * natoms, cnt = (size_t)nb * natoms;
-      D3_CK(cudaMemcpyAsync(d_z + o, h_numbers + o, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, pipe->in), "H2D numbers");
+      D3_CK(cudaMemcpyAsync(d_z + o, h_numbers + o, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, pipe->out), "H2D numbers");
+      if (h_g) D3_CK(cudaMemcpyAsync(d_g + o, h_g + o, cnt * sizeof(B), cudaMemcpyHostToDevice, pipe->out), "H2D cotangent");
+      D3_CK(cudaEventRecord(pipe->ev_in[k % nev], pipe->out), "cudaEventRecord");
       D3_CK(cudaMemcpyAsync(d_x + 3 * o, h_positions + 3 * o, cnt * 3 * sizeof(B), cudaMemcpyHostToDevice, pipe->in), "H2D positions");
-      if (h_g) D3_CK(cudaMemcpyAsync(d_g + o, h_g + o, cnt * sizeof(B), cudaMemcpyHostToDevice, pipe->in), "H2D cotangent");
+      D3_CK(cudaStreamWaitEvent(pipe->in, pipe->ev_in[k % nev], 0), "cudaStreamWaitEvent");
       D3_CK(cudaMemcpyAsync(d_ready + k, pipe->h_one, sizeof(int), cudaMemcpyHostToDevice, pipe->in), "H2D flag");
     }
     // the next call may reuse the staging buffers: `stream` also waits for the copy stream (already implied by the
