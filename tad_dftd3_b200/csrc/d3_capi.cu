@@ -614,10 +614,11 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       r.tile_stride = s->tile_stride != 0 ? s->tile_stride : 1;
       const int grid = atm3_grid();
       {
-        // about eight work units per persistent CTA (tail of the dynamic schedule), at most 8 per centre
+        // about four work units per persistent CTA, at most 8 per centre (eight per CTA measured slower:
+        // 10 k atoms on 8 GPUs 12.8 ms against 10.8 ms, profiles/r2_summary.md)
         const int astride = r.tile_stride < 0 ? -r.tile_stride : r.tile_stride;
         const int owned = (rows + astride - 1) / astride;
-        int parts = owned > 0 ? (8 * grid + owned - 1) / owned : 1;
+        int parts = owned > 0 ? (4 * grid + owned - 1) / owned : 1;
         r.parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
       }
       char* wsp = reinterpret_cast<char*>(s->atm_work);

@@ -156,3 +156,73 @@ def test_batch_order_hint_does_not_change_results():
         d3.dftd3_host(nh, ph, par, ref=ref, energy_out=e_h, grad_out=g_h)
         assert np.array_equal(e_h.numpy(), outs[0][0].cpu().numpy())
         assert np.array_equal(g_h.numpy(), outs[0][1].cpu().numpy())
+
+
+def test_reference_tables_of_other_shapes_are_rejected_and_cache_follows_edits():
+    """The kernels index the tables with fixed strides ([104,7] / [104,104,7,7]): any other mutually consistent
+    shape (which the reference's holder accepts, reference.py:231-245) must be refused, not read out of bounds;
+    editing a table in place invalidates the prepared device copy."""
+    import tad_dftd3_b200 as d3
+
+    dt = torch.double
+    refcn, refc6, *_ = tables(dt, DEV)
+    numbers = torch.tensor([8, 1, 1], device=DEV)
+    pos = torch.tensor([[0.0, 0.0, -0.7], [1.4, 0.0, 0.4], [-1.4, 0.0, 0.4]], device=DEV, dtype=dt)
+    par = {"s6": torch.tensor(1.0), "s8": torch.tensor(0.8)}
+    small = d3.Reference(cn=refcn[:87, :5].contiguous(), c6=refc6[:87, :87, :5, :5].contiguous())   # consistent, but not 104 x 7
+    with pytest.raises(ValueError, match="reference tables"):
+        d3.dftd3(numbers, pos, par, ref=small)
+    ref = d3.Reference(cn=refcn.clone(), c6=refc6.clone())
+    e0 = d3.dftd3(numbers, pos, par, ref=ref)
+    ref.c6.mul_(2.0)                                   # in-place edit: version counter changes
+    e1 = d3.dftd3(numbers, pos, par, ref=ref)
+    assert torch.allclose(e1, 2.0 * e0, rtol=1e-13, atol=0)
+
+
+def test_arguments_without_derivatives_refuse_requires_grad():
+    """alp / cutoff / rcov / r4r2 / rvdw are constants of the kernels: asking for their gradient raises instead of
+    returning a silently detached result (the reference would differentiate them through autograd)."""
+    import tad_dftd3_b200 as d3
+
+    dt = torch.double
+    refcn, refc6, rcov, r4r2, rvdw = tables(dt, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    numbers = torch.tensor([8, 1, 1], device=DEV)
+    pos = torch.tensor([[0.0, 0.0, -0.7], [1.4, 0.0, 0.4], [-1.4, 0.0, 0.4]], device=DEV, dtype=dt)
+    par = {"s6": torch.tensor(1.0), "s8": torch.tensor(0.8)}
+    with pytest.raises(NotImplementedError, match="rcov"):
+        d3.dftd3(numbers, pos, par, ref=ref, rcov=rcov[numbers].clone().requires_grad_(True))
+    with pytest.raises(NotImplementedError, match="r4r2"):
+        d3.dftd3(numbers, pos, par, ref=ref, r4r2=r4r2[numbers].clone().requires_grad_(True))
+    with pytest.raises(NotImplementedError, match="alp"):
+        d3.dftd3(numbers, pos, dict(par, s9=torch.tensor(1.0), alp=torch.tensor(14.0, requires_grad=True)), ref=ref,
+                 rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)])
+    with pytest.raises(NotImplementedError, match="cutoff"):
+        d3.dftd3(numbers, pos, par, ref=ref, cutoff=torch.tensor(30.0, dtype=dt, requires_grad=True))
+
+
+def test_host_entry_non_contiguous_positions_are_re_read_every_call():
+    """A non-contiguous `positions` needs a private contiguous copy: the prepared-call fast path must not keep
+    returning the results of the first geometry when the caller updates its tensor in place."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+
+    dt = torch.double
+    refcn, refc6, *_ = tables(dt, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    numbers, positions = syn.drug_like_batch(6, seed=9, nmin=10, nmax=20)
+    wide = torch.zeros(*positions.shape[:-1], 4, dtype=dt)
+    wide[..., :3] = positions
+    view = wide[..., :3]                                         # non-contiguous view
+    assert not view.is_contiguous()
+    par = {"s6": torch.tensor(1.0), "s8": torch.tensor(0.7898), "a1": torch.tensor(0.4948), "a2": torch.tensor(5.7308)}
+    e_out = torch.empty(numbers.shape, dtype=dt).pin_memory()
+    g_out = torch.empty(*numbers.shape, 3, dtype=dt).pin_memory()
+    nh = numbers.pin_memory()
+    for step in range(3):
+        wide[..., :3] += 0.05 * torch.sin(wide[..., :3] + step)  # in-place update of the caller's tensor
+        d3.dftd3_host(nh, view, par, ref=ref, energy_out=e_out, grad_out=g_out)
+        x = view.contiguous().to(DEV).requires_grad_(True)
+        e = d3.dftd3(numbers.to(DEV), x, par, ref=ref)
+        (g,) = torch.autograd.grad(e.sum(), x)
+        assert torch.equal(e_out.to(DEV), e.detach()) and torch.equal(g_out.to(DEV), g), step
