@@ -14,6 +14,12 @@
 #include "d3_atm3.cuh"
 #include "d3_stages.cuh"
 #include "d3_system_sym.cuh"
+// 8-row-group form of the pair sweep: measured SLOWER than the 32-row form at the 50-Bohr cutoff (3.12 against
+// 2.61 ms on the 50k-atom cluster: the per-step butterfly, four distinct T rows per step and four candidate lists per
+// tile cost more than the lane efficiency gains, 59 -> 71 %); kept behind this switch, off by default.
+#ifndef D3_SYM_PAIR_Q8
+#define D3_SYM_PAIR_Q8 0
+#endif
 
 namespace {
 
@@ -451,7 +457,8 @@ int sys_cn(const typename SysOf<B>::type* s, const d3b200_params* par, void* str
   if (nblk == 0) return D3B200_OK;
   if (s->symmetric) {
     d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
-    d3::sym_cn_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    if (D3_SYM_Q8) d3::sym_cn_q8_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    else d3::sym_cn_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
     return launched("sym_cn_kernel");
   }
   d3::system_cn_kernel<B><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);
@@ -497,6 +504,11 @@ int sys_pair(const typename SysOf<B>::type* s, const d3b200_params* par, int wan
     d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
     const size_t smem = d3::sym_pair_smem_bytes<B>(a.nelem);
     const dim3 grid(a.jsplit, sym_tiles(s));
+#if D3_SYM_Q8 && D3_SYM_PAIR_Q8
+    if (want_grad) d3::sym_pair_q8_kernel<B, true><<<grid, d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    else d3::sym_pair_q8_kernel<B, false><<<grid, d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    return launched("sym_pair_q8_kernel");
+#endif
     if (want_grad) {
       auto kern = d3::sym_pair_t_kernel<B, true>;
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -563,7 +575,8 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
   if (nblk == 0) return D3B200_OK;
   if (s->symmetric) {
     d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
-    d3::sym_cnbwd_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    if (D3_SYM_Q8) d3::sym_cnbwd_q8_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    else d3::sym_cnbwd_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
     return launched("sym_cnbwd_kernel");
   }
   d3::system_cnbwd_kernel<B><<<dim3(nblk, a.jsplit), d3::kSysTile, 0, (cudaStream_t)stream>>>(a);

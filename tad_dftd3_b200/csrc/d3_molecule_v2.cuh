@@ -282,11 +282,15 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
   // block rb contributes its n-1-16rb partners j = 16rb+1 .. n-1, plus OVH
   // units of fixed per-block overhead so that warps with many short row
   // blocks -- more U contractions, more row epilogues -- get fewer partners).
-#define D3_PIECES_BEGIN(OVH)                                                    \
+#ifndef D3_V2_AL14
+#define D3_V2_AL14 8
+#endif
+#define D3_PIECES_BEGIN(OVH) D3_PIECES_BEGIN_A(OVH, D3_V2_AL14)
+#define D3_PIECES_BEGIN_A(OVH, AL)                                              \
   {                                                                             \
     const int T_ = nb * (n - 1 + (OVH)) - 8 * nb * (nb - 1);                    \
-    const int wlo_ = min(T_, ((T_ * wid / nw) + 7) & ~7);                       \
-    const int whi_ = wid == nw - 1 ? T_ : min(T_, ((T_ * (wid + 1) / nw) + 7) & ~7); \
+    const int wlo_ = min(T_, ((T_ * wid / nw) + (AL) - 1) & ~((AL) - 1));       \
+    const int whi_ = wid == nw - 1 ? T_ : min(T_, ((T_ * (wid + 1) / nw) + (AL) - 1) & ~((AL) - 1)); \
     int pos_ = 0;                                                               \
     for (int rb = 0; rb < nb; ++rb) {                                           \
       const int i0 = rb << 4;                                                   \
@@ -379,7 +383,10 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
 #ifndef D3_V2_OVH3
 #define D3_V2_OVH3 18
 #endif
-  D3_PIECES_BEGIN(D3_V2_OVH3)
+#ifndef D3_V2_AL3
+#define D3_V2_AL3 8
+#endif
+  D3_PIECES_BEGIN_A(D3_V2_OVH3, D3_V2_AL3)
   {
     const Atom4<S> ai = sA[ic];
     const Pair2<S> bi = sB[ic];
@@ -596,6 +603,7 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
   __syncthreads();
   if (kTmem && wid == 0) tmem::dealloc(tm_base);      // every warp has read its last value
 #undef D3_PIECES_BEGIN
+#undef D3_PIECES_BEGIN_A
 #undef D3_PIECES_END
   // host_io: gradient gathered into the caller's order in the (spent) energy slots of
   // warps 0..2, then written as one contiguous [N][3] block, zeros on padding
