@@ -27,6 +27,12 @@ namespace d3 {
 constexpr int kSymChunk = D3_SYM_CHUNK;  // partners per transposed chunk
 constexpr int kSymParts = 32 / kSymChunk; // lanes sharing one partner column
 constexpr int kSymPitch = 33;            // 32 rows + 1: conflict-free column reads
+// (measured on the 50k-atom cluster: 1 tile per barrier pair 2.39 ms, 2 tiles 2.45, 4 tiles 2.45 -- the warps'
+// imbalance does not average out over a batch, so the default stays at one tile)
+#ifndef D3_SYM_BATCH
+#define D3_SYM_BATCH 1
+#endif
+constexpr int kSymBatch = D3_SYM_T_GLOBAL != 0 ? D3_SYM_BATCH : 1;   // j-tiles staged per pair of barriers (pair sweep)
 
 template <typename S>
 struct SymArgs {
@@ -168,14 +174,16 @@ __global__ void __launch_bounds__(kSysTile) sym_cn_kernel(SymArgs<S> P) {
 
 // ---------------------------------------------------------------- pair sweep (T vectors)
 template <typename S, bool WANT_G>
-__global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
+__global__ void __launch_bounds__(kSysTile, 4) sym_pair_t_kernel(SymArgs<S> P) {
   const SysArgs<S>& A = P.sys;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int E = A.nelem;
-  Atom4<S>* sj = reinterpret_cast<Atom4<S>*>(smem_raw);
-  Pair2<S>* sb = reinterpret_cast<Pair2<S>*>(sj + kSysTile);
   constexpr bool kTG = D3_SYM_T_GLOBAL != 0;
-  S* sT = reinterpret_cast<S*>(sb + kSysTile);                 // [128][E][8]  T vectors of the j tile (staged form)
+  constexpr int NB = kSymBatch;
+  __shared__ int sjts[kSymBatch];                                // j-tiles staged per pair of CTA barriers
+  Atom4<S>* sj = reinterpret_cast<Atom4<S>*>(smem_raw);        // [NB][128]
+  Pair2<S>* sb = reinterpret_cast<Pair2<S>*>(sj + NB * kSysTile);
+  S* sT = reinterpret_cast<S*>(sb + NB * kSysTile);                 // [128][E][8]  T vectors of the j tile (staged form)
   S* sTd = sT + (kTG ? 0 : (size_t)kSysTile * E * 8);          // [128][E][8]  Td vectors (dw-contracted)
   S* sSall = sTd + (kTG ? 0 : (size_t)kSysTile * E * 8);       // [4 warps][3][chunk][33]
   S* sXi = sSall + (size_t)4 * 3 * kSymChunk * kSymPitch;      // [4 warps][32][4] rows' x,y,z
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
   for (int k = 0; k < 6; ++k) wbox[k] = A.box[((size_t)itile * 4 + wsub) * 6 + k];
   S* S_ = sSall + (size_t)wsub * 3 * kSymChunk * kSymPitch;
   S* Xi = sXi + wsub * 32 * 4;
-  unsigned char* cand = reinterpret_cast<unsigned char*>(sej + kSysTile) + wsub * (kSysTile + kSymChunk);
+  unsigned char* cand = reinterpret_cast<unsigned char*>(sej + NB * kSysTile) + wsub * (kSysTile + kSymChunk);
   Xi[lane * 4] = ai.x; Xi[lane * 4 + 1] = ai.y; Xi[lane * 4 + 2] = ai.z;
   __syncwarp();
   const int ntiles = A.natoms / kSysTile;
@@ -208,15 +216,22 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
   S e_i = S(0), gx = S(0), gy = S(0), gz = S(0), decn = S(0);
   const int jt_first = itile + blockIdx.x;
   for (int k0 = 0; jt_first + k0 * A.jsplit < ntiles; k0 += 32)
-  for (unsigned tmask = sym_tile_mask<S>(A.box, ibox, jt_first, A.jsplit, k0, ntiles, A.cutoff2, lane); tmask;
-       tmask &= tmask - 1) {
-    const int jt = jt_first + (k0 + __ffs(tmask) - 1) * A.jsplit;      // CTA-uniform
+  for (unsigned tmask = sym_tile_mask<S>(A.box, ibox, jt_first, A.jsplit, k0, ntiles, A.cutoff2, lane); tmask;) {
+    // up to NB reachable j-tiles are staged between one pair of CTA barriers: with the T vectors read from
+    // global memory a tile is 6.5 kB, and the warps' different candidate counts average out over the batch
+    int nbt = 0;
     __syncthreads();
-    {
-      const size_t j = (size_t)jt * kSysTile + t;
-      sj[t] = A.atoms[j];
-      sb[t] = A.aux[j];
-      sej[t] = A.eidx[j];
+#pragma unroll
+    for (int bb = 0; bb < NB; ++bb) {
+      if (!tmask) break;
+      const int jtb = jt_first + (k0 + __ffs(tmask) - 1) * A.jsplit;   // CTA-uniform
+      tmask &= tmask - 1;
+      ++nbt;
+      if (t == 0) sjts[bb] = jtb;
+      const size_t j = (size_t)jtb * kSysTile + t;
+      sj[bb * kSysTile + t] = A.atoms[j];
+      sb[bb * kSysTile + t] = A.aux[j];
+      sej[bb * kSysTile + t] = A.eidx[j];
       if (!kTG) {
         const Pair2<S>* src = reinterpret_cast<const Pair2<S>*>(A.tvec + j * E * 8);
         Pair2<S>* dst = reinterpret_cast<Pair2<S>*>(sT + (size_t)t * E * 8);
@@ -229,22 +244,27 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
       }
     }
     __syncthreads();
-    {
-      const int ncand = sym_candidates<S>(sj, A.box, wbox, jt, itile, wsub, A.cutoff2, cand, lane);
+#pragma unroll 1
+    for (int bb = 0; bb < nbt; ++bb) {
+      const int jt = sjts[bb];
+      const Atom4<S>* sjb = sj + bb * kSysTile;
+      const Pair2<S>* sbb = sb + bb * kSysTile;
+      const int* sejb = sej + bb * kSysTile;
+      const int ncand = sym_candidates<S>(sjb, A.box, wbox, jt, itile, wsub, A.cutoff2, cand, lane);
       for (int c0 = 0; c0 < ncand; c0 += kSymChunk) {
 #pragma unroll 2
         for (int jj = 0; jj < kSymChunk; ++jj) {
           const int jlr = cand[c0 + jj];                  // 255 = chunk padding (warp-uniform)
           const int jl = jlr & (kSysTile - 1);
           const int j = jt * kSysTile + jl;
-          const int ej = jlr < kSysTile ? sej[jl] : -1;
-          const Atom4<S> aj = sj[jl];
+          const int ej = jlr < kSysTile ? sejb[jl] : -1;
+          const Atom4<S> aj = sjb[jl];
           S dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
           S r2 = dx * dx + dy * dy + dz * dz;
           S ep = S(0), fj = S(0), dj = S(0);
           if (ej >= 0 && ei >= 0 && r2 <= A.cutoff2 && j > i) {
             r2 = r2 + tiny;
-            const Pair2<S> bj = sb[jl];
+            const Pair2<S> bj = sbb[jl];
             const Pair2<S>* tj = kTG ? reinterpret_cast<const Pair2<S>*>(A.tvec + ((size_t)j * E + eic) * 8)
                                      : reinterpret_cast<const Pair2<S>*>(sT + ((size_t)jl * E + eic) * 8);
             S tv[8];
@@ -302,7 +322,7 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
         {
           const int col = lane % kSymChunk, r0 = (lane / kSymChunk) * kSymChunk;
           const int jl = cand[c0 + col] & (kSysTile - 1);  // (padding columns sum to zero: no atomics)
-          const Atom4<S> aj = sj[jl];
+          const Atom4<S> aj = sjb[jl];
           S se = S(0), sf = S(0), sfx = S(0), sfy = S(0), sfz = S(0), sd = S(0);
 #pragma unroll 4
           for (int r = 0; r < kSymChunk; ++r) {
@@ -348,7 +368,7 @@ __global__ void __launch_bounds__(kSysTile) sym_pair_t_kernel(SymArgs<S> P) {
 template <typename S>
 inline size_t sym_pair_smem_bytes(int nelem) {
   const size_t tstage = D3_SYM_T_GLOBAL != 0 ? 0 : (size_t)kSysTile * nelem * 16;
-  return kSysTile * (sizeof(Atom4<S>) + sizeof(Pair2<S>) + sizeof(int)) +
+  return kSymBatch * kSysTile * (sizeof(Atom4<S>) + sizeof(Pair2<S>) + sizeof(int)) +
          (tstage + 4 * 3 * kSymChunk * kSymPitch + 4 * 32 * 4) * sizeof(S) +
          4 * (kSysTile + kSymChunk) + 64;
 }
