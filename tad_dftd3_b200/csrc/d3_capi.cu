@@ -439,6 +439,11 @@ int launched(const char* what) {
   return e == cudaSuccess ? D3B200_OK : cuda_fail(e, what);
 }
 
+// The 8-row-group CN sweeps pay while a CTA walks many j-tiles (one GPU: 0.61 -> 0.50 ms on the 50k-atom cluster); with
+// the fine j-split of 8 ranks (73 CTAs per row tile, a few j-tiles each) their per-CTA set-up costs more than the
+// better lane efficiency gains (0.138 -> 0.160 ms), so the 32-row form is kept there.
+inline bool sym_use_q8(int jsplit) { return D3_SYM_Q8 != 0 && jsplit <= 40; }
+
 // row tiles owned by a symmetric launch
 template <typename T>
 int sym_tiles(const T* s) {
@@ -457,7 +462,7 @@ int sys_cn(const typename SysOf<B>::type* s, const d3b200_params* par, void* str
   if (nblk == 0) return D3B200_OK;
   if (s->symmetric) {
     d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
-    if (D3_SYM_Q8) d3::sym_cn_q8_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    if (sym_use_q8(a.jsplit)) d3::sym_cn_q8_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
     else d3::sym_cn_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
     return launched("sym_cn_kernel");
   }
@@ -575,7 +580,7 @@ int sys_cnbwd(const typename SysOf<B>::type* s, const d3b200_params* par, void* 
   if (nblk == 0) return D3B200_OK;
   if (s->symmetric) {
     d3::SymArgs<B> p{a, s->tile_stride > 0 ? s->tile_stride : 1};
-    if (D3_SYM_Q8) d3::sym_cnbwd_q8_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
+    if (sym_use_q8(a.jsplit)) d3::sym_cnbwd_q8_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
     else d3::sym_cnbwd_kernel<B><<<dim3(a.jsplit, sym_tiles(s)), d3::kSysTile, 0, (cudaStream_t)stream>>>(p);
     return launched("sym_cnbwd_kernel");
   }
