@@ -184,30 +184,42 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
   // raw positions: in the reduction tiles when they fit (idle until phase 1), else in acc
   const bool pos_in_red = (size_t)3 * N <= (size_t)nw * 2 * kRedV * kRedStride;
   const S* spos = hio ? (pos_in_red ? red : acc) : pos;
+  // the first global loads of the CTA are issued before any set-up work, so that their latency (HBM, or PCIe
+  // in the zero-copy form) overlaps it: this thread's first atomic number and, with resident inputs, its position
+  const int64_t z_first = t < N ? numbers[t] : 0;
+  S p_first[3] = {S(0), S(0), S(0)};
+  if (!hio && t < N) { p_first[0] = pos[3 * t]; p_first[1] = pos[3 * t + 1]; p_first[2] = pos[3 * t + 2]; }
   for (int k = t; k < kMaxZ; k += nt) cnt[k] = 0;
-  if (hio) {
-    S* dst = pos_in_red ? red : acc;
-    for (int m = t; m < 3 * N; m += nt) dst[m] = pos[m];
-  }
+  if (t == 0) misc[2] = 0;
   if (!hio || pos_in_red)
     for (int k = t; k < nw * 5 * N; k += nt) acc[k] = S(0);
   if (kTmem) tmem::fence_before_sync();
   __syncthreads();
   uint32_t tm_base = 0;
   if (kTmem) { tmem::fence_after_sync(); tm_base = tm_base_s; }
+  int last_real = 0;
   for (int k = t; k < N; k += nt) {
-    int Z = (int)numbers[k];
+    int Z = (int)(k == t ? z_first : numbers[k]);
     if (Z < 0 || Z >= kMaxZ) Z = 0;
     sorigZ[k] = (unsigned char)Z;
     if (Z > 0) {
       atomicAdd(&cnt[Z], 1);
+      last_real = k + 1;
     } else if (!hio) {
       size_t o = (size_t)b * N + k;
       if (A.energy) A.energy[o] = S(0);
       if (WANT_G) { A.grad[3 * o] = S(0); A.grad[3 * o + 1] = S(0); A.grad[3 * o + 2] = S(0); }
     }
   }
+  if (hio && last_real) atomicMax(&misc[2], last_real);
   __syncthreads();
+  if (hio) {
+    // host_io: only the positions up to the last real atom cross the bus (a padded batch of 50..120-atom
+    // structures is 29 % padding), as one coalesced block
+    S* dst = pos_in_red ? red : acc;
+    const int m3 = 3 * misc[2];
+    for (int m = t; m < m3; m += nt) dst[m] = pos[m];
+  }
   if (t < 32) {
     // element histogram -> sorted offsets and group list, one warp, 4 elements per lane
     int c[4], present = 0, total = 0;
@@ -251,7 +263,9 @@ __global__ void __launch_bounds__(32 * kV2Warps, 4) molecule_kernel_v2(MolArgs<S
     S rc = A.rcov_per_element ? A.rcov[Z] : A.rcov[(size_t)b * N + k];
     S q = A.r4r2_per_element ? A.r4r2[Z] : A.r4r2[(size_t)b * N + k];
     Atom4<S> a4;
-    a4.x = spos[3 * k]; a4.y = spos[3 * k + 1]; a4.z = spos[3 * k + 2]; a4.rk = A.kcn * rc;
+    if (!hio && k == t) { a4.x = p_first[0]; a4.y = p_first[1]; a4.z = p_first[2]; }
+    else { a4.x = spos[3 * k]; a4.y = spos[3 * k + 1]; a4.z = spos[3 * k + 2]; }
+    a4.rk = A.kcn * rc;
     sA[p] = a4;
     Pair2<S> b2;
     b2.a = sqr(q);
