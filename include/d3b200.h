@@ -401,6 +401,18 @@ int d3b200_stage_atm_f64(int nbatch, int natoms, const int64_t* numbers, const d
  *                       from ge[B][N]
  *   _stage_atm_bwd      gx[B][N][3], gc6[B][N][N] from ge[B][N]; both outputs must be ZERO on entry (fp64 atomics);
  *                       the ordered term (i; j, k) uses c6[i][j], c6[i][k], c6[j][k] as damping/atm.py:93-97 indexes them */
+/* `_stage_cn_` / `_stage_cn_bwd_` with the counting function chosen by id (d3b200_params.counting: 0 exp_count,
+ * 1 erf_count); `_stage_disp2_` / `_stage_disp2_bwd_` read the damping function from par->damping (and par->alp). */
+int d3b200_stage_cn_model_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
+                              const double* rcov, double cutoff, double kcn, int counting, double* cn, void* stream);
+int d3b200_stage_cn_model_bwd_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
+                                  const double* rcov, double cutoff, double kcn, int counting, const double* gcn,
+                                  double* gx, void* stream);
+int d3b200_stage_cn_model_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
+                              const float* rcov, double cutoff, double kcn, int counting, float* cn, void* stream);
+int d3b200_stage_cn_model_bwd_f32(int nbatch, int natoms, const int64_t* numbers, const float* positions,
+                                  const float* rcov, double cutoff, double kcn, int counting, const float* gcn,
+                                  float* gx, void* stream);
 int d3b200_stage_cn_bwd_f64(int nbatch, int natoms, const int64_t* numbers, const double* positions,
                             const double* rcov, double cutoff, double kcn, const double* gcn, double* gx, void* stream);
 int d3b200_stage_weights_bwd_f64(size_t n, const int64_t* numbers, const double* cn, const double* refcn,

@@ -88,6 +88,8 @@ for _sfx in ("f64", "f32"):
     _SIGNATURES[f"d3b200_stage_c6_contract_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_disp2_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, C.POINTER(Params), _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_atm_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, C.POINTER(Params), _P, _P], C.c_int)
+    _SIGNATURES[f"d3b200_stage_cn_model_{_sfx}"] = ([_I, _I, _P, _P, _P, C.c_double, C.c_double, _I, _P, _P], C.c_int)
+    _SIGNATURES[f"d3b200_stage_cn_model_bwd_{_sfx}"] = ([_I, _I, _P, _P, _P, C.c_double, C.c_double, _I, _P, _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_cn_bwd_{_sfx}"] = ([_I, _I, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_weights_bwd_{_sfx}"] = ([C.c_size_t, _P, _P, _P, _P, _P, _P], C.c_int)
     _SIGNATURES[f"d3b200_stage_disp2_bwd_{_sfx}"] = ([_I, _I, _P, _P, _P, _P, C.POINTER(Params), _P, _P, _P, _P, _P], C.c_int)

@@ -680,6 +680,24 @@ int stage_cn(int nb, int n, const int64_t* z, const B* x, const B* rcov, double 
   return launched("stage_cn_kernel");
 }
 template <typename B>
+int stage_cn_model(int nb, int n, const int64_t* z, const B* x, const B* rcov, double cutoff, double kcn, int counting,
+                   B* cn, void* st) {
+  if (nb < 0 || n < 0 || !z || !x || !rcov || !cn || counting < 0 || counting > 1) return fail(D3B200_EINVAL, "bad stage_cn_model argument%s");
+  if (!nb || !n) return D3B200_OK;
+  B c = (B)cutoff;
+  d3::stage_cn_kernel<B><<<dim3((n + 127) / 128, nb), 128, 0, (cudaStream_t)st>>>(n, z, x, rcov, c * c, (B)kcn, cn, counting);
+  return launched("stage_cn_kernel");
+}
+template <typename B>
+int stage_cn_model_bwd(int nb, int n, const int64_t* z, const B* x, const B* rcov, double cutoff, double kcn, int counting,
+                       const B* gcn, B* gx, void* st) {
+  if (nb < 0 || n < 0 || !z || !x || !rcov || !gcn || !gx || counting < 0 || counting > 1) return fail(D3B200_EINVAL, "bad stage_cn_model_bwd argument%s");
+  if (!nb || !n) return D3B200_OK;
+  B c = (B)cutoff;
+  d3::stage_cn_bwd_kernel<B><<<dim3((n + 127) / 128, nb), 128, 0, (cudaStream_t)st>>>(n, z, x, rcov, c * c, (B)kcn, gcn, gx, counting);
+  return launched("stage_cn_bwd_kernel");
+}
+template <typename B>
 int stage_weights(size_t n, const int64_t* z, const B* cn, const B* refcn, B* w, void* st) {
   if (!z || !cn || !refcn || !w) return fail(D3B200_EINVAL, "bad stage_weights argument%s");
   if (!n) return D3B200_OK;
@@ -716,7 +734,7 @@ int stage_disp2(int nb, int n, const int64_t* z, const B* x, const B* c6, const 
   if (!nb || !n) return D3B200_OK;
   B c = (B)p->cutoff;
   d3::stage_disp2_kernel<B><<<dim3((n + 127) / 128, nb), 128, 0, (cudaStream_t)st>>>(
-      n, z, x, c6, q, (B)p->s6, (B)p->s8, (B)p->a1, (B)p->a2, c * c, e);
+      n, z, x, c6, q, (B)p->s6, (B)p->s8, (B)p->a1, (B)p->a2, c * c, e, p->damping, (B)(p->alp > 0 ? p->alp : 14.0));
   return launched("stage_disp2_kernel");
 }
 template <typename B>
@@ -753,7 +771,8 @@ int stage_disp2_bwd(int nb, int n, const int64_t* z, const B* x, const B* c6, co
   if (!nb || !n) return D3B200_OK;
   B c = (B)p->cutoff;
   d3::stage_disp2_bwd_kernel<B><<<dim3((n + 127) / 128, nb), 128, 0, (cudaStream_t)st>>>(
-      n, z, x, c6, q, (B)p->s6, (B)p->s8, (B)p->a1, (B)p->a2, c * c, ge, gx, gc6, gpar);
+      n, z, x, c6, q, (B)p->s6, (B)p->s8, (B)p->a1, (B)p->a2, c * c, ge, gx, gc6, gpar, p->damping,
+      (B)(p->alp > 0 ? p->alp : 14.0));
   return launched("stage_disp2_bwd_kernel");
 }
 template <typename B>
@@ -776,6 +795,12 @@ extern "C" {
 #define D3_STAGE_API(SFX, T)                                                                                  \
   int d3b200_stage_cn_##SFX(int nb, int n, const int64_t* z, const T* x, const T* rcov, double cutoff,       \
                             double kcn, T* cn, void* st) { return stage_cn<T>(nb, n, z, x, rcov, cutoff, kcn, cn, st); } \
+  int d3b200_stage_cn_model_##SFX(int nb, int n, const int64_t* z, const T* x, const T* rcov, double cutoff, \
+                                  double kcn, int counting, T* cn, void* st) {                               \
+    return stage_cn_model<T>(nb, n, z, x, rcov, cutoff, kcn, counting, cn, st); }                             \
+  int d3b200_stage_cn_model_bwd_##SFX(int nb, int n, const int64_t* z, const T* x, const T* rcov, double cutoff, \
+                                      double kcn, int counting, const T* gcn, T* gx, void* st) {             \
+    return stage_cn_model_bwd<T>(nb, n, z, x, rcov, cutoff, kcn, counting, gcn, gx, st); }                    \
   int d3b200_stage_weights_##SFX(size_t n, const int64_t* z, const T* cn, const T* refcn, T* w, void* st) {  \
     return stage_weights<T>(n, z, cn, refcn, w, st); }                                                        \
   int d3b200_stage_c6_##SFX(int nb, int n, const int64_t* z, const T* w, const T* refc6, T* c6, void* st) {  \

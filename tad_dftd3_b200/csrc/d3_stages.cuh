@@ -16,7 +16,7 @@ namespace d3 {
 
 template <typename S>
 __global__ void stage_cn_kernel(int natoms, const int64_t* numbers, const S* pos, const S* rcov,
-                                S cutoff2, S kcn, S* cn) {
+                                S cutoff2, S kcn, S* cn, int counting = kCountExp) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= natoms) return;
   const size_t o = (size_t)b * natoms;
@@ -30,8 +30,14 @@ __global__ void stage_cn_kernel(int natoms, const int64_t* numbers, const S* pos
       S r2 = dx * dx + dy * dy + dz * dz;
       if (r2 > cutoff2) continue;
       if (r2 < eps) r2 = eps;
-      S rinv = rsq(r2);
-      acc += rcp(S(1) + ex(-kcn * ((ri + rcov[o + j]) * rinv - S(1))));
+      if (counting == kCountExp) {
+        S rinv = rsq(r2);
+        acc += rcp(S(1) + ex(-kcn * ((ri + rcov[o + j]) * rinv - S(1))));
+      } else {
+        S f, df;
+        counting_pair<S, S>(counting, r2, ri + rcov[o + j], kcn, f, df);
+        acc += f;
+      }
     }
   }
   cn[o + i] = acc;
@@ -133,7 +139,8 @@ __global__ void stage_c6_contract_kernel(int natoms, const int64_t* numbers, con
 
 template <typename S>
 __global__ void stage_disp2_kernel(int natoms, const int64_t* numbers, const S* pos, const S* c6,
-                                   const S* r4r2, S s6, S s8, S a1, S a2, S cutoff2, S* energy) {
+                                   const S* r4r2, S s6, S s8, S a1, S a2, S cutoff2, S* energy,
+                                   int damping = kDampRational, S alp = S(14)) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= natoms) return;
   const size_t o = (size_t)b * natoms;
@@ -148,12 +155,19 @@ __global__ void stage_disp2_kernel(int natoms, const int64_t* numbers, const S* 
       if (r2 > cutoff2) continue;
       if (r2 < eps) r2 = eps;
       S qq = S(3) * qi * r4r2[o + j];
-      S r0 = a1 * sqr(qq) + a2;
-      S r02 = r0 * r0, r06 = r02 * r02 * r02, r08 = r06 * r02;
-      S r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
       S c = c6[(o + i) * natoms + j];
-      e6 += c * rcp(r6 + r06);
-      e8 += (c * qq) * rcp(r8 + r08);
+      if (damping == kDampRational) {
+        S r0 = a1 * sqr(qq) + a2;
+        S r02 = r0 * r0, r06 = r02 * r02 * r02, r08 = r06 * r02;
+        S r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+        e6 += c * rcp(r6 + r06);
+        e8 += (c * qq) * rcp(r8 + r08);
+      } else {
+        S t6, t8, dt6, dt8, t6p1, t6p2, t8p1, t8p2;
+        damping_pair<S, S>(damping, r2, sqr(qq), a1, a2, alp, t6, t8, dt6, dt8, t6p1, t6p2, t8p1, t8p2);
+        e6 += c * t6;
+        e8 += (c * qq) * t8;
+      }
     }
   }
   energy[o + i] = s6 * (S(-0.5) * e6) + s8 * (S(-0.5) * e8);
@@ -209,7 +223,7 @@ __global__ void stage_atm_kernel(int natoms, const int64_t* numbers, const S* po
 // cn_d3: gx_i = sum_j (gcn_i + gcn_j) f'(r_ij) (x_i - x_j) / r_ij       (thread per atom, all partners)
 template <typename S>
 __global__ void stage_cn_bwd_kernel(int natoms, const int64_t* numbers, const S* pos, const S* rcov,
-                                    S cutoff2, S kcn, const S* gcn, S* gx) {
+                                    S cutoff2, S kcn, const S* gcn, S* gx, int counting = kCountExp) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= natoms) return;
   const size_t o = (size_t)b * natoms;
@@ -224,7 +238,7 @@ __global__ void stage_cn_bwd_kernel(int natoms, const int64_t* numbers, const S*
       S r2 = dx * dx + dy * dy + dz * dz;
       if (r2 > cutoff2 || r2 < eps) continue;          // clamped distance: no position dependence
       S f, df;
-      counting_pair<S, S>(kCountExp, r2, ri + rcov[o + j], kcn, f, df);
+      counting_pair<S, S>(counting, r2, ri + rcov[o + j], kcn, f, df);
       const S c = (gi + gcn[o + j]) * df;
       ax += c * dx; ay += c * dy; az += c * dz;
     }
@@ -254,7 +268,7 @@ __global__ void stage_weights_bwd_kernel(size_t n, const int64_t* numbers, const
 template <typename S>
 __global__ void stage_disp2_bwd_kernel(int natoms, const int64_t* numbers, const S* pos, const S* c6,
                                        const S* r4r2, S s6, S s8, S a1, S a2, S cutoff2, const S* ge,
-                                       S* gx, S* gc6, S* gpar) {
+                                       S* gx, S* gc6, S* gpar, int damping = kDampRational, S alp = S(14)) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= natoms) return;
   const size_t o = (size_t)b * natoms;
@@ -273,7 +287,7 @@ __global__ void stage_disp2_bwd_kernel(int natoms, const int64_t* numbers, const
         if (clamped) r2 = eps;
         const S qq = S(3) * qi * r4r2[o + j];
         S t6, t8, dt6, dt8, t6p1, t6p2, t8p1, t8p2;
-        damping_pair<S, S>(kDampRational, r2, sqr(qq), a1, a2, S(14), t6, t8, dt6, dt8, t6p1, t6p2, t8p1, t8p2);
+        damping_pair<S, S>(damping, r2, sqr(qq), a1, a2, alp, t6, t8, dt6, dt8, t6p1, t6p2, t8p1, t8p2);
         const S cij = c6[(o + i) * natoms + j], cji = c6[(o + j) * natoms + i];
         gcij = S(-0.5) * gi * (s6 * t6 + s8 * qq * t8);
         if (!clamped) {

@@ -86,10 +86,10 @@ class _CnD3(torch.autograd.Function):
     """cn_d3 with its VJP with respect to the positions (`d3b200_stage_cn_bwd_*`)."""
 
     @staticmethod
-    def forward(ctx, numbers, positions, rcov, cutoff, kcn):
+    def forward(ctx, numbers, positions, rcov, cutoff, kcn, counting):
         ctx.save_for_backward(numbers, positions, rcov)
-        ctx.cutoff, ctx.kcn = cutoff, kcn
-        return _cn_forward(numbers, positions, rcov, cutoff, kcn)
+        ctx.cutoff, ctx.kcn, ctx.counting = cutoff, kcn, counting
+        return _cn_forward(numbers, positions, rcov, cutoff, kcn, counting)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -102,32 +102,37 @@ class _CnD3(torch.autograd.Function):
         rc = rcov.detach().to(dt).reshape(-1, n).contiguous()
         g = gcn.detach().to(dt).expand(numbers.shape).reshape(-1, n).contiguous()
         gx = torch.empty_like(x)
-        fn = getattr(_lib.lib(), f"d3b200_stage_cn_bwd_{_sfx(dt)}")
+        fn = getattr(_lib.lib(), f"d3b200_stage_cn_model_bwd_{_sfx(dt)}")
         with torch.cuda.device(dev):
-            _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(rc), ctx.cutoff, ctx.kcn, _p(g), _p(gx), _stream(dev)))
-        return None, gx.reshape(positions.shape), None, None, None
+            _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(rc), ctx.cutoff, ctx.kcn, ctx.counting, _p(g), _p(gx),
+                          _stream(dev)))
+        return None, gx.reshape(positions.shape), None, None, None, None
 
 
-def _cn_forward(numbers, positions, rcov, cutoff, kcn):
+def _cn_forward(numbers, positions, rcov, cutoff, kcn, counting=0):
     dt, dev = positions.dtype, positions.device
     n = numbers.shape[-1]
     z = _z(numbers).reshape(-1, n)
     x = positions.detach().reshape(-1, n, 3).contiguous()
     rc = rcov.detach().to(dt).reshape(-1, n).contiguous()
     out = torch.empty(z.shape, dtype=dt, device=dev)
-    fn = getattr(_lib.lib(), f"d3b200_stage_cn_{_sfx(dt)}")
+    fn = getattr(_lib.lib(), f"d3b200_stage_cn_model_{_sfx(dt)}")
     with torch.cuda.device(dev):
-        _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(rc), cutoff, kcn, _p(out), _stream(dev)))
+        _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(rc), cutoff, kcn, counting, _p(out), _stream(dev)))
     return out.reshape(numbers.shape)
 
 
 def cn_d3(numbers, positions, *, counting_function=None, rcov=None, cutoff=None, **kwargs):
-    """D3 coordination number (tad-mctc `cn_d3`, call site disp.py:150-152); differentiable with respect to
-    the positions (first order) on the CUDA kernels."""
-    from .ncoord import exp_count
+    """D3 coordination number (tad-mctc `cn_d3`, call site disp.py:150-152) with `exp_count` (default) or
+    `erf_count`; differentiable with respect to the positions (first order) on the CUDA kernels."""
+    from .ncoord import COUNTING_IDS, exp_count
 
-    if counting_function is not None and counting_function is not exp_count:
-        raise NotImplementedError("the stage-level cn_d3 implements exp_count; erf_count is available through dftd3()")
+    if counting_function is None:
+        counting_function = exp_count
+    if counting_function not in COUNTING_IDS:
+        raise NotImplementedError("cn_d3 implements the counting functions exp_count and erf_count of "
+                                  "tad_dftd3_b200.ncoord as CUDA kernels; other callables are not supported")
+    counting, kcn_default = COUNTING_IDS[counting_function]
     _cuda(positions, "positions")
     _no_grad(rcov)
     dt, dev = positions.dtype, positions.device
@@ -139,10 +144,10 @@ def cn_d3(numbers, positions, *, counting_function=None, rcov=None, cutoff=None,
         raise ValueError(
             f"Shape of positions ({tuple(positions.shape[:-1])}) is not consistent with atomic numbers ({tuple(numbers.shape)})."
         )
-    cut, kcn = _scalar(cutoff, defaults.D3_CN_CUTOFF), float(kwargs.get("kcn", defaults.D3_KCN))
+    cut, kcn = _scalar(cutoff, defaults.D3_CN_CUTOFF), float(kwargs.get("kcn", kcn_default))
     if _wants_grad(positions):
-        return _CnD3.apply(numbers, positions, rcov, cut, kcn)
-    return _cn_forward(numbers, positions, rcov, cut, kcn)
+        return _CnD3.apply(numbers, positions, rcov, cut, kcn, counting)
+    return _cn_forward(numbers, positions, rcov, cut, kcn, counting)
 
 
 class _Weights(torch.autograd.Function):
@@ -321,6 +326,16 @@ def _prep(numbers, positions, c6):
 
 
 _PKEYS2 = (("s6", defaults.S6), ("s8", defaults.S8), ("a1", defaults.A1), ("a2", defaults.A2))
+# zero damping reads (s6, s8, rs6, rs8) in the same four slots (disp._param_vector)
+_PKEYS2_ZERO = (("s6", defaults.S6), ("s8", defaults.S8), ("rs6", 1.0), ("rs8", 1.0))
+
+
+def _params2(pvals, cutoff, model) -> _lib.Params:
+    par = _lib.Params()
+    par.s6, par.s8, par.a1, par.a2 = pvals
+    par.cutoff = cutoff
+    par.damping, par.alp = model
+    return par
 
 
 class _Disp2(torch.autograd.Function):
@@ -328,10 +343,10 @@ class _Disp2(torch.autograd.Function):
     (`d3b200_stage_disp2_bwd_*`)."""
 
     @staticmethod
-    def forward(ctx, numbers, positions, c6, r4r2, pvec, cutoff):
+    def forward(ctx, numbers, positions, c6, r4r2, pvec, cutoff, model):
         ctx.save_for_backward(numbers, positions, c6, r4r2, pvec)
-        ctx.cutoff = cutoff
-        return _disp2_forward(numbers, positions, c6, r4r2, pvec.detach().tolist(), cutoff)
+        ctx.cutoff, ctx.model = cutoff, model
+        return _disp2_forward(numbers, positions, c6, r4r2, pvec.detach().tolist(), cutoff, model)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -339,9 +354,7 @@ class _Disp2(torch.autograd.Function):
         numbers, positions, c6, r4r2, pvec = ctx.saved_tensors
         dt, dev, n, z, x, c = _prep(numbers, positions, c6)
         q = r4r2.detach().to(dt).reshape(-1, n).contiguous()
-        par = _lib.Params()
-        par.s6, par.s8, par.a1, par.a2 = pvec.detach().tolist()
-        par.cutoff = ctx.cutoff
+        par = _params2(pvec.detach().tolist(), ctx.cutoff, ctx.model)
         g = ge.detach().to(dt).expand(numbers.shape).reshape(-1, n).contiguous()
         gx, gc6 = torch.empty_like(x), torch.empty_like(c)
         gpar = torch.empty(z.shape[0], n, 4, dtype=dt, device=dev)
@@ -350,15 +363,13 @@ class _Disp2(torch.autograd.Function):
             _lib.check(fn(z.shape[0], n, _p(z), _p(x), _p(c), _p(q), C.byref(par), _p(g), _p(gx), _p(gc6), _p(gpar),
                           _stream(dev)))
         gp = gpar.sum((0, 1)).to(device=pvec.device, dtype=pvec.dtype) if ctx.needs_input_grad[4] else None
-        return None, gx.reshape(positions.shape), gc6.reshape(c6.shape).to(c6.dtype), None, gp, None
+        return None, gx.reshape(positions.shape), gc6.reshape(c6.shape).to(c6.dtype), None, gp, None, None
 
 
-def _disp2_forward(numbers, positions, c6, r4r2, pvals, cutoff):
+def _disp2_forward(numbers, positions, c6, r4r2, pvals, cutoff, model=(0, defaults.ALP)):
     dt, dev, n, z, x, c = _prep(numbers, positions, c6)
     q = r4r2.detach().to(dt).reshape(-1, n).contiguous()
-    par = _lib.Params()
-    par.s6, par.s8, par.a1, par.a2 = pvals
-    par.cutoff = cutoff
+    par = _params2(pvals, cutoff, model)
     out = torch.empty(z.shape, dtype=dt, device=dev)
     fn = getattr(_lib.lib(), f"d3b200_stage_disp2_{_sfx(dt)}")
     with torch.cuda.device(dev):
@@ -367,24 +378,31 @@ def _disp2_forward(numbers, positions, c6, r4r2, pvals, cutoff):
 
 
 def dispersion2(numbers, positions, param, c6, r4r2, damping_function=None, cutoff=None, **kwargs):
-    """Becke-Johnson two-body energy from a dense c6 (disp.py:245-302); differentiable (first order) with respect
-    to positions, c6 and the parameters s6, s8, a1, a2."""
-    from .damping import rational_damping
+    """Two-body energy from a dense c6 (disp.py:245-302) with `rational_damping` (Becke-Johnson, default) or
+    `zero_damping`; differentiable (first order) with respect to positions, c6 and the parameters s6, s8 and
+    a1, a2 (rs6, rs8 for zero damping)."""
+    from .damping import DAMPING_IDS, rational_damping
 
-    if damping_function is not None and damping_function is not rational_damping or kwargs:
-        raise NotImplementedError("the stage-level dispersion2 implements rational_damping; zero_damping is available through dftd3()")
-    _no_grad(r4r2)
+    if damping_function is None:
+        damping_function = rational_damping
+    if damping_function not in DAMPING_IDS or kwargs:
+        raise NotImplementedError("dispersion2 implements the damping functions rational_damping and zero_damping "
+                                  "of tad_dftd3_b200.damping as CUDA kernels; other callables / keyword arguments "
+                                  "are not supported")
+    damping = DAMPING_IDS[damping_function]
+    _no_grad(r4r2, param.get("alp"))
     _cuda(positions, "positions")
     cut = _scalar(cutoff, defaults.D3_DISP_CUTOFF)
-    vals = [param.get(k, d) for k, d in _PKEYS2]
+    model = (damping, _scalar(param.get("alp"), defaults.ALP))
+    vals = [param.get(k, d) for k, d in (_PKEYS2 if damping == 0 else _PKEYS2_ZERO)]
     if _wants_grad(positions, c6, *vals):
         dt = positions.dtype
         live = [v for v in vals if isinstance(v, Tensor) and v.requires_grad]
         pdev = live[0].device if live else torch.device("cpu")
         pvec = torch.stack([(v.to(device=pdev, dtype=dt) if isinstance(v, Tensor)
                              else torch.tensor(float(v), dtype=dt, device=pdev)).reshape(()) for v in vals])
-        return _Disp2.apply(numbers, positions, c6, r4r2, pvec, cut)
-    return _disp2_forward(numbers, positions, c6, r4r2, [_scalar(v) for v in vals], cut)
+        return _Disp2.apply(numbers, positions, c6, r4r2, pvec, cut, model)
+    return _disp2_forward(numbers, positions, c6, r4r2, [_scalar(v) for v in vals], cut, model)
 
 
 class _Atm(torch.autograd.Function):

@@ -506,6 +506,75 @@ def test_stage_vjps_gradcheck():
         d3.ncoord.cn_d3(numbers, positions, rcov=rcov[numbers].clone().requires_grad_(True))
 
 
+def test_stage_functions_with_erf_count_and_zero_damping():
+    """The stage-level hooks take the same non-default callables as dftd3() (disp.py:89-91): cn_d3 with erf_count
+    and dispersion2 with zero_damping.  Each VJP against finite differences, and the composed pipeline against
+    dftd3() with the same callables (which tests/golden/reference_models.npz pins to the unmodified reference)."""
+    import tad_dftd3_b200 as d3
+    from tad_dftd3_b200 import synthetic as syn
+    from tad_dftd3_b200.damping import zero_damping
+    from tad_dftd3_b200.ncoord import erf_count
+
+    dt = torch.double
+    numbers, positions = syn.water_cluster(4, seed=5)
+    numbers = torch.cat([numbers, torch.tensor([0])]).to(DEV)
+    positions = torch.cat([positions, torch.zeros(1, 3, dtype=dt)]).to(DEV)
+    refcn, refc6, rcov, r4r2, rvdw = tables(dt, DEV)
+    ref = d3.Reference(cn=refcn, c6=refc6)
+    gc = dict(eps=1e-6, atol=1e-8, rtol=1e-6, nondet_tol=1e-12)
+    x = positions.clone().requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda p: d3.ncoord.cn_d3(numbers, p, counting_function=erf_count), (x,), **gc)
+    # elementwise formula of the callable == the kernel's counting function
+    with torch.no_grad():
+        cn_k = d3.ncoord.cn_d3(numbers, positions, counting_function=erf_count)
+        real = numbers != 0
+        d = torch.cdist(positions, positions)
+        r0 = rcov[numbers].unsqueeze(-1) + rcov[numbers].unsqueeze(-2)
+        mask = real.unsqueeze(-1) & real.unsqueeze(-2) & ~torch.eye(len(numbers), dtype=torch.bool, device=DEV) & (d <= 25.0)
+        cf = torch.where(mask, erf_count(torch.where(mask, d, torch.ones_like(d)), r0), torch.zeros_like(d))
+    assert_close(cn_k.cpu(), cf.sum(-1).cpu(), RTOL, ATOL, "erf_count cn")
+
+    par = {k: torch.tensor(v, dtype=dt, device=DEV, requires_grad=True)
+           for k, v in (("s6", 1.0), ("s8", 1.2), ("rs6", 1.1), ("rs8", 0.9))}
+    with torch.no_grad():
+        c6 = d3.model.atomic_c6(numbers, d3.model.weight_references(numbers, cn_k, ref), ref)
+    c6r = (c6 * (1.0 + 0.1 * torch.rand_like(c6))).requires_grad_(True)
+    q = r4r2[numbers]
+
+    def e2(p, c, s6, s8, rs6, rs8):
+        return d3.disp.dispersion2(numbers, p, {"s6": s6, "s8": s8, "rs6": rs6, "rs8": rs8, "alp": torch.tensor(14.0)},
+                                   c, q, zero_damping, None)
+
+    assert torch.autograd.gradcheck(e2, (x, c6r, *par.values()), **gc)
+
+    # composed pipeline == fused dftd3() with the same callables: energy, gradient, parameter gradients
+    for atm in (False, True):
+        vals = {"s6": 1.0, "s8": 1.2, "rs6": 1.1, "rs8": 0.9, "alp": 14.0}
+        if atm:
+            vals["s9"] = 1.0
+        pa = {k: torch.tensor(v, dtype=dt, device=DEV, requires_grad=k in ("s6", "s8", "rs6", "rs8")) for k, v in vals.items()}
+        pb = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in pa.items()}
+        xa, xb = positions.clone().requires_grad_(True), positions.clone().requires_grad_(True)
+        cn = d3.ncoord.cn_d3(numbers, xa, counting_function=erf_count, rcov=rcov[numbers])
+        c6 = d3.model.atomic_c6(numbers, d3.model.weight_references(numbers, cn, ref), ref)
+        ea = d3.disp.dispersion(numbers, xa, pa, c6, rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)],
+                                r4r2=q, damping_function=zero_damping)
+        eb = d3.dftd3(numbers, xb, pb, ref=ref, rvdw=rvdw[numbers.unsqueeze(-1), numbers.unsqueeze(-2)],
+                      counting_function=erf_count, damping_function=zero_damping)
+        assert_close(ea.detach().cpu(), eb.detach().cpu(), RTOL, ATOL, f"stage energy (erf, zero, atm={atm})")
+        keys = ("s6", "s8", "rs6", "rs8")
+        ga = torch.autograd.grad(ea.sum(), [xa] + [pa[k] for k in keys])
+        gb = torch.autograd.grad(eb.sum(), [xb] + [pb[k] for k in keys])
+        assert_close(ga[0].cpu(), gb[0].cpu(), RTOL, ATOL, f"stage gradient (erf, zero, atm={atm})")
+        assert_close(np.asarray([float(v) for v in ga[1:]]), np.asarray([float(v) for v in gb[1:]]), 1e-9, 1e-12,
+                     f"stage pgrad (erf, zero, atm={atm})")
+    # unknown callables are still refused
+    with pytest.raises(NotImplementedError):
+        d3.ncoord.cn_d3(numbers, positions, counting_function=lambda r, r0, kcn=1.0: r)
+    with pytest.raises(NotImplementedError):
+        d3.disp.dispersion2(numbers, positions, {}, c6.detach(), q, lambda *a, **k: None, None)
+
+
 def test_atomic_c6_is_differentiable_like_the_reference_op(runs):
     """atomic_c6 w.r.t. the weights: VJP against autograd through the oracle's dense
     einsum, gradcheck / gradgradcheck (reference test_c6.py:223-262) and vmap."""
