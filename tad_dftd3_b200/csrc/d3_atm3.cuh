@@ -27,7 +27,15 @@
 //    added to the global arrays with five fp64 atomics per 32 triples; the i-side
 //    sums stay in registers until the centre is finished;
 //  * C6_jk and its two CN derivatives are 7-wide dots of the lane's w_k / dw_k
-//    with the pre-contracted vectors T_j[e_k], Td_j[e_k] (`system_tvec_kernel`).
+//    with the pre-contracted vectors T_j[e_k], Td_j[e_k] (`system_tvec_kernel`);
+//  * TAB variant: everything of a triple that depends on ONE edge is the same for every centre whose list holds
+//    both ends (hundreds at a 25 Bohr cutoff): sqrt|C6_jk| and the two logarithmic CN derivatives of C6_jk, and,
+//    because the damping argument and the distance product factorise over the edges,
+//      (r0/r)^p = prod_ab (rs9 R_ab / r_ab)^p,   1/(r_ij r_ik r_jk) = prod_ab 1/r_ab,
+//    also U_ab = (rs9 R_ab / r_ab)^p and 1/r_ab.  `system_atm_pairtab_kernel` computes them ONCE per pair into a
+//    dense [natoms][natoms] table of 48-byte entries (upper triangle); the records carry them for the edges at
+//    the centre.  The sweep then reads 1.5 - 2 sectors per lane and triple instead of three 7-wide dots, a square
+//    root, a reciprocal, a reciprocal square root and the power.  Used while the table fits `atm_work` (d3b200.h).
 #pragma once
 #include "d3_atm.cuh"
 
@@ -43,8 +51,14 @@ namespace d3 {
 constexpr int kAtm3Kpl = D3_ATM3_KPL;
 constexpr int kAtm3Warps = D3_ATM3_WARPS;
 constexpr int kAtm3Ctas = D3_ATM3_CTAS;         // resident CTAs per SM the kernel is built for
+#ifndef D3_ATM3_TAB_CTAS
+#define D3_ATM3_TAB_CTAS D3_ATM3_CTAS
+#endif
+constexpr int kAtm3TabCtas = D3_ATM3_TAB_CTAS;  // ... of the pair-table variant (fewer live registers)
+
 constexpr int kAtm3Rec = 12;         // reals per neighbour record (11 used), 16-byte aligned pairs
 constexpr int kAtm3RedStride = 40;   // row stride of the reduction tile (rows 16 banks apart)
+constexpr int kAtm3Tab = 6;          // reals per entry of the pair table (5 used)
 
 template <typename S>
 struct AtmArgs3 {
@@ -56,12 +70,16 @@ struct AtmArgs3 {
                    // < 0: the atoms row_begin + k * |tile_stride| below row_end
   int parts;       // a centre is split into `parts` work units (every parts-th tile of its list): keeps
                    // the persistent CTAs busy when a launch owns few centres (several GPUs)
+  const S* tab;    // TAB variant: [natoms][natoms][kAtm3Tab] pair table of `system_atm_pairtab_kernel`, else unused
 };
 
 template <typename S>
 inline size_t atm3_workspace_bytes(int natoms, int grid) {
-  return 256 + (size_t)grid * natoms * (sizeof(int) + kAtm3Rec * sizeof(S));
+  const size_t b = 256 + (size_t)grid * natoms * (sizeof(int) + kAtm3Rec * sizeof(S));
+  return (b + 255) / 256 * 256;
 }
+template <typename S>
+inline size_t atm3_pairtab_bytes(int natoms) { return (size_t)natoms * natoms * kAtm3Tab * sizeof(S); }
 
 // Column sums of vals[V] over the 32 lanes through this warp's tile [V][kAtm3RedStride].
 // On return lanes 4r .. 4r+3 hold the total of row r (r < V <= 8).
@@ -110,6 +128,12 @@ __device__ __forceinline__ S pow16_3_fast(S x) {
   return c8 * c8;
 }
 
+// (rs9 R / r)^p of one edge (damping/atm.py:133-135 per edge); the power of a triple is the product of its three
+template <typename S>
+__device__ __forceinline__ S atm_edge_pow(S base, S pexp, int cube_root_pow) {
+  return cube_root_pow ? pow16_3_fast<S>(base) : fex(fmx(pexp * lg(base), S(-700)));
+}
+
 // Largest number of neighbours within the cutoff of any atom: sizes the per-CTA slots of the neighbour scratch
 // of `system_atm3_kernel` (slots of `natoms` entries, 1 MB apart, alias in the L2 sets and were written back
 // to DRAM at 50x the algorithmic bytes, profiles/r1h_system_atm3_raw.csv).  One warp per 32-atom sub-tile,
@@ -150,11 +174,67 @@ __global__ void __launch_bounds__(32 * kMaxnWarps) system_atm_maxn_kernel(SysArg
   }
 }
 
+// Pair table of the TAB variant: entry [j][k] (k > j; the blocks on the diagonal are written completely) =
+//   { sqrt(|C6_jk| + tiny), U_jk = (rs9 R_jk / r_jk)^p, 1 / r_jk, (dC6_jk/dCN_j) / C6_jk, (dC6_jk/dCN_k) / C6_jk, - }
+// with C6_jk = sum_a w_k[a] T_j[e_k][a] in the summation order of the sweep (damping/atm.py:93-100, model/c6.py:81-87).
+// One CTA per (128 columns k, 32 rows j); a thread owns a column, the T / Td vectors of the rows sit in shared memory.
+constexpr int kPairTabCols = 128, kPairTabRows = 32;
+template <typename S>
+__global__ void __launch_bounds__(kPairTabCols) system_atm_pairtab_kernel(AtmArgs2<S> P, S* tab) {
+  __shared__ __align__(16) S sT[kPairTabRows * kAtmEmax * 8];
+  __shared__ __align__(16) S sTd[kPairTabRows * kAtmEmax * 8];
+  __shared__ S rv[kAtmEmax * kAtmEmax];
+  __shared__ int sej[kPairTabRows];
+  __shared__ S sx[kPairTabRows], sy[kPairTabRows], sz[kPairTabRows];
+  const SysArgs<S>& A = P.sys;
+  const int natoms = A.natoms, E = P.nelem;
+  const int k0 = blockIdx.x * kPairTabCols, j0 = blockIdx.y * kPairTabRows;
+  if (k0 + kPairTabCols <= j0) return;                  // block entirely below the diagonal
+  const int tid = threadIdx.x;
+  const size_t toff = (size_t)j0 * E * 8, tdoff = (size_t)natoms * E * 8;
+  for (int q = tid; q < kPairTabRows * E * 8; q += kPairTabCols) { sT[q] = P.tvec[toff + q]; sTd[q] = P.tvec[tdoff + toff + q]; }
+  for (int q = tid; q < E * E; q += kPairTabCols) rv[q] = P.rvdw_e[q];
+  if (tid < kPairTabRows) {
+    sej[tid] = P.eidx[j0 + tid];
+    const Atom4<S> aj = A.atoms[j0 + tid];
+    sx[tid] = aj.x; sy[tid] = aj.y; sz[tid] = aj.z;
+  }
+  __syncthreads();
+  const int k = k0 + tid;
+  if (k >= natoms) return;
+  const int ek = P.eidx[k];
+  if (ek < 0) return;                                   // padding column: never in a neighbour list
+  S wk[kNRef], dwk[kNRef];
+#pragma unroll
+  for (int a = 0; a < kNRef; ++a) { wk[a] = A.w[8 * (size_t)k + a]; dwk[a] = A.dw[8 * (size_t)k + a]; }
+  const Atom4<S> ak = A.atoms[k];
+  const S tiny = tiny_of<S>();
+  for (int jj = 0; jj < kPairTabRows; ++jj) {
+    const int ej = sej[jj];
+    if (ej < 0) continue;                               // CTA-uniform
+    const S* T = sT + (jj * E + ek) * 8;
+    const S* Td = sTd + (jj * E + ek) * 8;
+    S c6 = wk[0] * T[0], dk = dwk[0] * T[0], dj = wk[0] * Td[0];
+#pragma unroll
+    for (int a = 1; a < kNRef; ++a) { c6 += wk[a] * T[a]; dk += dwk[a] * T[a]; dj += wk[a] * Td[a]; }
+    const S x = ab(c6) + tiny;
+    const S ic = rcp0(c6);
+    const S dx = sx[jj] - ak.x, dy = sy[jj] - ak.y, dz = sz[jj] - ak.z;
+    const S rinv = frsq(dx * dx + dy * dy + dz * dz + tiny);
+    const S U = atm_edge_pow<S>((P.rs9 * rv[ej * E + ek]) * rinv, P.pexp, P.cube_root_pow);
+    Pair2<S>* out = reinterpret_cast<Pair2<S>*>(tab + ((size_t)(j0 + jj) * natoms + k) * kAtm3Tab);
+    Pair2<S> q;
+    q.a = x * frsq(x); q.b = U; out[0] = q;
+    q.a = rinv; q.b = dj * ic; out[1] = q;
+    q.a = dk * ic; q.b = S(0); out[2] = q;
+  }
+}
+
 // record slots
 enum { kRx = 0, kRy, kRz, kRidx, kRh, kRr2, kRinv, kRci, kRcn, kRvdw, kRg, kRe };
 
-template <typename S, bool WANT_G>
-__global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel(AtmArgs3<S> Q) {
+template <typename S, bool WANT_G, bool TAB = false>
+__global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Ctas) system_atm3_kernel(AtmArgs3<S> Q) {
   const AtmArgs2<S>& P = Q.a;
   const SysArgs<S>& A = P.sys;
   constexpr int nw = kAtm3Warps;
@@ -164,7 +244,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
   __shared__ S rv[kAtmEmax * kAtmEmax];
   __shared__ __align__(16) S wiS[16];
   __shared__ __align__(16) S red[nw * 7 * kAtm3RedStride];
-  __shared__ S wsh[nw][KPL][2 * kNRef][32];         // w_k, dw_k of each warp's tile, [k of the lane][a][lane]
+  __shared__ S wsh[TAB ? 1 : nw][KPL][2 * kNRef][32];   // w_k, dw_k of each warp's tile, [k of the lane][a][lane]
   __shared__ S isum[nw][5];
   __shared__ int cnt[nw];
   __shared__ int s_center, s_tile;
@@ -250,8 +330,15 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       q.a = an.z; q.b = int_as(nn, S(0)); r[1] = q;
       q.a = sqr(ab(c6) + tiny); q.b = r2; r[2] = q;
       q.a = frcp(r2); q.b = d_i * ic6; r[3] = q;
-      q.a = d_n * ic6; q.b = rv[ei * E + en]; r[4] = q;
-      q.a = A.aux[nn].b; q.b = int_as(en, S(0)); r[5] = q;
+      if (TAB) {
+        // edge factors of the damping power and of 1/(r_ij r_ik r_jk)
+        const S rinv = frsq(r2);
+        q.a = d_n * ic6; q.b = atm_edge_pow<S>((P.rs9 * rv[ei * E + en]) * rinv, P.pexp, P.cube_root_pow); r[4] = q;
+        q.a = A.aux[nn].b; q.b = rinv; r[5] = q;
+      } else {
+        q.a = d_n * ic6; q.b = rv[ei * E + en]; r[4] = q;
+        q.a = A.aux[nn].b; q.b = int_as(en, S(0)); r[5] = q;
+      }
     }
     const int ntile = (n + TK - 1) / TK;
     if (tid == 0) s_tile = (ntile - 1 - part + parts) / parts - 1;   // tiles part, part + parts, ... of this unit
@@ -269,8 +356,9 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
       int kpos[KPL];
       bool kvalid[KPL];
       const Pair2<S>* rk[KPL];
-      S akx[KPL], aky[KPL], akz[KPL], hik[KPL], b2[KPL], inv_b[KPL], Rik[KPL], gk[KPL];
-      unsigned ekoff[KPL];
+      S akx[KPL], aky[KPL], akz[KPL], hik[KPL], b2[KPL], inv_b[KPL], Rik[KPL], gk[KPL];   // Rik: TAB: U_ik
+      S rinvk[KPL];                                                                        // TAB: 1 / r_ik
+      unsigned ekoff[KPL];       // !TAB: offset of T_j[e_k]; TAB: offset of column k in a table row
       const S* rvk[KPL];
       S Sfb[KPL], Swe[KPL], Ek[KPL], Vx[KPL], Vy[KPL], Vz[KPL], Dk[KPL];
       __syncwarp();
@@ -282,13 +370,16 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
         const Pair2<S> k0_ = rk[kk][0], k2_ = rk[kk][2];
         akx[kk] = k0_.a; aky[kk] = k0_.b; akz[kk] = rk[kk][1].a;
         hik[kk] = k2_.a; b2[kk] = k2_.b; inv_b[kk] = rk[kk][3].a; Rik[kk] = rk[kk][4].b; gk[kk] = rk[kk][5].a;
-        const int kidx = as_int(rk[kk][1].b), ek = as_int(rk[kk][5].b);
+        const int kidx = as_int(rk[kk][1].b), ek = TAB ? 0 : as_int(rk[kk][5].b);
+        rinvk[kk] = TAB ? rk[kk][5].b : S(0);
+        if (!TAB) {
 #pragma unroll
-        for (int a = 0; a < kNRef; ++a) {
-          wsh[wid][kk][a][lane] = A.w[8 * (size_t)kidx + a];
-          if (WANT_G) wsh[wid][kk][kNRef + a][lane] = A.dw[8 * (size_t)kidx + a];
+          for (int a = 0; a < kNRef; ++a) {
+            wsh[wid][kk][a][lane] = A.w[8 * (size_t)kidx + a];
+            if (WANT_G) wsh[wid][kk][kNRef + a][lane] = A.dw[8 * (size_t)kidx + a];
+          }
         }
-        ekoff[kk] = (unsigned)ek * 8;
+        ekoff[kk] = TAB ? (unsigned)kidx * (unsigned)kAtm3Tab : (unsigned)ek * 8;
         rvk[kk] = rv + ek;
         Sfb[kk] = Swe[kk] = Ek[kk] = Vx[kk] = Vy[kk] = Vz[kk] = Dk[kk] = S(0);
       }
@@ -313,9 +404,10 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
         if (!__any_sync(0xffffffffu, any_act)) continue;
         const Pair2<S> j2_ = rj[2], j3_ = rj[3], j4_ = rj[4], j5_ = rj[5];
         const S hij = j2_.a, a2 = j2_.b, inv_a = j3_.a;
-        const int ej = as_int(j5_.b);
+        const int ej = TAB ? 0 : as_int(j5_.b);
         const unsigned jbase = (unsigned)jidx * (unsigned)E * 8u;
-        const S r0j = rs93 * j4_.b;
+        const S* tabrow = TAB ? Q.tab + (size_t)jidx * natoms * kAtm3Tab : nullptr;
+        const S r0j = rs93 * j4_.b;                      // TAB: j4_.b = U_ij, j5_.b = 1 / r_ij
         S vals[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) vals[v] = S(0);
@@ -324,21 +416,41 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
 #pragma unroll
         for (int kk = 0; kk < KPL; ++kk) {
           const S* Tjp = tvec + (jbase + ekoff[kk]);
-          const Pair2<S>* Tj2 = reinterpret_cast<const Pair2<S>*>(Tjp);
           S Tj[8];
+          S c6jk = S(0), hjk;
+          Pair2<S> t0, t1, t2;                           // TAB: {sqrt|C6_jk|, U_jk}, {1/r_jk, dlnC6/dCN_j}, {dlnC6/dCN_k, -}
+          if (TAB) {
+            t0.a = t0.b = t1.a = t1.b = t2.a = t2.b = S(0);
+            if (act[kk]) {
+              const Pair2<S>* tp = reinterpret_cast<const Pair2<S>*>(tabrow + ekoff[kk]);
+              t0 = tp[0];
+              t1 = tp[1];
+              if (WANT_G) t2 = tp[2];
+            }
+            hjk = t0.a;
+          } else {
+            const Pair2<S>* Tj2 = reinterpret_cast<const Pair2<S>*>(Tjp);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { const Pair2<S> pp = Tj2[q]; Tj[2 * q] = pp.a; Tj[2 * q + 1] = pp.b; }
-          S c6jk = wsh[wid][kk][0][lane] * Tj[0];
+            for (int q = 0; q < 4; ++q) { const Pair2<S> pp = Tj2[q]; Tj[2 * q] = pp.a; Tj[2 * q + 1] = pp.b; }
+            c6jk = wsh[wid][kk][0][lane] * Tj[0];
 #pragma unroll
-          for (int a = 1; a < kNRef; ++a) c6jk += wsh[wid][kk][a][lane] * Tj[a];
-          const S xjk = ab(c6jk) + tiny;
-          const S hjk = xjk * frsq(xjk);
+            for (int a = 1; a < kNRef; ++a) c6jk += wsh[wid][kk][a][lane] * Tj[a];
+            const S xjk = ab(c6jk) + tiny;
+            hjk = xjk * frsq(xjk);
+          }
           const S c9 = P.s9 * (hij * (hik[kk] * hjk));
-          const S r0 = r0j * (Rik[kk] * rvk[kk][ej * E]);
           const S c2 = c2e[kk] + tiny;
           const S ab2 = a2 * b2[kk];
-          const S r2 = ab2 * c2;
-          const S r1inv = frsq(r2);
+          S r1inv, u;
+          if (TAB) {
+            // inactive lanes: zeros from the table -> r1inv = u = 0, fd = 1, everything selected away below
+            r1inv = (j5_.b * rinvk[kk]) * t1.a;
+            u = (j4_.b * Rik[kk]) * t0.b;
+          } else {
+            const S r0 = r0j * (Rik[kk] * rvk[kk][ej * E]);
+            r1inv = frsq(ab2 * c2);
+            u = atm_edge_pow<S>(r0 * r1inv, P.pexp, P.cube_root_pow);
+          }
           const S r1inv2 = r1inv * r1inv;
           const S r3inv = r1inv2 * r1inv;
           const S r5inv = r3inv * r1inv2;
@@ -346,8 +458,6 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
           const S s = p * q * tt;
           const S sr5 = s * r5inv;
           const S ang = S(0.375) * sr5 + r3inv;
-          const S base = r0 * r1inv;
-          const S u = P.cube_root_pow ? pow16_3_fast<S>(base) : fex(fmx(P.pexp * lg(base), S(-700)));
           const S fd = frcp(S(1) + S(6) * u);
           const S e = act[kk] ? c9 * (ang * fd) : S(0);
           const S share = mjk[kk] ? S(2) : S(1);       // 1 + m_jk
@@ -371,17 +481,23 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, kAtm3Ctas) system_atm3_kernel
             Swe[kk] += we;
             const S vx = fc * dxjk[kk], vy = fc * dyjk[kk], vz = fc * dzjk[kk];
             Vx[kk] += vx; Vy[kk] += vy; Vz[kk] += vz;
-            const Pair2<S>* Td2 = reinterpret_cast<const Pair2<S>*>(Tjp + tdoff);
-            S Td[8];
-#pragma unroll
-            for (int q2 = 0; q2 < 4; ++q2) { const Pair2<S> pp = Td2[q2]; Td[2 * q2] = pp.a; Td[2 * q2 + 1] = pp.b; }
-            S dk = wsh[wid][kk][kNRef][lane] * Tj[0], dj = wsh[wid][kk][0][lane] * Td[0];
-#pragma unroll
-            for (int a = 1; a < kNRef; ++a) { dk += wsh[wid][kk][kNRef + a][lane] * Tj[a]; dj += wsh[wid][kk][a][lane] * Td[a]; }
-            const S qc = act[kk] ? we * rcp0(c6jk) : S(0);
-            Dk[kk] += qc * dk;
             vals[1 % NV] += fa; vals[2 % NV] += we; vals[3 % NV] += vx; vals[4 % NV] += vy; vals[5 % NV] += vz;
-            vals[6 % NV] += qc * dj;
+            if (TAB) {
+              // inactive lanes: we == 0 and the table values are zeros (not loaded)
+              Dk[kk] += we * t2.a;
+              vals[6 % NV] += we * t1.b;
+            } else {
+              const Pair2<S>* Td2 = reinterpret_cast<const Pair2<S>*>(Tjp + tdoff);
+              S Td[8];
+#pragma unroll
+              for (int q2 = 0; q2 < 4; ++q2) { const Pair2<S> pp = Td2[q2]; Td[2 * q2] = pp.a; Td[2 * q2 + 1] = pp.b; }
+              S dk = wsh[wid][kk][kNRef][lane] * Tj[0], dj = wsh[wid][kk][0][lane] * Td[0];
+#pragma unroll
+              for (int a = 1; a < kNRef; ++a) { dk += wsh[wid][kk][kNRef + a][lane] * Tj[a]; dj += wsh[wid][kk][a][lane] * Td[a]; }
+              const S qc = act[kk] ? we * rcp0(c6jk) : S(0);
+              Dk[kk] += qc * dk;
+              vals[6 % NV] += qc * dj;
+            }
           }
         }
         // ---- j side of this step: sums over the 32 lanes, five atomics

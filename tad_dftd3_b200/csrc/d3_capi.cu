@@ -601,6 +601,20 @@ int atm3_grid() {
   return nsm * d3::kAtm3Ctas;
 }
 
+// Largest pair table (bytes) the triples-once ATM kernel may place in `atm_work`: 32 natoms^2 bytes in fp64
+// (3.2 GB for 10 k atoms).  Beyond it the sweep contracts C6_jk on the fly.  $D3B200_ATM_PAIRTAB_MAX_BYTES, 0 = never.
+size_t atm3_pairtab_limit() {
+  const char* e = getenv("D3B200_ATM_PAIRTAB_MAX_BYTES");
+  if (e && *e) return (size_t)strtoull(e, nullptr, 10);
+  return (size_t)8 << 30;
+}
+template <typename B>
+size_t atm3_total_workspace_bytes(int natoms) {
+  const size_t scratch = d3::atm3_workspace_bytes<B>(natoms, atm3_grid());
+  const size_t tab = d3::atm3_pairtab_bytes<B>(natoms);
+  return tab <= atm3_pairtab_limit() ? scratch + tab : scratch;
+}
+
 template <typename B>
 int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B* rvdw, int want_grad, void* stream) {
   d3::AtmArgs<B> p;
@@ -647,6 +661,19 @@ int sys_atm(const typename SysOf<B>::type* s, const d3b200_params* par, const B*
       if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
       // largest neighbour count -> stride of the per-CTA neighbour slots (keeps the scratch L2-resident)
       d3::system_atm_maxn_kernel<B><<<p.sys.natoms / d3::kSysSub, 32 * d3::kMaxnWarps, 0, st>>>(p.sys, q.eidx, r.counter + 1);
+      const size_t scratch = d3::atm3_workspace_bytes<B>(p.sys.natoms, grid);
+      const size_t tabb = d3::atm3_pairtab_bytes<B>(p.sys.natoms);
+      r.tab = nullptr;
+      if (tabb <= atm3_pairtab_limit() && s->atm_work_bytes >= scratch + tabb) {
+        // everything that belongs to an edge jk alone, once per pair (upper triangle of a dense table)
+        B* tab = reinterpret_cast<B*>(wsp + scratch);
+        r.tab = tab;
+        const dim3 tg((p.sys.natoms + d3::kPairTabCols - 1) / d3::kPairTabCols, p.sys.natoms / d3::kPairTabRows);
+        d3::system_atm_pairtab_kernel<B><<<tg, d3::kPairTabCols, 0, st>>>(q, tab);
+        if (want_grad) d3::system_atm3_kernel<B, true, true><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
+        else d3::system_atm3_kernel<B, false, true><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
+        return launched("system_atm3_kernel");
+      }
       if (want_grad) d3::system_atm3_kernel<B, true><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
       else d3::system_atm3_kernel<B, false><<<grid, 32 * d3::kAtm3Warps, 0, st>>>(r);
       return launched("system_atm3_kernel");
@@ -828,8 +855,8 @@ D3_STAGE_API(f64, double)
 D3_STAGE_API(f32, float)
 #undef D3_STAGE_API
 
-size_t d3b200_system_atm_workspace_bytes_f64(int natoms) { return natoms > 0 ? d3::atm3_workspace_bytes<double>(natoms, atm3_grid()) : 0; }
-size_t d3b200_system_atm_workspace_bytes_f32(int natoms) { return natoms > 0 ? d3::atm3_workspace_bytes<float>(natoms, atm3_grid()) : 0; }
+size_t d3b200_system_atm_workspace_bytes_f64(int natoms) { return natoms > 0 ? atm3_total_workspace_bytes<double>(natoms) : 0; }
+size_t d3b200_system_atm_workspace_bytes_f32(int natoms) { return natoms > 0 ? atm3_total_workspace_bytes<float>(natoms) : 0; }
 int d3b200_system_atm_f64(const d3b200_system_f64* s, const d3b200_params* p, const double* r, int g, void* st) { return sys_atm<double>(s, p, r, g, st); }
 int d3b200_system_atm_f32(const d3b200_system_f32* s, const d3b200_params* p, const float* r, int g, void* st) { return sys_atm<float>(s, p, r, g, st); }
 int d3b200_system_tvec_f64(const d3b200_system_f64* s, const d3b200_params* p, void* st) { return sys_tvec<double>(s, p, st); }
