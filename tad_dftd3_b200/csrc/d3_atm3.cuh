@@ -31,11 +31,12 @@
 //  * TAB variant: everything of a triple that depends on ONE edge is the same for every centre whose list holds
 //    both ends (hundreds at a 25 Bohr cutoff): sqrt|C6_jk| and the two logarithmic CN derivatives of C6_jk, and,
 //    because the damping argument and the distance product factorise over the edges,
-//      (r0/r)^p = prod_ab (rs9 R_ab / r_ab)^p,   1/(r_ij r_ik r_jk) = prod_ab 1/r_ab,
-//    also U_ab = (rs9 R_ab / r_ab)^p and 1/r_ab.  `system_atm_pairtab_kernel` computes them ONCE per pair into a
-//    dense [natoms][natoms] table of 48-byte entries (upper triangle); the records carry them for the edges at
-//    the centre.  The sweep then reads 1.5 - 2 sectors per lane and triple instead of three 7-wide dots, a square
-//    root, a reciprocal, a reciprocal square root and the power.  Used while the table fits `atm_work` (d3b200.h).
+//      (r0/r)^p = prod_ab (rs9 R_ab / r_ab)^p,
+//    also U_ab = (rs9 R_ab / r_ab)^p.  `system_atm_pairtab_kernel` computes them ONCE per pair into a dense
+//    [natoms][natoms] table of 32-byte entries (upper triangle); the records carry U for the edges at the
+//    centre.  The sweep then reads one sector per lane and triple instead of three 7-wide dots, a square
+//    root, a reciprocal and the power, and needs the values only at the end of a triple's dependency chain.
+//    Used while the table fits `atm_work` (d3b200.h).
 #pragma once
 #include "d3_atm.cuh"
 
@@ -55,10 +56,15 @@ constexpr int kAtm3Ctas = D3_ATM3_CTAS;         // resident CTAs per SM the kern
 #define D3_ATM3_TAB_CTAS D3_ATM3_CTAS
 #endif
 constexpr int kAtm3TabCtas = D3_ATM3_TAB_CTAS;  // ... of the pair-table variant (fewer live registers)
+#ifndef D3_ATM3_JEARLY
+#define D3_ATM3_JEARLY 1                        // whole record of list entry j loaded at the top of a step
+#endif
+
+
 
 constexpr int kAtm3Rec = 12;         // reals per neighbour record (11 used), 16-byte aligned pairs
 constexpr int kAtm3RedStride = 40;   // row stride of the reduction tile (rows 16 banks apart)
-constexpr int kAtm3Tab = 6;          // reals per entry of the pair table (5 used)
+constexpr int kAtm3Tab = 4;          // reals per entry of the pair table (one 32-byte sector in fp64)
 
 template <typename S>
 struct AtmArgs3 {
@@ -102,6 +108,21 @@ __device__ __forceinline__ S warp_rows_reduce(const S (&vals)[V], S* tile, int l
   tot += shx(tot, 2);
   __syncwarp();
   return tot;
+}
+
+// One 16-byte half of a pair-table entry, loaded only where `on` (zeros elsewhere), around L1 (ld.global.cg: an
+// entry is read once per centre, and L1 is what keeps the CTA's neighbour records).
+__device__ __forceinline__ Pair2<double> tab_load(const Pair2<double>* p, bool on) {
+  Pair2<double> r;
+  r.a = r.b = 0.0;
+  if (on) { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); r.a = v.x; r.b = v.y; }
+  return r;
+}
+__device__ __forceinline__ Pair2<float> tab_load(const Pair2<float>* p, bool on) {
+  Pair2<float> r;
+  r.a = r.b = 0.0f;
+  if (on) { const float2 v = __ldcg(reinterpret_cast<const float2*>(p)); r.a = v.x; r.b = v.y; }
+  return r;
 }
 
 __device__ __forceinline__ float bcast(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(32 * kMaxnWarps) system_atm_maxn_kernel(SysArg
 }
 
 // Pair table of the TAB variant: entry [j][k] (k > j; the blocks on the diagonal are written completely) =
-//   { sqrt(|C6_jk| + tiny), U_jk = (rs9 R_jk / r_jk)^p, 1 / r_jk, (dC6_jk/dCN_j) / C6_jk, (dC6_jk/dCN_k) / C6_jk, - }
+//   { sqrt(|C6_jk| + tiny), U_jk = (rs9 R_jk / r_jk)^p, (dC6_jk/dCN_j) / C6_jk, (dC6_jk/dCN_k) / C6_jk }
 // with C6_jk = sum_a w_k[a] T_j[e_k][a] in the summation order of the sweep (damping/atm.py:93-100, model/c6.py:81-87).
 // One CTA per (128 columns k, 32 rows j); a thread owns a column, the T / Td vectors of the rows sit in shared memory.
 constexpr int kPairTabCols = 128, kPairTabRows = 32;
@@ -225,8 +246,7 @@ __global__ void __launch_bounds__(kPairTabCols) system_atm_pairtab_kernel(AtmArg
     Pair2<S>* out = reinterpret_cast<Pair2<S>*>(tab + ((size_t)(j0 + jj) * natoms + k) * kAtm3Tab);
     Pair2<S> q;
     q.a = x * frsq(x); q.b = U; out[0] = q;
-    q.a = rinv; q.b = dj * ic; out[1] = q;
-    q.a = dk * ic; q.b = S(0); out[2] = q;
+    q.a = dj * ic; q.b = dk * ic; out[1] = q;
   }
 }
 
@@ -331,10 +351,9 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
       q.a = sqr(ab(c6) + tiny); q.b = r2; r[2] = q;
       q.a = frcp(r2); q.b = d_i * ic6; r[3] = q;
       if (TAB) {
-        // edge factors of the damping power and of 1/(r_ij r_ik r_jk)
-        const S rinv = frsq(r2);
-        q.a = d_n * ic6; q.b = atm_edge_pow<S>((P.rs9 * rv[ei * E + en]) * rinv, P.pexp, P.cube_root_pow); r[4] = q;
-        q.a = A.aux[nn].b; q.b = rinv; r[5] = q;
+        // edge factor of the damping power
+        q.a = d_n * ic6; q.b = atm_edge_pow<S>((P.rs9 * rv[ei * E + en]) * frsq(r2), P.pexp, P.cube_root_pow); r[4] = q;
+        q.a = A.aux[nn].b; q.b = S(0); r[5] = q;
       } else {
         q.a = d_n * ic6; q.b = rv[ei * E + en]; r[4] = q;
         q.a = A.aux[nn].b; q.b = int_as(en, S(0)); r[5] = q;
@@ -357,7 +376,6 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
       bool kvalid[KPL];
       const Pair2<S>* rk[KPL];
       S akx[KPL], aky[KPL], akz[KPL], hik[KPL], b2[KPL], inv_b[KPL], Rik[KPL], gk[KPL];   // Rik: TAB: U_ik
-      S rinvk[KPL];                                                                        // TAB: 1 / r_ik
       unsigned ekoff[KPL];       // !TAB: offset of T_j[e_k]; TAB: offset of column k in a table row
       const S* rvk[KPL];
       S Sfb[KPL], Swe[KPL], Ek[KPL], Vx[KPL], Vy[KPL], Vz[KPL], Dk[KPL];
@@ -371,7 +389,6 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
         akx[kk] = k0_.a; aky[kk] = k0_.b; akz[kk] = rk[kk][1].a;
         hik[kk] = k2_.a; b2[kk] = k2_.b; inv_b[kk] = rk[kk][3].a; Rik[kk] = rk[kk][4].b; gk[kk] = rk[kk][5].a;
         const int kidx = as_int(rk[kk][1].b), ek = TAB ? 0 : as_int(rk[kk][5].b);
-        rinvk[kk] = TAB ? rk[kk][5].b : S(0);
         if (!TAB) {
 #pragma unroll
           for (int a = 0; a < kNRef; ++a) {
@@ -388,6 +405,10 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
       const Pair2<S>* rj = reinterpret_cast<const Pair2<S>*>(rec);
       for (int jpos = 0; jpos < jend; ++jpos, rj += kAtm3Rec / 2) {
         const Pair2<S> j0_ = rj[0], j1_ = rj[1];         // warp-uniform loads
+#if D3_ATM3_JEARLY
+        // the rest of the record with them (skipped steps are rare), so that its latency overlaps the distances
+        const Pair2<S> j2_ = rj[2], j3_ = rj[3], j4_ = rj[4], j5_ = rj[5];
+#endif
         const int jidx = as_int(j1_.b);
         S dxjk[KPL], dyjk[KPL], dzjk[KPL], c2e[KPL];
         bool mjk[KPL], act[KPL];
@@ -401,13 +422,27 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
           act[kk] = kvalid[kk] && kpos[kk] > jpos && (!mjk[kk] || jidx > i);
           any_act = any_act || act[kk];
         }
+        // TAB: {sqrt|C6_jk|, U_jk}, {dlnC6/dCN_j, dlnC6/dCN_k} of the counted triples (zeros elsewhere), requested
+        // at the top of the step, before the vote: a whole dependency chain ahead of their first use (inside the
+        // per-triple code the scheduler sank them to ~90 instructions before the use: 43.5 -> 39.0 ms)
+        Pair2<S> tb0[KPL], tb1[KPL];
+        if (TAB) {
+          const S* tabrow = Q.tab + (size_t)jidx * natoms * kAtm3Tab;
+#pragma unroll
+          for (int kk = 0; kk < KPL; ++kk) {
+            const Pair2<S>* tp = reinterpret_cast<const Pair2<S>*>(tabrow + ekoff[kk]);
+            tb0[kk] = tab_load(tp, act[kk]);
+            if (WANT_G) tb1[kk] = tab_load(tp + 1, act[kk]);
+          }
+        }
         if (!__any_sync(0xffffffffu, any_act)) continue;
+#if !D3_ATM3_JEARLY
         const Pair2<S> j2_ = rj[2], j3_ = rj[3], j4_ = rj[4], j5_ = rj[5];
+#endif
         const S hij = j2_.a, a2 = j2_.b, inv_a = j3_.a;
         const int ej = TAB ? 0 : as_int(j5_.b);
         const unsigned jbase = (unsigned)jidx * (unsigned)E * 8u;
-        const S* tabrow = TAB ? Q.tab + (size_t)jidx * natoms * kAtm3Tab : nullptr;
-        const S r0j = rs93 * j4_.b;                      // TAB: j4_.b = U_ij, j5_.b = 1 / r_ij
+        const S r0j = rs93 * j4_.b;                      // TAB: j4_.b = U_ij
         S vals[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) vals[v] = S(0);
@@ -418,15 +453,10 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
           const S* Tjp = tvec + (jbase + ekoff[kk]);
           S Tj[8];
           S c6jk = S(0), hjk;
-          Pair2<S> t0, t1, t2;                           // TAB: {sqrt|C6_jk|, U_jk}, {1/r_jk, dlnC6/dCN_j}, {dlnC6/dCN_k, -}
+          Pair2<S> t0, t1;
           if (TAB) {
-            t0.a = t0.b = t1.a = t1.b = t2.a = t2.b = S(0);
-            if (act[kk]) {
-              const Pair2<S>* tp = reinterpret_cast<const Pair2<S>*>(tabrow + ekoff[kk]);
-              t0 = tp[0];
-              t1 = tp[1];
-              if (WANT_G) t2 = tp[2];
-            }
+            t0 = tb0[kk];
+            if (WANT_G) t1 = tb1[kk];
             hjk = t0.a;
           } else {
             const Pair2<S>* Tj2 = reinterpret_cast<const Pair2<S>*>(Tjp);
@@ -441,14 +471,13 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
           const S c9 = P.s9 * (hij * (hik[kk] * hjk));
           const S c2 = c2e[kk] + tiny;
           const S ab2 = a2 * b2[kk];
-          S r1inv, u;
+          const S r1inv = frsq(ab2 * c2);
+          S u;
           if (TAB) {
-            // inactive lanes: zeros from the table -> r1inv = u = 0, fd = 1, everything selected away below
-            r1inv = (j5_.b * rinvk[kk]) * t1.a;
+            // inactive lanes: zeros from the table -> u = 0, fd = 1, everything selected away below
             u = (j4_.b * Rik[kk]) * t0.b;
           } else {
             const S r0 = r0j * (Rik[kk] * rvk[kk][ej * E]);
-            r1inv = frsq(ab2 * c2);
             u = atm_edge_pow<S>(r0 * r1inv, P.pexp, P.cube_root_pow);
           }
           const S r1inv2 = r1inv * r1inv;
@@ -484,8 +513,8 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
             vals[1 % NV] += fa; vals[2 % NV] += we; vals[3 % NV] += vx; vals[4 % NV] += vy; vals[5 % NV] += vz;
             if (TAB) {
               // inactive lanes: we == 0 and the table values are zeros (not loaded)
-              Dk[kk] += we * t2.a;
-              vals[6 % NV] += we * t1.b;
+              Dk[kk] += we * t1.b;
+              vals[6 % NV] += we * t1.a;
             } else {
               const Pair2<S>* Td2 = reinterpret_cast<const Pair2<S>*>(Tjp + tdoff);
               S Td[8];
