@@ -296,6 +296,11 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
   const S cutoff2 = A.cutoff2;
 
   for (int k = tid; k < E * E; k += blockDim.x) rv[k] = P.rvdw_e[k];
+  // j side of a step: what lane 0..4 adds (row of the reduced sums, factor, target, stride)
+  const int jsrc = lane == 0 ? 0 : (lane == 4 ? 24 : 4 * (2 + (lane & 3)));
+  const S jk1 = lane == 0 ? sixth : (lane == 4 ? half6 : two6);
+  S* const jptr = lane == 0 ? A.energy : (lane == 4 ? A.decn : A.grad + ((lane - 1) & 3));
+  const int jmul = (lane >= 1 && lane <= 3) ? 3 : 1;
 
   for (;;) {
     __syncthreads();                       // previous centre completely finished (list, wiS, isum reusable)
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
             if (TAB) {
               // inactive lanes: we == 0 and the table values are zeros (not loaded)
               Dk[kk] += we * t1.b;
-              vals[6 % NV] += we * t1.a;
+              vals[6 % NV] += we * (t1.a + j4_.a);       // + dlnC6_ij/dCN_j: the whole dE/dCN_j of the step
             } else {
               const Pair2<S>* Td2 = reinterpret_cast<const Pair2<S>*>(Tjp + tdoff);
               S Td[8];
@@ -539,26 +544,26 @@ __global__ void __launch_bounds__(32 * kAtm3Warps, TAB ? kAtm3TabCtas : kAtm3Cta
               for (int a = 1; a < kNRef; ++a) { dk += wsh[wid][kk][kNRef + a][lane] * Tj[a]; dj += wsh[wid][kk][a][lane] * Td[a]; }
               const S qc = act[kk] ? we * rcp0(c6jk) : S(0);
               Dk[kk] += qc * dk;
-              vals[6 % NV] += qc * dj;
+              vals[6 % NV] += qc * dj + we * j4_.a;
             }
           }
         }
         // ---- j side of this step: sums over the 32 lanes, five atomics
         const S tot = warp_rows_reduce<NV, S>(vals, redw, lane);
-        const S EJ = bcast(tot, 0);
         if (WANT_G) {
-          const S FA = bcast(tot, 4), WE = bcast(tot, 8), DJ = bcast(tot, 24);
-          // lanes 1..3 fetch V_x, V_y, V_z (rows 3..5); branch-free selects
-          const S VC = bcast(tot, 4 * (2 + (lane & 3)));
+          // lanes 0..4 add one sum each -- E_j, dE/dx_j, dE/dy_j, dE/dz_j, dE/dCN_j -- through ONE branch-free
+          // formula k (X - FA dc): source row, factor, target array and stride are per-lane constants
+          // (ternaries over the lane index compiled to ten branches per step: 0.62 stall cycles per issue on
+          // branch resolving, profiles/r2_atm3_tab_raw.csv)
+          const S FA = bcast(tot, 4), WE = bcast(tot, 8);
+          const S X = bcast(tot, jsrc);
           const S dxij = ai.x - j0_.a, dyij = ai.y - j0_.b, dzij = ai.z - j1_.a;
-          const S dc = lane == 1 ? dxij : (lane == 2 ? dyij : dzij);
-          const S gv = two6 * (VC - FA * dc);
-          const S dv_ = half6 * (WE * j4_.a + DJ);
-          const S out = lane == 0 ? sixth * EJ : (lane == 4 ? dv_ : gv);
-          S* addr = lane == 0 ? A.energy + jidx : (lane == 4 ? A.decn + jidx : A.grad + 3 * (size_t)jidx + (lane - 1));
+          const S dc = lane == 1 ? dxij : (lane == 2 ? dyij : (lane == 3 ? dzij : S(0)));
+          const S out = jk1 * (X - FA * dc);
           if (lane == 0) { Gix += FA * dxij; Giy += FA * dyij; Giz += FA * dzij; Di += WE * j3_.b; }
-          if (lane < 5) red_add(addr, out);
+          if (lane < 5) red_add(jptr + (size_t)jidx * jmul, out);
         } else {
+          const S EJ = bcast(tot, 0);
           if (lane == 0) red_add(A.energy + jidx, sixth * EJ);
         }
       }
