@@ -350,7 +350,12 @@ int d3b200_system_cnbwd_f32(const d3b200_system_f32* sys, const d3b200_params* p
  * the 32-atom sub-tiles row_begin/32 + k*tile_stride below row_end (row range
  * aligned to 32; tile_stride 0 or 1: the whole range), or, with tile_stride < 0, the
  * single atoms row_begin + k*|tile_stride| below row_end (any row_begin), which is how
- * ranks shard the term: dealt atom by atom the ranks' costs differ by well under 1 %. */
+ * ranks shard the term: dealt atom by atom the ranks' costs differ by well under 1 %.
+ * `_workspace_bytes_` includes, while it stays below $D3B200_ATM_PAIRTAB_MAX_BYTES (default
+ * 8 GiB; 0 = never), a dense pair table of 4 reals per atom pair (32 natoms^2 bytes in fp64)
+ * that the launch fills itself: everything of a triple that depends on one edge alone is then
+ * computed once per pair instead of once per triple.  A smaller `atm_work` (at least the
+ * neighbour scratch) selects the table-free sweep; the results agree to rounding. */
 size_t d3b200_system_atm_workspace_bytes_f64(int natoms);
 size_t d3b200_system_atm_workspace_bytes_f32(int natoms);
 int d3b200_system_atm_f64(const d3b200_system_f64* sys, const d3b200_params* par,
