@@ -367,6 +367,27 @@ def test_tiled_atm_reference_runs(runs, case, force_tiled):
         assert_close(out["grad"], c["grad"], RTOL, ATOL, case + " grad")
 
 
+@pytest.mark.parametrize("case", ["c2_atm_f64", "mols6_atm_cut12_f64", "water64_cut20_atm_f64", "c2_atm_f32",
+                                  "water100_atm_cut18_f64"])
+def test_tiled_atm_without_pair_table(runs, case, force_tiled, monkeypatch):
+    """Structures whose pair table would exceed $D3B200_ATM_PAIRTAB_MAX_BYTES (32 N^2 bytes: beyond ~16 k atoms at the
+    default cap) run the table-free sweep, which contracts C6_jk per triple: same fixtures with the table switched
+    off, against the reference and against the table variant."""
+    c = runs.case(case)
+    dtype, numbers, positions, g, param, cutoff = case_inputs(c)
+    with_table = run_cuda(numbers, positions, param, cutoff, dtype, g=g, rvdw_table=True)
+    monkeypatch.setenv("D3B200_ATM_PAIRTAB_MAX_BYTES", "0")
+    out = run_cuda(numbers, positions, param, cutoff, dtype, g=g, rvdw_table=True)
+    if dtype == torch.float32:
+        assert_close(out["energy"], c["energy"], 5e-4, 1e-8, case + " energy")
+        assert_close(out["energy"], with_table["energy"], 1e-4, 1e-9, case + " energy, table-free vs table")
+    else:
+        assert_close(out["energy"], c["energy"], RTOL, ATOL, case + " energy")
+        assert_close(out["grad"], c["grad"], RTOL, ATOL, case + " grad")
+        assert_close(out["energy"], with_table["energy"], RTOL, ATOL, case + " energy, table-free vs table")
+        assert_close(out["grad"], with_table["grad"], RTOL, ATOL, case + " grad, table-free vs table")
+
+
 def test_rvdw_table_equals_dense(runs):
     """rvdw=None with a registered element-pair table == dense per-pair rvdw (fused kernel)."""
     c = runs.case("mols6_atm_f64")
