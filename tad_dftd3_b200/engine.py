@@ -194,12 +194,16 @@ _engines: dict = {}
 
 
 def shutdown() -> None:
-    """Release every cached engine (graphs first).  Call before `dist.destroy_process_group()`."""
+    """Release every cached engine (graphs first) and the cached ATM workspaces (neighbour scratch + pair table:
+    32 N^2 bytes per device and stream).  Call before `dist.destroy_process_group()`."""
     import gc
+
+    from . import system as _system
 
     for _, eng in list(_engines.values()):
         eng.release_graph()
     _engines.clear()
+    _system._atm_work_cache.clear()
     gc.collect()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
