@@ -256,3 +256,26 @@ def test_check_memory_contract(monkeypatch):
         c6._check_memory(torch.zeros(10000, dtype=torch.double), x)
     monkeypatch.undo()
     c6._check_memory(torch.zeros(10, dtype=torch.int64), torch.zeros(10, 7))     # plenty of memory: silent
+
+
+def test_atm_workspace_holds_the_pair_table_up_to_the_cap(lib, monkeypatch):
+    """`d3b200_system_atm_workspace_bytes_*` = neighbour scratch + the dense pair table of the ATM sweep
+    (4 reals per atom pair) while the table stays below $D3B200_ATM_PAIRTAB_MAX_BYTES (d3b200.h); no CUDA call."""
+    n = 1024
+    monkeypatch.setenv("D3B200_ATM_PAIRTAB_MAX_BYTES", "0")
+    scratch64 = lib.d3b200_system_atm_workspace_bytes_f64(n)
+    scratch32 = lib.d3b200_system_atm_workspace_bytes_f32(n)
+    assert scratch64 > 0 and scratch64 % 256 == 0 and scratch32 < scratch64
+    monkeypatch.delenv("D3B200_ATM_PAIRTAB_MAX_BYTES")
+    assert lib.d3b200_system_atm_workspace_bytes_f64(n) == scratch64 + 32 * n * n
+    assert lib.d3b200_system_atm_workspace_bytes_f32(n) == scratch32 + 16 * n * n
+    # just below / at the cap
+    monkeypatch.setenv("D3B200_ATM_PAIRTAB_MAX_BYTES", str(32 * n * n - 1))
+    assert lib.d3b200_system_atm_workspace_bytes_f64(n) == scratch64
+    monkeypatch.setenv("D3B200_ATM_PAIRTAB_MAX_BYTES", str(32 * n * n))
+    assert lib.d3b200_system_atm_workspace_bytes_f64(n) == scratch64 + 32 * n * n
+    # default cap 8 GiB: 16 k atoms get the table, 50 k atoms do not
+    monkeypatch.delenv("D3B200_ATM_PAIRTAB_MAX_BYTES")
+    big = 50048
+    assert lib.d3b200_system_atm_workspace_bytes_f64(big) < 32 * big * big
+    assert lib.d3b200_system_atm_workspace_bytes_f64(0) == 0
