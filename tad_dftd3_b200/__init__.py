@@ -11,15 +11,16 @@ parameter dicts as the reference; the body runs as hand-written sm_100a CUDA
 kernels behind the C ABI in `include/d3b200.h`, with analytic first and second
 derivatives wired into torch autograd / torch.func.
 """
-from . import damping, data, defaults, disp, exception, model, ncoord, reference, typing
+from . import damping, data, defaults, disp, exception, model, ncoord, periodic, reference, typing
 from .disp import dftd3, hessian
+from .periodic import dftd3_periodic
 from .host import HostPipeline, bind_host_thread_to_gpu, dftd3_host
 from .reference import Reference
 
 from .__version__ import __version__
 
 __all__ = [
-    "dftd3", "hessian", "dftd3_host", "HostPipeline", "bind_host_thread_to_gpu", "damping", "data", "defaults", "disp", "exception",
+    "dftd3", "hessian", "dftd3_periodic", "periodic", "dftd3_host", "HostPipeline", "bind_host_thread_to_gpu", "damping", "data", "defaults", "disp", "exception",
     "model", "ncoord", "reference", "typing",
     "Reference", "__version__",
 ]
