@@ -235,3 +235,40 @@ def test_periodic_product_path_matches_oracle(cutoff, atm):
     assert_close(e1.detach().cpu(), e0.detach(), 1e-10, 1e-12, "periodic energies")
     assert_close(gx1.cpu(), gx0, 1e-10, 1e-12, "periodic dE/dpositions")
     assert_close(gc1.cpu(), gc0, 1e-10, 1e-12, "periodic dE/dcell")
+
+
+def test_image_list_reuse_and_per_atom_arguments():
+    """An image list built with some slack on the radius serves displaced positions (MD / optimisation steps);
+    per-atom `rcov` / `r4r2` and a dense `rvdw` of the cell are expanded to the images."""
+    from tad_dftd3_b200.periodic import _gather, dftd3_periodic, image_radius, lattice_images
+
+    numbers, positions, cell = water_cell(4)
+    fn = blocked_evaluator()
+    cutoff = 9.3
+    images = lattice_images(numbers, positions, cell, image_radius(cutoff, False) + 0.5)
+    g = torch.Generator().manual_seed(7)
+    moved = positions + 0.1 * (torch.rand(positions.shape, generator=g, dtype=DT) - 0.5)      # |dx| < 0.09 Bohr
+    e_reuse = dftd3_periodic(numbers, moved, cell, PARAM, cutoff=cutoff, images=images, _energy_fn=fn)
+    e_fresh = dftd3_periodic(numbers, moved, cell, PARAM, cutoff=cutoff, _energy_fn=fn)
+    assert_close(e_reuse, e_fresh, 1e-12, 1e-16, "reused image list")
+    assert images[0].shape[0] > lattice_images(numbers, moved, cell, image_radius(cutoff, False))[0].shape[0]
+
+    index = images[0]
+    n = numbers.shape[0]
+    per_atom = torch.arange(n, dtype=DT)
+    assert torch.equal(_gather(per_atom, index, n), per_atom[index])
+    dense = torch.arange(n * n, dtype=DT).reshape(n, n)
+    got = _gather(dense, index, n)
+    assert got.shape == (index.shape[0], index.shape[0]) and torch.equal(got[7, 11], dense[index[7], index[11]])
+    table = torch.zeros(104, 104, dtype=DT)
+    assert _gather(table, index, n) is table and _gather(None, index, n) is None
+    seen = {}
+
+    def spy(z, x, param, **kw):
+        seen.update(kw)
+        return torch.zeros(z.shape[0], dtype=DT)
+
+    dftd3_periodic(numbers, positions, cell, PARAM, cutoff=cutoff, images=images, rcov=per_atom, r4r2=per_atom + 1,
+                   rvdw=dense, _energy_fn=spy)
+    assert torch.equal(seen["rcov"], per_atom[index]) and torch.equal(seen["r4r2"], per_atom[index] + 1)
+    assert seen["rvdw"].shape == (index.shape[0],) * 2
