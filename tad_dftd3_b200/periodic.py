@@ -97,7 +97,7 @@ def lattice_images(numbers: Tensor, positions: Tensor, cell: Tensor, radius: flo
             continue
         q = p[ti, ai]                                            # [C, 3]
         ok = torch.zeros(q.shape[0], dtype=torch.bool, device=dev)
-        cstep = max(1, int(2.0e7 // max(1, xr.shape[0])))
+        cstep = max(1, int(4.0e6 // max(1, xr.shape[0])))           # [cstep, R, 3] doubles: <= 96 MB
         for c0 in range(0, q.shape[0], cstep):
             qq = q[c0:c0 + cstep]
             d2 = ((qq.unsqueeze(1) - xr.unsqueeze(0)) ** 2).sum(-1)   # exact differences (no |x|^2 expansion)
